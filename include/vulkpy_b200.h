@@ -1,0 +1,151 @@
+/* vulkpy_b200.h -- C ABI of the B200 backend that replaces vulkpy's Vulkan layer.
+ *
+ * Drop-in boundary: this header replaces the pybind11 module `vulkpy._vkarray`
+ * (reference vulkpy/_vkarray.cc:756-898).  Every entry point names the reference
+ * interface it stands in for.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message of the
+ *     last failure on the calling thread is returned by vkp_last_error()
+ *     (reference: C++ exceptions -> Python RuntimeError, _vkarray.cc:32,286,446-456,508,752).
+ *   - all work is enqueued on ONE in-order CUDA stream per context, so read-after-write,
+ *     write-after-read and write-after-write hazards between submitted ops are ordered by
+ *     construction (the reference host-blocks on every dependency: _vkarray.cc:430-432).
+ *   - sizes that cross the reference boundary are uint32 (_vkarray.cc:132-203); the
+ *     parameter structs below keep that layout bit-for-bit.  Kernels index with 64 bits.
+ *   - buffers are CUDA managed allocations: the returned pointer is valid on the host
+ *     (NumPy view, reference _vkarray.cc:61-72,805-814) and on the device.
+ */
+#ifndef VULKPY_B200_H
+#define VULKPY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VKP_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VKP_API __attribute__((visibility("default")))
+#else
+#define VKP_API
+#endif
+
+typedef struct vkp_ctx vkp_ctx;     /* replaces class GPU        (_vkarray.cc:460-574) */
+typedef struct vkp_job vkp_job;     /* replaces class Job        (_vkarray.cc:392-457) */
+typedef struct vkp_rng vkp_rng;     /* replaces PRNG::Xoshiro128pp (_vkarray.cc:577-719) */
+typedef struct vkp_timer vkp_timer; /* CUDA event on the context stream (measurement only) */
+
+/* ---- error / introspection ------------------------------------------------------- */
+VKP_API int         vkp_abi_version(void);
+VKP_API const char* vkp_last_error(void);
+VKP_API int         vkp_device_count(int* count);
+
+/* ---- context: createGPU(n, priority) (_vkarray.cc:759-763), GPU::wait (:560-562) -- */
+VKP_API int vkp_ctx_create(int device, float priority, vkp_ctx** out);
+VKP_API int vkp_ctx_destroy(vkp_ctx* ctx);
+VKP_API int vkp_ctx_sync(vkp_ctx* ctx);                          /* GPU.wait()                  */
+VKP_API int vkp_ctx_device(vkp_ctx* ctx, int* device);
+VKP_API int vkp_ctx_sm_count(vkp_ctx* ctx, int* sms);
+VKP_API int vkp_ctx_set_debug_sync(vkp_ctx* ctx, int enable);    /* util.enable_debug analogue  */
+VKP_API int vkp_ctx_launch_count(vkp_ctx* ctx, uint64_t* kernels);/* kernels launched so far    */
+VKP_API int vkp_ctx_mem_info(vkp_ctx* ctx, size_t* pooled_bytes, size_t* live_bytes);
+VKP_API int vkp_ctx_trim(vkp_ctx* ctx);                          /* give cached blocks back     */
+
+/* ---- buffers: GPU::createBuffer<T>/toBuffer<T> (_vkarray.cc:512-525), Buffer<T> (:38-130) */
+VKP_API int vkp_alloc(vkp_ctx* ctx, size_t bytes, void** ptr);
+VKP_API int vkp_free(vkp_ctx* ctx, void* ptr);
+/* stream-ordered host->buffer / buffer->host copies (Buffer::set, _vkarray.cc:98-108) */
+VKP_API int vkp_upload(vkp_ctx* ctx, void* dst, const void* src_host, size_t bytes);
+VKP_API int vkp_download(vkp_ctx* ctx, void* dst_host, const void* src, size_t bytes);
+/* Call before the host touches `ptr` through its NumPy view.  Makes sure no earlier
+ * user of a recycled block is still in flight and (prefetch!=0) migrates the pages to
+ * host memory in one bulk transfer instead of page faults. */
+VKP_API int vkp_host_acquire(vkp_ctx* ctx, void* ptr, size_t bytes, int prefetch);
+/* pinned host staging memory for callers that want full-rate PCIe copies */
+VKP_API int vkp_host_alloc(size_t bytes, void** ptr);
+VKP_API int vkp_host_free(void* ptr);
+
+/* ---- parameter blocks: namespace OpParams (_vkarray.cc:132-203), same field order -- */
+typedef struct { uint32_t size; }                                   vkp_vector_params;        /* Vector            */
+typedef struct { uint32_t size[2]; }                                vkp_multivector2_params;  /* MultiVector<2>    */
+typedef struct { uint32_t shift, size; }                            vkp_shiftvector_params;   /* ShiftVector       */
+typedef struct { uint32_t size, low, high; }                        vkp_vectorrange_params;   /* VectorRange       */
+typedef struct { uint32_t size; float scalar; }                     vkp_vectorscalar_params;  /* VectorScalar<f32> */
+typedef struct { uint32_t size; float scalar[2]; }                  vkp_vectorscalar2_params; /* VectorMultiScalar<f32,2> */
+typedef struct { uint32_t rowA, contractSize, columnB; }            vkp_matmul_params;        /* MatMul            */
+typedef struct { uint32_t batch_size, input_size, output_size; }    vkp_batchaffine_params;   /* BatchAffine       */
+typedef struct { uint32_t prev_prod, axis_size, post_prod; }        vkp_axisreduction_params; /* AxisReduction     */
+typedef struct { uint32_t size[2]; uint32_t ndim; }                 vkp_broadcast_params;     /* Broadcast         */
+typedef struct { uint32_t size[3]; uint32_t ndim; }                 vkp_multi3broadcast_params;/* MultiBroadcast<3>*/
+typedef struct { uint32_t prev_prod, post_prod, axis_size, index_size; } vkp_axisgather_params;/* AxisGather       */
+
+/* ---- ops: GPU::submit(spv, x,y,z, infos, DataShape, Params, wait) (_vkarray.cc:527-548)
+ * The kernel is named by the reference shader's base name ("add", "iadd_scalar",
+ * "sum_axis_rebroadcast", "sum_v1.3", ... the 121 files of vulkpy/shader/ and setup.py:11-48);
+ * vkp_op_id() turns the name into the integer id vkp_submit() takes (-1 if unknown).
+ * `bufs` are the bindings in the shader's binding order; `params` is the matching struct
+ * above.  Shape bindings of the broadcast family (add_broadcast.comp binding 3,
+ * iadd_broadcast.comp binding 2, broadcast.comp bindings 2 and 3) are read on the HOST
+ * at submit time (they are tiny and produced by the host), every other binding is a
+ * buffer from vkp_alloc.  The workgroup/DataShape arguments of the reference are not
+ * needed: grids are derived from `params`.  *job receives a waitable handle (may be NULL). */
+VKP_API int vkp_op_id(const char* name);
+VKP_API const char* vkp_op_name(int op);
+VKP_API int vkp_op_count(void);
+VKP_API int vkp_submit(vkp_ctx* ctx, int op, void* const* bufs, int nbuf,
+               const void* params, size_t params_bytes, vkp_job** job);
+
+/* extra device-side utilities with no shader counterpart in the reference */
+VKP_API int vkp_fill_u32(vkp_ctx* ctx, void* dst, size_t count, uint32_t bits, vkp_job** job); /* `a[:] = v` host fills: vkarray.py:1540-1542, nn/parameters.py:81-86 */
+
+/* General fp32 GEMM behind "matmul"/"batch_affine": C[M,N] = op(A)·op(B) (+ bias[N]).
+ * transA=0: A is [M,K] row-major, 1: A is [K,M].  transB=0: B is [K,N], 1: B is [N,K].
+ * Used for Dense.backward (nn/layers.py:104-141) where the reference materialises
+ * a B x out x in temporary instead.  flags: VKP_GEMM_* */
+#define VKP_GEMM_AUTO      0   /* tcgen05 3xTF32 when the shape allows, SIMT otherwise */
+#define VKP_GEMM_FORCE_SIMT 1
+#define VKP_GEMM_FORCE_TC   2
+#define VKP_GEMM_ACCUMULATE 4  /* C += instead of C = */
+VKP_API int vkp_gemm(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K,
+             const float* A, const float* B, float* C, const float* bias, int flags,
+             vkp_job** job);
+
+/* ---- jobs: Job::wait (_vkarray.cc:446-456, :876-879) ------------------------------ */
+VKP_API int vkp_job_wait(vkp_job* job, uint64_t timeout_ns);   /* timeout_ns==UINT64_MAX: forever; 2 = timeout */
+VKP_API int vkp_job_done(vkp_job* job, int* done);
+VKP_API int vkp_job_release(vkp_job* job);
+
+/* ---- PRNG: Xoshiro128pp(gpu, spv_u32, spv_f32, size[, seed]) (_vkarray.cc:643-679),
+ *      random_uint32 / random_float (:681-717).  Bit-exact stream and state layout. ---- */
+VKP_API int vkp_rng_create(vkp_ctx* ctx, uint32_t size, uint64_t seed, int has_seed, vkp_rng** out);
+VKP_API int vkp_rng_destroy(vkp_rng* rng);
+VKP_API int vkp_rng_uint32(vkp_rng* rng, uint32_t* out, uint32_t n, vkp_job** job);
+VKP_API int vkp_rng_float(vkp_rng* rng, float* out, uint32_t n, vkp_job** job);
+/* fused uniform -> Box-Muller (random.py:60-124 + prng_box_muller.comp / prng_ibox_muller.comp):
+ * consumes n (even) or n+1 (odd) uniforms exactly like the reference */
+VKP_API int vkp_rng_normal(vkp_rng* rng, float* out, uint32_t n, float mean, float stddev, vkp_job** job);
+VKP_API int vkp_rng_state(vkp_rng* rng, uint32_t* host_out /* 4*size words */);
+
+/* ---- timing on the context stream (bench only) ------------------------------------ */
+VKP_API int vkp_timer_create(vkp_ctx* ctx, vkp_timer** out);
+VKP_API int vkp_timer_record(vkp_timer* t);
+VKP_API int vkp_timer_elapsed_ms(vkp_timer* start, vkp_timer* stop, float* ms); /* syncs on stop */
+VKP_API int vkp_timer_destroy(vkp_timer* t);
+
+/* ---- multi-GPU (additive; the reference has no multi-device surface) -------------- */
+#define VKP_COMM_ID_BYTES 128
+VKP_API int vkp_comm_unique_id(void* id_out /* VKP_COMM_ID_BYTES */);
+VKP_API int vkp_comm_init(vkp_ctx* ctx, int nranks, int rank, const void* id);
+VKP_API int vkp_comm_destroy(vkp_ctx* ctx);
+/* op: 0 sum, 1 prod, 2 max, 3 min (the four reductions of vkarray.py:1278-1396) */
+VKP_API int vkp_comm_allreduce(vkp_ctx* ctx, const float* send, float* recv, size_t count, int op, vkp_job** job);
+VKP_API int vkp_comm_allgather(vkp_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank, vkp_job** job);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VULKPY_B200_H */

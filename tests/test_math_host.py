@@ -1,0 +1,113 @@
+"""vkp_math.cuh compiled for the HOST (it is __host__ __device__): exp/exp2/log/log2/pow are the
+same code the kernels run, so their accuracy is verified here, on the CPU, against float64."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = """
+#include "vkp_math.cuh"
+extern "C" {
+void h_exp(const float* x, float* y, long n){ for(long i=0;i<n;i++) y[i]=vkpm::exp_f(x[i]); }
+void h_exp2(const float* x, float* y, long n){ for(long i=0;i<n;i++) y[i]=vkpm::exp2_f(x[i]); }
+void h_log(const float* x, float* y, long n){ for(long i=0;i<n;i++) y[i]=vkpm::log_f(x[i]); }
+void h_log2(const float* x, float* y, long n){ for(long i=0;i<n;i++) y[i]=vkpm::log2_f(x[i]); }
+void h_pow(const float* x, const float* y, float* z, long n){ for(long i=0;i<n;i++) z[i]=vkpm::pow_f(x[i],y[i]); }
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def hm(tmp_path_factory):
+    d = tmp_path_factory.mktemp("hostmath")
+    src = d / "h.cpp"
+    src.write_text(SRC)
+    so = d / "h.so"
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I",
+                    os.path.join(ROOT, "vulkpy_b200", "csrc"), "-o", str(so), str(src)], check=True)
+    return C.CDLL(str(so))
+
+
+def call1(lib, name, x):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.empty_like(x)
+    getattr(lib, name)(C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), C.c_long(x.size))
+    return y
+
+
+def call2(lib, x, y):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    z = np.empty_like(x)
+    lib.h_pow(C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), C.c_void_p(z.ctypes.data), C.c_long(x.size))
+    return z
+
+
+def ulps(got, exact):
+    with np.errstate(all="ignore"):
+        r32 = exact.astype(np.float32)
+    return np.abs(got.astype(np.float64) - exact) / np.spacing(np.abs(r32)).astype(np.float64)
+
+
+def bits(v):
+    return [hex(int(b)) for b in np.asarray(v, dtype=np.float32).view(np.uint32)]
+
+
+def test_appendix_a_points(hm):
+    """correctly rounded results the reference's rtol=1e-7 tests need."""
+    x = [1, 2, 3]
+    assert bits(call1(hm, "h_exp", x)) == ["0x402df854", "0x40ec7326", "0x41a0af2e"]
+    assert bits(call1(hm, "h_log", x)) == ["0x0", "0x3f317218", "0x3f8c9f54"]
+    assert list(call1(hm, "h_exp2", x)) == [2.0, 4.0, 8.0]
+    assert bits(call1(hm, "h_log2", x)) == ["0x0", "0x3f800000", "0x3fcae00d"]
+    assert bits(call2(hm, x, [1.1, 2.2, 1.4])) == ["0x3f800000", "0x4093088d", "0x4094fa28"]
+    assert bits(call2(hm, x, [2.7] * 3)) == ["0x3f800000", "0x40cfefc6", "0x419b5a2a"]
+    assert bits(call2(hm, [1.3] * 3, [1.1, 2.2, 1.4])) == ["0x3faad2d2", "0x3fe3f958", "0x3fb8cfec"]
+    assert list(call2(hm, [1, 2, 3, 4], [2, 3, 2, 3])) == [1.0, 8.0, 9.0, 64.0]
+
+
+@pytest.mark.parametrize("name,f,lo,hi", [("h_exp", np.exp, -87.0, 88.0), ("h_exp2", np.exp2, -126.0, 127.0)])
+def test_exp_accuracy(hm, name, f, lo, hi):
+    x = np.random.default_rng(0).uniform(lo, hi, 2_000_000).astype(np.float32)
+    got = call1(hm, name, x)
+    assert ulps(got, f(x.astype(np.float64))).max() < 0.5002
+
+
+@pytest.mark.parametrize("name,f", [("h_log", np.log), ("h_log2", np.log2)])
+def test_log_accuracy(hm, name, f):
+    rs = np.random.default_rng(1)
+    x = rs.integers(1, 0x7f800000, 2_000_000, dtype=np.uint32).view(np.float32)  # every positive finite float
+    assert ulps(call1(hm, name, x), f(x.astype(np.float64))).max() < 0.5002
+    x = rs.uniform(0.5, 2.0, 1_000_000).astype(np.float32)
+    e = ulps(call1(hm, name, x), f(x.astype(np.float64)))
+    assert e[np.isfinite(e)].max() < 0.5002
+
+
+def test_pow_accuracy(hm):
+    rs = np.random.default_rng(2)
+    x = rs.uniform(0.01, 100, 2_000_000).astype(np.float32)
+    y = rs.uniform(-10, 10, 2_000_000).astype(np.float32)
+    exact = np.power(x.astype(np.float64), y.astype(np.float64))
+    with np.errstate(all="ignore"):
+        ok = np.isfinite(exact.astype(np.float32)) & (exact.astype(np.float32) != 0)
+    assert ulps(call2(hm, x, y)[ok], exact[ok]).max() < 0.5002
+
+
+def test_special_values(hm):
+    inf, nan = np.inf, np.nan
+    assert list(call1(hm, "h_exp", [-inf, inf, -200, 200])) == [0.0, inf, 0.0, inf]
+    assert np.isnan(call1(hm, "h_exp", [nan])[0])
+    r = call1(hm, "h_log", [0.0, -1.0, inf, 1e-45])
+    assert r[0] == -inf and np.isnan(r[1]) and r[2] == inf and abs(r[3] - np.log(1.401298464e-45)) < 1e-4
+    # C99 pow corner cases
+    got = call2(hm, [2, -2, -2, 0, -0.0, inf, -8, 2, 0.5, 7, 1, -1],
+                    [0, 3, 2, -1, -3, -1, 1 / 3, inf, inf, -inf, nan, inf])
+    want = [1, -8, 4, inf, -inf, 0, nan, inf, 0, 0, 1, 1]
+    for g, w in zip(got, want):
+        assert (np.isnan(g) and np.isnan(w)) or g == w, (got, want)
+    # subnormal results round once
+    x = np.float32([-140.5, -149.0, -126.0])
+    np.testing.assert_array_equal(call1(hm, "h_exp2", x), np.exp2(x.astype(np.float64)).astype(np.float32))

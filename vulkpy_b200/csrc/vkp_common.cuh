@@ -1,0 +1,153 @@
+// vkp_common.cuh -- shared internals of libvulkpy_b200 (context, error handling, launch helpers)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/vulkpy_b200.h"
+
+#define VKP_OK 0
+#define VKP_ERR 1
+#define VKP_TIMEOUT 2
+
+int vkp_set_error(const char* fmt, ...);
+
+#define VKP_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (call);                                                        \
+    if (_e != cudaSuccess)                                                          \
+      return vkp_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e),  \
+                           __FILE__, __LINE__);                                     \
+  } while (0)
+
+#define VKP_CHECK(cond, ...)                        \
+  do {                                              \
+    if (!(cond)) return vkp_set_error(__VA_ARGS__); \
+  } while (0)
+
+#define VKP_TRY(expr)          \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != VKP_OK) return _r; \
+  } while (0)
+
+struct vkp_block {
+  void* ptr = nullptr;
+  size_t bytes = 0;         // rounded size class
+  uint64_t guard_seq = 0;   // work submitted up to this sequence number may still touch the block
+  bool host_dirty = false;  // pages may live in host memory -> prefetch before the next kernel
+  bool in_use = false;
+};
+
+struct vkp_comm_state;  // vkp_comm.cu
+
+struct vkp_ctx {
+  int device = 0;
+  int sms = 148;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  uint64_t seq = 0;        // number of operations enqueued so far
+  uint64_t done_seq = 0;   // all operations with sequence <= done_seq are known complete
+  uint64_t kernel_launches = 0;
+  bool debug_sync = false;
+  int refcount = 1;
+  std::unordered_map<void*, vkp_block*> blocks;
+  std::unordered_map<size_t, std::vector<vkp_block*>> free_lists;
+  size_t pooled_bytes = 0, live_bytes = 0;
+  std::vector<cudaEvent_t> event_pool;
+  // device scratch: slot 0 = partials of two-pass reductions, slot 1 = reduced values awaiting
+  // re-broadcast / GEMM staging (two slots so that nested users never alias)
+  void* workspace[2] = {nullptr, nullptr};
+  size_t workspace_bytes[2] = {0, 0};
+  vkp_comm_state* comm = nullptr;
+};
+
+struct vkp_job {
+  vkp_ctx* ctx;
+  cudaEvent_t ev;
+  uint64_t seq;
+};
+
+struct vkp_timer {
+  vkp_ctx* ctx;
+  cudaEvent_t ev;
+};
+
+// ---- helpers implemented in vkp_runtime.cu ----------------------------------------
+int vkp_make_current(vkp_ctx* ctx);
+// prefetch host-dirty managed blocks that a kernel is about to touch
+int vkp_prepare_buffers(vkp_ctx* ctx, void* const* bufs, int nbuf);
+// marks one enqueued operation; records the job event if requested
+int vkp_finish_op(vkp_ctx* ctx, vkp_job** job);
+int vkp_workspace(vkp_ctx* ctx, int slot, size_t bytes, void** out);
+// call right after each <<<>>> launch
+int vkp_after_launch(vkp_ctx* ctx, const char* what);
+
+static inline unsigned vkp_grid_for(vkp_ctx* ctx, size_t work_items, unsigned per_block,
+                                    unsigned blocks_per_sm) {
+  size_t need = (work_items + per_block - 1) / per_block;
+  size_t cap = (size_t)ctx->sms * blocks_per_sm;
+  if (need < 1) need = 1;
+  return (unsigned)(need < cap ? need : cap);
+}
+
+// ---- family entry points (one per .cu file) ------------------------------------------
+int vkp_launch_elementwise(vkp_ctx* ctx, int fam, int sub, void* const* bufs, int nbuf,
+                           const void* params, size_t pbytes);
+int vkp_launch_broadcast(vkp_ctx* ctx, int fam, int sub, void* const* bufs, int nbuf,
+                         const void* params, size_t pbytes);
+int vkp_launch_reduce(vkp_ctx* ctx, int fam, int sub, void* const* bufs, int nbuf,
+                      const void* params, size_t pbytes);
+int vkp_launch_gather(vkp_ctx* ctx, int fam, int sub, void* const* bufs, int nbuf,
+                      const void* params, size_t pbytes);
+int vkp_launch_gemm(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K,
+                    const float* A, const float* B, float* C, const float* bias, int flags);
+
+// op families
+enum {
+  VKF_BIN = 0,       // c = a op b            (add.comp ...)
+  VKF_IBIN,          // a = a op b            (iadd.comp ...)
+  VKF_SCALAR,        // b = a op s / s op a   (add_scalar.comp, rsub_scalar.comp ...)
+  VKF_ISCALAR,       // a = a op s            (iadd_scalar.comp ...)
+  VKF_BCAST,         // c = a op b, NumPy broadcasting (add_broadcast.comp ...)
+  VKF_IBCAST,        // a = a op b, b broadcast (iadd_broadcast.comp ...)
+  VKF_BCAST_COPY,    // broadcast.comp
+  VKF_UNARY,         // b = f(a)              (abs.comp ...)
+  VKF_IUNARY,        // a = f(a)              (iabs.comp ...)
+  VKF_CLAMP,         // clamp*.comp, iclamp*.comp (sub = variant)
+  VKF_REDUCE,        // sum.comp / prod / maximum / minimum (MultiVector<2>)
+  VKF_REDUCE_SG,     // sum_v1.3.comp ... (Vector)
+  VKF_REDUCE_AXIS,   // sum_axis.comp ...
+  VKF_REDUCE_AXIS_RB,// sum_axis_rebroadcast.comp ...
+  VKF_GATHER,        // gather.comp
+  VKF_GATHER_AXIS,   // gather_axis.comp
+  VKF_MATMUL,        // matmul.comp
+  VKF_BATCH_AFFINE,  // batch_affine.comp
+  VKF_CE,            // nn_cross_entropy.comp
+  VKF_CE_BWD,        // nn_cross_entropy_backward.comp
+  VKF_BOX_MULLER,    // prng_box_muller.comp
+  VKF_IBOX_MULLER,   // prng_ibox_muller.comp
+  VKF_RANDRANGE,     // prng_randrange.comp
+  VKF_PRNG_U32,      // prng_xoshiro128pp_uint32.comp (bufs[0] = state, one draw per lane)
+  VKF_PRNG_F32,      // prng_xoshiro128pp_float.comp
+};
+
+// binary sub-ops
+enum { VKB_ADD = 0, VKB_SUB, VKB_MUL, VKB_DIV, VKB_MAX, VKB_MIN, VKB_POW, VKB_RSUB, VKB_RDIV, VKB_RPOW };
+// unary sub-ops
+enum {
+  VKU_ABS = 0, VKU_SIGN, VKU_SIN, VKU_COS, VKU_TAN, VKU_ASIN, VKU_ACOS, VKU_ATAN, VKU_SINH,
+  VKU_COSH, VKU_TANH, VKU_ASINH, VKU_ACOSH, VKU_ATANH, VKU_EXP, VKU_LOG, VKU_EXP2, VKU_LOG2,
+  VKU_SQRT, VKU_INVSQRT, VKU_COUNT
+};
+// clamp variants: bit0 = in-place, bits1-2: 0 vvv, 1 sv (scalar min), 2 vs (scalar max), 3 ss
+enum { VKC_VV = 0, VKC_SV = 1, VKC_VS = 2, VKC_SS = 3 };
+// reductions
+enum { VKR_SUM = 0, VKR_PROD, VKR_MAX, VKR_MIN };

@@ -1,0 +1,390 @@
+// vkp_elementwise.cu -- same-shape element-wise kernels (HBM-bound, 128-bit vectorised).
+//
+// Replaces the one-element-per-invocation shaders of the reference:
+//   vec (+) vec      add/sub/mul/div/max/min/pow.comp          (shader/add.comp:21-26)
+//   vec (+)= vec     iadd ... ipow.comp                         (shader/iadd.comp:18-23)
+//   vec (+) scalar   *_scalar.comp, r*_scalar.comp              (shader/add_scalar.comp:19-24)
+//   vec (+)= scalar  i*_scalar.comp                             (shader/iadd_scalar.comp:16-21)
+//   unary            abs ... invsqrt.comp and i-forms           (shader/abs.comp:22)
+//   clamp x8         clamp{,_sv,_vs,_ss}.comp, iclamp*.comp     (shader/clamp.comp:24-29)
+//   nn_cross_entropy{,_backward}.comp                           (:25)
+//   prng_box_muller.comp / prng_ibox_muller.comp / prng_randrange.comp
+//
+// Layout: flat contiguous float32.  Every thread moves EW_UNROLL independent 16-byte
+// vectors per operand per tile (coalesced: consecutive lanes -> consecutive float4),
+// loads are all issued before the first use so ~64 B per thread per operand are in
+// flight; the grid is a multiple of the SM count and strides over tiles.
+// Compiled with -fmad=false: one IEEE rounding per reference operation.
+#include "vkp_common.cuh"
+#include "vkp_math.cuh"
+
+namespace {
+
+constexpr int EW_BLOCK = 256;
+constexpr int EW_UNROLL = 4;
+constexpr int EW_TILE_VEC = EW_BLOCK * EW_UNROLL;  // float4 per tile
+constexpr int EW_BLOCKS_PER_SM = 8;
+
+// ---- functors ---------------------------------------------------------------------------
+struct FAdd { __device__ float operator()(float a, float b) const { return a + b; } };
+struct FSub { __device__ float operator()(float a, float b) const { return a - b; } };
+struct FMul { __device__ float operator()(float a, float b) const { return a * b; } };
+struct FDiv { __device__ float operator()(float a, float b) const { return a / b; } };
+struct FMax { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+struct FMin { __device__ float operator()(float a, float b) const { return fminf(a, b); } };
+struct FPow { __device__ float operator()(float a, float b) const { return vkpm::pow_f(a, b); } };
+
+template <class B, bool REV>
+struct FScalar {
+  float s;
+  __device__ float operator()(float a) const { return REV ? B()(s, a) : B()(a, s); }
+};
+
+struct UAbs   { __device__ float operator()(float a) const { return fabsf(a); } };
+struct USign  { __device__ float operator()(float a) const { return vkpm::sign_f(a); } };
+struct USin   { __device__ float operator()(float a) const { return sinf(a); } };
+struct UCos   { __device__ float operator()(float a) const { return cosf(a); } };
+struct UTan   { __device__ float operator()(float a) const { return tanf(a); } };
+struct UAsin  { __device__ float operator()(float a) const { return asinf(a); } };
+struct UAcos  { __device__ float operator()(float a) const { return acosf(a); } };
+struct UAtan  { __device__ float operator()(float a) const { return atanf(a); } };
+struct USinh  { __device__ float operator()(float a) const { return sinhf(a); } };
+struct UCosh  { __device__ float operator()(float a) const { return coshf(a); } };
+struct UTanh  { __device__ float operator()(float a) const { return tanhf(a); } };
+struct UAsinh { __device__ float operator()(float a) const { return asinhf(a); } };
+struct UAcosh { __device__ float operator()(float a) const { return acoshf(a); } };
+struct UAtanh { __device__ float operator()(float a) const { return atanhf(a); } };
+struct UExp   { __device__ float operator()(float a) const { return vkpm::exp_f(a); } };
+struct ULog   { __device__ float operator()(float a) const { return vkpm::log_f(a); } };
+struct UExp2  { __device__ float operator()(float a) const { return vkpm::exp2_f(a); } };
+struct ULog2  { __device__ float operator()(float a) const { return vkpm::log2_f(a); } };
+struct USqrt  { __device__ float operator()(float a) const { return __fsqrt_rn(a); } };
+struct UInvSqrt { __device__ float operator()(float a) const { return __fdiv_rn(1.0f, __fsqrt_rn(a)); } };
+
+// GLSL clamp(x, lo, hi) = min(max(x, lo), hi)
+struct CClampVV { __device__ float operator()(float a, float lo, float hi) const { return fminf(fmaxf(a, lo), hi); } };
+struct CClampSV { float lo; __device__ float operator()(float a, float hi) const { return fminf(fmaxf(a, lo), hi); } };
+struct CClampVS { float hi; __device__ float operator()(float a, float lo) const { return fminf(fmaxf(a, lo), hi); } };
+struct CClampSS { float lo, hi; __device__ float operator()(float a) const { return fminf(fmaxf(a, lo), hi); } };
+
+// L = -y * log(x + 1e-8)   (nn_cross_entropy.comp:25);  dx = -y / (x + 1e-8)  (..._backward.comp:25)
+struct FCrossEntropy { __device__ float operator()(float x, float y) const { return (-y) * vkpm::log_f(x + 1e-8f); } };
+struct FCrossEntropyBwd { __device__ float operator()(float x, float y) const { return (-y) / (x + 1e-8f); } };
+
+// ---- generic vectorised kernel ------------------------------------------------------------
+template <int NIN>
+struct Apply;
+template <> struct Apply<1> { template <class F> static __device__ float go(const F& f, float a, float, float) { return f(a); } };
+template <> struct Apply<2> { template <class F> static __device__ float go(const F& f, float a, float b, float) { return f(a, b); } };
+template <> struct Apply<3> { template <class F> static __device__ float go(const F& f, float a, float b, float c) { return f(a, b, c); } };
+
+template <int NIN, class F>
+__global__ void __launch_bounds__(EW_BLOCK)
+ew_kernel(F f, const float* in0, const float* in1, const float* in2, float* out, size_t n) {
+  const size_t nvec = n >> 2;
+  const size_t ntiles = (nvec + EW_TILE_VEC - 1) / EW_TILE_VEC;
+  const float4* v0 = reinterpret_cast<const float4*>(in0);
+  const float4* v1 = reinterpret_cast<const float4*>(in1);
+  const float4* v2 = reinterpret_cast<const float4*>(in2);
+  float4* vo = reinterpret_cast<float4*>(out);
+
+  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const size_t base = tile * EW_TILE_VEC + threadIdx.x;
+    float4 a[EW_UNROLL], b[EW_UNROLL], c[EW_UNROLL];
+    if (base + (EW_UNROLL - 1) * EW_BLOCK < nvec) {  // whole tile in range for this thread
+#pragma unroll
+      for (int u = 0; u < EW_UNROLL; u++) {
+        const size_t i = base + (size_t)u * EW_BLOCK;
+        a[u] = v0[i];
+        if (NIN > 1) b[u] = v1[i];
+        if (NIN > 2) c[u] = v2[i];
+      }
+#pragma unroll
+      for (int u = 0; u < EW_UNROLL; u++) {
+        float4 r;
+        r.x = Apply<NIN>::go(f, a[u].x, b[u].x, c[u].x);
+        r.y = Apply<NIN>::go(f, a[u].y, b[u].y, c[u].y);
+        r.z = Apply<NIN>::go(f, a[u].z, b[u].z, c[u].z);
+        r.w = Apply<NIN>::go(f, a[u].w, b[u].w, c[u].w);
+        vo[base + (size_t)u * EW_BLOCK] = r;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < EW_UNROLL; u++) {
+        const size_t i = base + (size_t)u * EW_BLOCK;
+        if (i < nvec) {
+          a[u] = v0[i];
+          if (NIN > 1) b[u] = v1[i];
+          if (NIN > 2) c[u] = v2[i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < EW_UNROLL; u++) {
+        const size_t i = base + (size_t)u * EW_BLOCK;
+        if (i < nvec) {
+          float4 r;
+          r.x = Apply<NIN>::go(f, a[u].x, b[u].x, c[u].x);
+          r.y = Apply<NIN>::go(f, a[u].y, b[u].y, c[u].y);
+          r.z = Apply<NIN>::go(f, a[u].z, b[u].z, c[u].z);
+          r.w = Apply<NIN>::go(f, a[u].w, b[u].w, c[u].w);
+          vo[i] = r;
+        }
+      }
+    }
+  }
+  // scalar tail (n % 4 elements)
+  if (blockIdx.x == 0) {
+    const size_t i = (nvec << 2) + threadIdx.x;
+    if (i < n) {
+      const float a = in0[i];
+      const float b = NIN > 1 ? in1[i] : 0.f;
+      const float c = NIN > 2 ? in2[i] : 0.f;
+      out[i] = Apply<NIN>::go(f, a, b, c);
+    }
+  }
+}
+
+template <int NIN, class F>
+int launch_ew(vkp_ctx* ctx, const char* name, F f, const void* in0, const void* in1,
+              const void* in2, void* out, size_t n) {
+  if (n == 0) return VKP_OK;
+  const unsigned grid = vkp_grid_for(ctx, (n + 3) / 4, EW_TILE_VEC, EW_BLOCKS_PER_SM);
+  ew_kernel<NIN, F><<<grid, EW_BLOCK, 0, ctx->stream>>>(
+      f, (const float*)in0, (const float*)in1, (const float*)in2, (float*)out, n);
+  return vkp_after_launch(ctx, name);
+}
+
+// ---- Box-Muller (prng_box_muller.comp:19-32, prng_ibox_muller.comp:16-27) -----------------
+// One thread per pair.  Unlike the reference dispatch (floor(n/2) invocations rounded up to a
+// workgroup, random.py:106-121) the last element of an odd-length output is always written.
+__global__ void __launch_bounds__(256)
+box_muller_kernel(const float* a, float* b, size_t n, float mean, float stddev) {
+  const size_t npair = (n + 1) >> 1;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npair;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t j = 2 * i, k = j + 1;
+    const float2 u = *reinterpret_cast<const float2*>(a + j);  // a has an even number of elements
+    const float r = __fsqrt_rn(-2.0f * vkpm::log_f(1.0f - u.x)) * stddev;
+    const float angle = 6.28318530718f * u.y;
+    float s, c;
+    sincosf(angle, &s, &c);
+    const float o0 = mean + r * s, o1 = mean + r * c;
+    if (k < n) {
+      *reinterpret_cast<float2*>(b + j) = make_float2(o0, o1);
+    } else {
+      b[j] = o0;
+    }
+  }
+}
+
+// b[i] = low + uint(float(high - low + 1) * a[i])   (prng_randrange.comp:20-27)
+__global__ void __launch_bounds__(256)
+randrange_kernel(const float* a, uint32_t* b, size_t n, uint32_t low, uint32_t high) {
+  const float range = __uint2float_rn(high - low + 1u);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    b[i] = low + __float2uint_rz(range * a[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) fill_u32_kernel(uint32_t* dst, size_t n, uint32_t v) {
+  const size_t nvec = n >> 2;
+  uint4* dv = reinterpret_cast<uint4*>(dst);
+  const uint4 vv = make_uint4(v, v, v, v);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (size_t)gridDim.x * blockDim.x)
+    dv[i] = vv;
+  if (blockIdx.x == 0) {
+    const size_t i = (nvec << 2) + threadIdx.x;
+    if (i < n) dst[i] = v;
+  }
+}
+
+// one draw per lane (prng_xoshiro128pp_uint32.comp:26-43 / _float.comp:26-44); the stream API
+// in vkp_prng.cu is the fast path, this is the literal single-dispatch form.
+template <bool AS_FLOAT>
+__global__ void xoshiro_step_kernel(uint32_t* state, uint32_t* out, uint32_t shift, uint32_t size) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= size) return;
+  uint4 s = reinterpret_cast<uint4*>(state)[i];
+  const uint32_t sum = s.x + s.w;
+  const uint32_t result = ((sum << 7) | (sum >> 25)) + s.x;
+  out[i + shift] = AS_FLOAT ? __float_as_uint(__uint_as_float((result >> 9) | 0x3f800000u) - 1.0f) : result;
+  const uint32_t t = s.y << 9;
+  s.z ^= s.x; s.w ^= s.y; s.y ^= s.z; s.x ^= s.w;
+  s.z ^= t;
+  s.w = (s.w << 11) | (s.w >> 21);
+  reinterpret_cast<uint4*>(state)[i] = s;
+}
+
+template <class B>
+int launch_scalar(vkp_ctx* ctx, const char* name, bool rev, float s, const void* a, void* out, size_t n) {
+  if (rev) return launch_ew<1>(ctx, name, FScalar<B, true>{s}, a, nullptr, nullptr, out, n);
+  return launch_ew<1>(ctx, name, FScalar<B, false>{s}, a, nullptr, nullptr, out, n);
+}
+
+int dispatch_binary(vkp_ctx* ctx, int sub, const void* a, const void* b, void* out, size_t n) {
+  switch (sub) {
+    case VKB_ADD: return launch_ew<2>(ctx, "add", FAdd(), a, b, nullptr, out, n);
+    case VKB_SUB: return launch_ew<2>(ctx, "sub", FSub(), a, b, nullptr, out, n);
+    case VKB_MUL: return launch_ew<2>(ctx, "mul", FMul(), a, b, nullptr, out, n);
+    case VKB_DIV: return launch_ew<2>(ctx, "div", FDiv(), a, b, nullptr, out, n);
+    case VKB_MAX: return launch_ew<2>(ctx, "max", FMax(), a, b, nullptr, out, n);
+    case VKB_MIN: return launch_ew<2>(ctx, "min", FMin(), a, b, nullptr, out, n);
+    case VKB_POW: return launch_ew<2>(ctx, "pow", FPow(), a, b, nullptr, out, n);
+  }
+  return vkp_set_error("unknown binary op %d", sub);
+}
+
+int dispatch_scalar(vkp_ctx* ctx, int sub, float s, const void* a, void* out, size_t n) {
+  switch (sub) {
+    case VKB_ADD: return launch_scalar<FAdd>(ctx, "add_scalar", false, s, a, out, n);
+    case VKB_SUB: return launch_scalar<FSub>(ctx, "sub_scalar", false, s, a, out, n);
+    case VKB_MUL: return launch_scalar<FMul>(ctx, "mul_scalar", false, s, a, out, n);
+    case VKB_DIV: return launch_scalar<FDiv>(ctx, "div_scalar", false, s, a, out, n);
+    case VKB_MAX: return launch_scalar<FMax>(ctx, "max_scalar", false, s, a, out, n);
+    case VKB_MIN: return launch_scalar<FMin>(ctx, "min_scalar", false, s, a, out, n);
+    case VKB_POW: return launch_scalar<FPow>(ctx, "pow_scalar", false, s, a, out, n);
+    case VKB_RSUB: return launch_scalar<FSub>(ctx, "rsub_scalar", true, s, a, out, n);
+    case VKB_RDIV: return launch_scalar<FDiv>(ctx, "rdiv_scalar", true, s, a, out, n);
+    case VKB_RPOW: return launch_scalar<FPow>(ctx, "rpow_scalar", true, s, a, out, n);
+  }
+  return vkp_set_error("unknown scalar op %d", sub);
+}
+
+int dispatch_unary(vkp_ctx* ctx, int sub, const void* a, void* out, size_t n) {
+#define U(ID, FN, NAME) case ID: return launch_ew<1>(ctx, NAME, FN(), a, nullptr, nullptr, out, n);
+  switch (sub) {
+    U(VKU_ABS, UAbs, "abs") U(VKU_SIGN, USign, "sign") U(VKU_SIN, USin, "sin") U(VKU_COS, UCos, "cos")
+    U(VKU_TAN, UTan, "tan") U(VKU_ASIN, UAsin, "asin") U(VKU_ACOS, UAcos, "acos") U(VKU_ATAN, UAtan, "atan")
+    U(VKU_SINH, USinh, "sinh") U(VKU_COSH, UCosh, "cosh") U(VKU_TANH, UTanh, "tanh")
+    U(VKU_ASINH, UAsinh, "asinh") U(VKU_ACOSH, UAcosh, "acosh") U(VKU_ATANH, UAtanh, "atanh")
+    U(VKU_EXP, UExp, "exp") U(VKU_LOG, ULog, "log") U(VKU_EXP2, UExp2, "exp2") U(VKU_LOG2, ULog2, "log2")
+    U(VKU_SQRT, USqrt, "sqrt") U(VKU_INVSQRT, UInvSqrt, "invsqrt")
+  }
+#undef U
+  return vkp_set_error("unknown unary op %d", sub);
+}
+
+}  // namespace
+
+#define NEED(nb, T)                                                                           \
+  VKP_CHECK(nbuf == (nb) && pbytes == sizeof(T), "%s: expected %d buffers and %zu parameter " \
+            "bytes, got %d and %zu", __func__, (nb), sizeof(T), nbuf, pbytes);                \
+  const T* p = static_cast<const T*>(params)
+
+int vkp_launch_elementwise(vkp_ctx* ctx, int fam, int sub, void* const* bufs, int nbuf,
+                           const void* params, size_t pbytes) {
+  switch (fam) {
+    case VKF_BIN: {   // bindings A, B, C
+      NEED(3, vkp_vector_params);
+      return dispatch_binary(ctx, sub, bufs[0], bufs[1], bufs[2], p->size);
+    }
+    case VKF_IBIN: {  // bindings A (rw), B
+      NEED(2, vkp_vector_params);
+      return dispatch_binary(ctx, sub, bufs[0], bufs[1], bufs[0], p->size);
+    }
+    case VKF_SCALAR: {  // bindings A, B (out)
+      NEED(2, vkp_vectorscalar_params);
+      return dispatch_scalar(ctx, sub, p->scalar, bufs[0], bufs[1], p->size);
+    }
+    case VKF_ISCALAR: {  // binding A (rw)
+      NEED(1, vkp_vectorscalar_params);
+      return dispatch_scalar(ctx, sub, p->scalar, bufs[0], bufs[0], p->size);
+    }
+    case VKF_UNARY: {
+      NEED(2, vkp_vector_params);
+      return dispatch_unary(ctx, sub, bufs[0], bufs[1], p->size);
+    }
+    case VKF_IUNARY: {
+      NEED(1, vkp_vector_params);
+      return dispatch_unary(ctx, sub, bufs[0], bufs[0], p->size);
+    }
+    case VKF_CLAMP: {
+      const bool inplace = sub & 1;
+      const int variant = sub >> 1;
+      switch (variant) {
+        case VKC_VV: {  // clamp.comp: A, B=min, C=max, D / iclamp.comp: A, B, C
+          NEED(inplace ? 3 : 4, vkp_vector_params);
+          return launch_ew<3>(ctx, "clamp", CClampVV(), bufs[0], bufs[1], bufs[2],
+                              inplace ? bufs[0] : bufs[3], p->size);
+        }
+        case VKC_SV: {  // clamp_sv.comp: A, B=max, C ; scalar = min
+          NEED(inplace ? 2 : 3, vkp_vectorscalar_params);
+          return launch_ew<2>(ctx, "clamp_sv", CClampSV{p->scalar}, bufs[0], bufs[1], nullptr,
+                              inplace ? bufs[0] : bufs[2], p->size);
+        }
+        case VKC_VS: {  // clamp_vs.comp: A, B=min, C ; scalar = max
+          NEED(inplace ? 2 : 3, vkp_vectorscalar_params);
+          return launch_ew<2>(ctx, "clamp_vs", CClampVS{p->scalar}, bufs[0], bufs[1], nullptr,
+                              inplace ? bufs[0] : bufs[2], p->size);
+        }
+        case VKC_SS: {  // clamp_ss.comp: A, B ; scalars = [min, max]
+          NEED(inplace ? 1 : 2, vkp_vectorscalar2_params);
+          return launch_ew<1>(ctx, "clamp_ss", CClampSS{p->scalar[0], p->scalar[1]}, bufs[0],
+                              nullptr, nullptr, inplace ? bufs[0] : bufs[1], p->size);
+        }
+      }
+      return vkp_set_error("unknown clamp variant %d", variant);
+    }
+    case VKF_CE: {  // X, Y, L
+      NEED(3, vkp_vector_params);
+      return launch_ew<2>(ctx, "nn_cross_entropy", FCrossEntropy(), bufs[0], bufs[1], nullptr, bufs[2], p->size);
+    }
+    case VKF_CE_BWD: {  // X, Y, dX
+      NEED(3, vkp_vector_params);
+      return launch_ew<2>(ctx, "nn_cross_entropy_backward", FCrossEntropyBwd(), bufs[0], bufs[1], nullptr, bufs[2], p->size);
+    }
+    case VKF_BOX_MULLER: {  // A (uniform, n rounded up to even), B (out, n)
+      NEED(2, vkp_vectorscalar2_params);
+      if (p->size == 0) return VKP_OK;
+      const unsigned grid = vkp_grid_for(ctx, (p->size + 1) / 2, 256, 8);
+      box_muller_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)bufs[0], (float*)bufs[1], p->size,
+                                                        p->scalar[0], p->scalar[1]);
+      return vkp_after_launch(ctx, "prng_box_muller");
+    }
+    case VKF_IBOX_MULLER: {  // A (rw, even n)
+      NEED(1, vkp_vectorscalar2_params);
+      if (p->size == 0) return VKP_OK;
+      VKP_CHECK(p->size % 2 == 0, "prng_ibox_muller needs an even element count (random.py:109-115)");
+      const unsigned grid = vkp_grid_for(ctx, p->size / 2, 256, 8);
+      box_muller_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)bufs[0], (float*)bufs[0], p->size,
+                                                        p->scalar[0], p->scalar[1]);
+      return vkp_after_launch(ctx, "prng_ibox_muller");
+    }
+    case VKF_RANDRANGE: {  // A ([0,1) floats), B (u32 out)
+      NEED(2, vkp_vectorrange_params);
+      if (p->size == 0) return VKP_OK;
+      const unsigned grid = vkp_grid_for(ctx, p->size, 256, 8);
+      randrange_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)bufs[0], (uint32_t*)bufs[1], p->size,
+                                                       p->low, p->high);
+      return vkp_after_launch(ctx, "prng_randrange");
+    }
+    case VKF_PRNG_U32:
+    case VKF_PRNG_F32: {  // A = state (4 words per lane), B = out
+      NEED(2, vkp_shiftvector_params);
+      if (p->size == 0) return VKP_OK;
+      const unsigned grid = (p->size + 63) / 64;
+      if (fam == VKF_PRNG_F32)
+        xoshiro_step_kernel<true><<<grid, 64, 0, ctx->stream>>>((uint32_t*)bufs[0], (uint32_t*)bufs[1], p->shift, p->size);
+      else
+        xoshiro_step_kernel<false><<<grid, 64, 0, ctx->stream>>>((uint32_t*)bufs[0], (uint32_t*)bufs[1], p->shift, p->size);
+      return vkp_after_launch(ctx, "prng_xoshiro128pp");
+    }
+  }
+  return vkp_set_error("vkp_launch_elementwise: unknown family %d", fam);
+}
+
+extern "C" int vkp_fill_u32(vkp_ctx* ctx, void* dst, size_t count, uint32_t bits, vkp_job** job) {
+  VKP_CHECK(ctx && (dst || count == 0), "vkp_fill_u32: null argument");
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  void* bufs[1] = {dst};
+  VKP_TRY(vkp_prepare_buffers(ctx, bufs, 1));
+  if (count) {
+    const unsigned grid = vkp_grid_for(ctx, (count + 3) / 4, 256, 8);
+    fill_u32_kernel<<<grid, 256, 0, ctx->stream>>>((uint32_t*)dst, count, bits);
+    VKP_TRY(vkp_after_launch(ctx, "fill"));
+  }
+  return vkp_finish_op(ctx, job);
+}

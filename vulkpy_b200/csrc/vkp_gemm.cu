@@ -1,0 +1,128 @@
+// vkp_gemm.cu -- float32 contraction behind `@` and nn.Dense.
+//
+// Replaces shader/matmul.comp:23-33 (C[M,N] = A[M,K] B[K,N], one thread per C element, serial
+// fp32 loop over K) and shader/batch_affine.comp:25-39 (Y[B,out] = X[B,in] W[out,in]^T + b).
+// Dense.backward of the reference builds a B x out x in temporary and sums it
+// (nn/layers.py:126-141); here dW = dy^T x and dx = dy W are two more calls of the same GEMM.
+//
+// Two implementations behind one entry point (vkp_launch_gemm):
+//   * gemm_simt: register-tiled fp32 FFMA kernel, any shape / any transposition.  It is the
+//     path for small or unaligned problems and the on-device cross-check of the tensor path.
+//   * gemm_tc (vkp_gemm_tc.cu): tcgen05 3xTF32 kernel with TMEM accumulators fed by TMA, used
+//     when the shape is tile-aligned.
+#include "vkp_common.cuh"
+
+int vkp_gemm_tc_supported(int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
+                          const float* B, float* C);
+int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
+                const float* B, float* C, const float* bias, int accumulate);
+
+namespace {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+// C[m,n] (+)= sum_k a(m,k) b(k,n) + bias[n]
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                 const float* __restrict__ bias, uint32_t M, uint32_t N, uint32_t K, int accumulate) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t tx = tid % 16, ty = tid / 16;
+  const uint32_t m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+
+  for (uint32_t k0 = 0; k0 < K; k0 += TK) {
+    // stage A tile (TM x TK) and B tile (TK x TN); the fast thread index follows the
+    // contiguous direction of the source
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const uint32_t e = tid + r * 256;  // 0..1023
+      uint32_t m, k;
+      if (TA) { m = e % TM; k = e / TM; } else { k = e % TK; m = e / TK; }
+      const uint32_t gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < K) v = TA ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk];
+      As[k][m] = v;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const uint32_t e = tid + r * 256;
+      uint32_t n, k;
+      if (TB) { k = e % TK; n = e / TK; } else { n = e % TN; k = e / TN; }
+      const uint32_t gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < N && gk < K) v = TB ? B[(size_t)gn * K + gk] : B[(size_t)gk * N + gn];
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; k++) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint32_t gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[gn];
+      float* c = C + (size_t)gm * N + gn;
+      *c = accumulate ? (*c + v) : v;
+    }
+  }
+}
+
+int gemm_simt(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
+              const float* B, float* C, const float* bias, int accumulate) {
+  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
+  VKP_CHECK(grid.y <= 65535, "gemm_simt: M too large for the fallback kernel");
+  if (!transA && !transB) gemm_simt_kernel<false, false><<<grid, 256, 0, ctx->stream>>>(A, B, C, bias, M, N, K, accumulate);
+  else if (!transA && transB) gemm_simt_kernel<false, true><<<grid, 256, 0, ctx->stream>>>(A, B, C, bias, M, N, K, accumulate);
+  else if (transA && !transB) gemm_simt_kernel<true, false><<<grid, 256, 0, ctx->stream>>>(A, B, C, bias, M, N, K, accumulate);
+  else gemm_simt_kernel<true, true><<<grid, 256, 0, ctx->stream>>>(A, B, C, bias, M, N, K, accumulate);
+  return vkp_after_launch(ctx, "gemm_simt");
+}
+
+}  // namespace
+
+int vkp_launch_gemm(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K,
+                    const float* A, const float* B, float* C, const float* bias, int flags) {
+  if (M == 0 || N == 0) return VKP_OK;
+  const int accumulate = (flags & VKP_GEMM_ACCUMULATE) ? 1 : 0;
+  const bool force_simt = flags & VKP_GEMM_FORCE_SIMT, force_tc = flags & VKP_GEMM_FORCE_TC;
+  const bool tc_ok = !force_simt && vkp_gemm_tc_supported(transA, transB, M, N, K, A, B, C);
+  VKP_CHECK(!(force_tc && !tc_ok), "vkp_gemm: tensor-core path forced but the shape (%u,%u,%u) is not supported", M, N, K);
+  if (tc_ok) return vkp_gemm_tc(ctx, transA, transB, M, N, K, A, B, C, bias, accumulate);
+  return gemm_simt(ctx, transA, transB, M, N, K, A, B, C, bias, accumulate);
+}
+
+extern "C" int vkp_gemm(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K,
+                        const float* A, const float* B, float* C, const float* bias, int flags,
+                        vkp_job** job) {
+  VKP_CHECK(ctx && A && B && C, "vkp_gemm: null argument");
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  void* bufs[4] = {(void*)A, (void*)B, (void*)C, (void*)bias};
+  VKP_TRY(vkp_prepare_buffers(ctx, bufs, 4));
+  VKP_TRY(vkp_launch_gemm(ctx, transA, transB, M, N, K, A, B, C, bias, flags));
+  return vkp_finish_op(ctx, job);
+}

@@ -1,0 +1,367 @@
+// vkp_prng.cu -- xoshiro128++ streams, bit-exact with the reference.
+//
+// Replaces PRNG::Xoshiro128pp (vulkpy/_vkarray.cc:577-719), prng_xoshiro128pp_uint32.comp:26-43,
+// prng_xoshiro128pp_float.comp:26-44 and, fused, random.py:60-124 + prng_box_muller.comp:19-32.
+//
+// Reference semantics that are reproduced exactly:
+//   * seeding: four chained splitmix64 outputs, truncated to 32 bit, form lane 0; lane i is
+//     lane i-1 advanced by the reference's jump(), which writes the accumulators back after
+//     EACH of the four JUMP words (_vkarray.cc:597-621) -- not the canonical jump;
+//   * `size` lanes; a request of n numbers is served in chunks of `size`: out[c*size + lane] is
+//     draw c of that lane, the last chunk advances only the first n % size lanes, and the state
+//     persists between calls (_vkarray.cc:697-717);
+//   * [0,1) mapping: uintBitsToFloat((x >> 9) | 0x3f800000) - 1.0.
+//
+// The reference issues ceil(n/size) dependent dispatches with the state round-tripping through
+// memory.  xoshiro's state transition T is linear over GF(2), so here a lane's sequential stream
+// is cut into segments of L = 2^m draws; thread (lane group, segment p) starts from
+// T^(p*L) * state, obtained by multiplying with precomputed 128x128 bit matrices T^(2^k)
+// (k = m + set bits of p), keeps the state in registers for L draws and stores with 8/16-byte
+// vectors (adjacent lanes are adjacent in memory).  States are double buffered so a segment that
+// starts late never sees the final state another segment already wrote.
+#include "vkp_common.cuh"
+#include "vkp_math.cuh"
+
+#include <random>
+
+namespace {
+
+constexpr int JUMP_LEVELS = 34;  // T^(2^k), k = 0..33
+
+struct HostState { uint32_t s[4]; };
+
+inline uint32_t rotl32(uint32_t x, int k) { return (x << k) | (x >> (32 - k)); }
+
+inline uint32_t next_host(uint32_t (&s)[4]) {
+  const uint32_t result = rotl32(s[0] + s[3], 7) + s[0];
+  const uint32_t t = s[1] << 9;
+  s[2] ^= s[0];
+  s[3] ^= s[1];
+  s[1] ^= s[2];
+  s[0] ^= s[3];
+  s[2] ^= t;
+  s[3] = rotl32(s[3], 11);
+  return result;
+}
+
+inline uint64_t splitmix64(uint64_t x) {
+  uint64_t z = (x += 0x9e3779b97f4a7c15ULL);
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+
+// the reference's jump(): accumulators are NOT reset between JUMP words and are written back
+// after each word
+inline void jump_ref(uint32_t (&s)[4]) {
+  static const uint32_t JUMP[4] = {0x8764000bu, 0xf542d2d3u, 0x6fa035c3u, 0x77f2db5bu};
+  uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  for (int w = 0; w < 4; w++) {
+    for (int b = 0; b < 32; b++) {
+      if (JUMP[w] & (1u << b)) {
+        s0 ^= s[0]; s1 ^= s[1]; s2 ^= s[2]; s3 ^= s[3];
+      }
+      next_host(s);
+    }
+    s[0] = s0; s[1] = s1; s[2] = s2; s[3] = s3;
+  }
+}
+
+// 128x128 GF(2) matrix stored by columns: col[c] = image of basis vector e_c (bit c of the
+// 128-bit state, word c/32, bit c%32)
+struct BitMat { uint32_t col[128][4]; };
+
+inline void matvec_host(const BitMat& m, const uint32_t (&v)[4], uint32_t (&out)[4]) {
+  uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  for (int w = 0; w < 4; w++)
+    for (int b = 0; b < 32; b++)
+      if ((v[w] >> b) & 1u) {
+        const uint32_t* c = m.col[w * 32 + b];
+        a0 ^= c[0]; a1 ^= c[1]; a2 ^= c[2]; a3 ^= c[3];
+      }
+  out[0] = a0; out[1] = a1; out[2] = a2; out[3] = a3;
+}
+
+std::once_flag g_jump_once;
+BitMat* g_jump_host = nullptr;  // [JUMP_LEVELS]
+
+void build_jump_tables() {
+  g_jump_host = new BitMat[JUMP_LEVELS];
+  for (int c = 0; c < 128; c++) {  // T itself
+    uint32_t s[4] = {0, 0, 0, 0};
+    s[c / 32] = 1u << (c % 32);
+    next_host(s);
+    for (int w = 0; w < 4; w++) g_jump_host[0].col[c][w] = s[w];
+  }
+  for (int k = 1; k < JUMP_LEVELS; k++)  // squaring: (M*M) e_c = M (M e_c)
+    for (int c = 0; c < 128; c++) matvec_host(g_jump_host[k - 1], g_jump_host[k - 1].col[c], g_jump_host[k].col[c]);
+}
+
+// ---- device ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rotl_d(uint32_t x, int k) { return __funnelshift_l(x, x, k); }
+
+__device__ __forceinline__ uint32_t next_dev(uint4& s) {
+  const uint32_t result = rotl_d(s.x + s.w, 7) + s.x;
+  const uint32_t t = s.y << 9;
+  s.z ^= s.x;
+  s.w ^= s.y;
+  s.y ^= s.z;
+  s.x ^= s.w;
+  s.z ^= t;
+  s.w = rotl_d(s.w, 11);
+  return result;
+}
+
+__device__ __forceinline__ uint4 matvec_dev(const uint4* __restrict__ m, uint4 v) {
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+#pragma unroll 8
+    for (int b = 0; b < 32; b++) {
+      const uint32_t mask = 0u - ((w[i] >> b) & 1u);
+      const uint4 c = __ldg(m + i * 32 + b);
+      acc.x ^= c.x & mask; acc.y ^= c.y & mask; acc.z ^= c.z & mask; acc.w ^= c.w & mask;
+    }
+  }
+  return acc;
+}
+
+__device__ __forceinline__ float u2f01(uint32_t r) { return __uint_as_float((r >> 9) | 0x3f800000u) - 1.0f; }
+
+enum { MODE_U32 = 0, MODE_F32 = 1, MODE_NORMAL = 2 };
+
+template <int LPT> struct VecStore;
+template <> struct VecStore<1> { static __device__ void st(uint32_t* p, const uint32_t* v) { p[0] = v[0]; } };
+template <> struct VecStore<2> { static __device__ void st(uint32_t* p, const uint32_t* v) { *reinterpret_cast<uint2*>(p) = make_uint2(v[0], v[1]); } };
+template <> struct VecStore<4> { static __device__ void st(uint32_t* p, const uint32_t* v) { *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]); } };
+
+// n_draw: uniforms consumed in total (n, or n+1 for an odd-length normal()); n_out: elements written
+template <int LPT, int MODE>
+__global__ void __launch_bounds__(128)
+xoshiro_stream_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ state_out,
+                      uint32_t* __restrict__ out, const uint4* __restrict__ jump, uint32_t size,
+                      uint64_t n_draw, uint64_t n_out, uint32_t log2L, uint32_t nseg, float mean,
+                      float stddev) {
+  const uint32_t groups = size / LPT;
+  const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)groups * nseg) return;
+  const uint32_t p = (uint32_t)(t / groups);
+  const uint32_t l0 = (uint32_t)(t % groups) * LPT;
+  const uint64_t full = n_draw / size;          // draws every lane makes
+  const uint32_t rem = (uint32_t)(n_draw % size);  // lanes < rem make one more
+  const uint64_t start = (uint64_t)p << log2L;
+  const uint64_t seg_end = start + (1ull << log2L);
+
+  uint4 s[LPT];
+#pragma unroll
+  for (int q = 0; q < LPT; q++) s[q] = state_in[l0 + q];
+
+  if (p == 0) {  // lanes that draw nothing keep their state
+#pragma unroll
+    for (int q = 0; q < LPT; q++)
+      if (full == 0 && l0 + q >= rem) state_out[l0 + q] = s[q];
+  }
+  // jump ahead by p * 2^log2L steps
+  for (uint32_t b = 0; (p >> b) != 0; b++) {
+    if ((p >> b) & 1u) {
+      const uint4* m = jump + (size_t)(log2L + b) * 128;
+#pragma unroll
+      for (int q = 0; q < LPT; q++) s[q] = matvec_dev(m, s[q]);
+    }
+  }
+
+  const uint64_t e1 = seg_end < full ? seg_end : full;
+  for (uint64_t c = start; c < e1; c++) {
+    uint32_t r[LPT];
+#pragma unroll
+    for (int q = 0; q < LPT; q++) r[q] = next_dev(s[q]);
+    const uint64_t j = c * size + l0;
+    if (MODE == MODE_U32) {
+      VecStore<LPT>::st(out + j, r);
+    } else if (MODE == MODE_F32) {
+#pragma unroll
+      for (int q = 0; q < LPT; q++) r[q] = __float_as_uint(u2f01(r[q]));
+      VecStore<LPT>::st(out + j, r);
+    } else {  // Box-Muller on the pair (lane l0, lane l0+1); LPT == 2
+      const float u0 = u2f01(r[0]), u1 = u2f01(r[LPT - 1]);
+      const float rad = __fsqrt_rn(-2.0f * vkpm::log_f(1.0f - u0)) * stddev;
+      float sn, cs;
+      sincosf(6.28318530718f * u1, &sn, &cs);
+      const float o0 = mean + rad * sn, o1 = mean + rad * cs;
+      if (j + 1 < n_out) *reinterpret_cast<float2*>(out + j) = make_float2(o0, o1);
+      else if (j < n_out) reinterpret_cast<float*>(out)[j] = o0;
+    }
+  }
+  // tail chunk: draw index `full`, lanes < rem only
+  if (rem != 0 && full >= start && full < seg_end) {
+    uint32_t r[LPT];
+#pragma unroll
+    for (int q = 0; q < LPT; q++) r[q] = (l0 + q < rem) ? next_dev(s[q]) : 0u;
+    const uint64_t j = full * size + l0;
+    if (MODE == MODE_NORMAL) {
+      if (l0 < rem) {  // rem and l0 are even: both lanes of the pair are in
+        const float u0 = u2f01(r[0]), u1 = u2f01(r[LPT - 1]);
+        const float rad = __fsqrt_rn(-2.0f * vkpm::log_f(1.0f - u0)) * stddev;
+        float sn, cs;
+        sincosf(6.28318530718f * u1, &sn, &cs);
+        if (j < n_out) reinterpret_cast<float*>(out)[j] = mean + rad * sn;
+        if (j + 1 < n_out) reinterpret_cast<float*>(out)[j + 1] = mean + rad * cs;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < LPT; q++)
+        if (l0 + q < rem) out[j + q] = (MODE == MODE_F32) ? __float_as_uint(u2f01(r[q])) : r[q];
+    }
+  }
+  // the segment that contains a lane's last draw publishes the lane's new state
+#pragma unroll
+  for (int q = 0; q < LPT; q++) {
+    const uint64_t cnt = full + ((l0 + q < rem) ? 1 : 0);
+    if (cnt > start && cnt <= seg_end) state_out[l0 + q] = s[q];
+  }
+}
+
+}  // namespace
+
+struct vkp_rng {
+  vkp_ctx* ctx;
+  uint32_t size;
+  uint4* state[2];  // device, double buffered; state[cur] is current
+  int cur;
+  uint4* jump;      // device copy of the T^(2^k) tables
+};
+
+static std::mutex g_jump_dev_mu;
+static uint4* g_jump_dev[64] = {nullptr};
+
+extern "C" int vkp_rng_create(vkp_ctx* ctx, uint32_t size, uint64_t seed, int has_seed, vkp_rng** out) {
+  VKP_CHECK(ctx && out, "vkp_rng_create: null argument");
+  VKP_CHECK(size >= 1, "Xoshiro128pp: size must be positive");
+  VKP_TRY(vkp_make_current(ctx));
+  if (!has_seed) seed = std::random_device{}();  // _vkarray.cc:679
+  std::call_once(g_jump_once, build_jump_tables);
+
+  std::vector<HostState> st(size);
+  uint32_t s[4];
+  for (int i = 0; i < 4; i++) {  // _vkarray.cc:659-663
+    seed = splitmix64(seed);
+    s[i] = (uint32_t)seed;
+  }
+  memcpy(st[0].s, s, 16);
+  for (uint32_t i = 1; i < size; i++) {  // _vkarray.cc:666-672
+    jump_ref(s);
+    memcpy(st[i].s, s, 16);
+  }
+
+  vkp_rng* r = new vkp_rng();
+  r->ctx = ctx;
+  r->size = size;
+  r->cur = 0;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  {
+    std::lock_guard<std::mutex> gj(g_jump_dev_mu);
+    if (!g_jump_dev[ctx->device]) {
+      VKP_CUDA(cudaMalloc(&g_jump_dev[ctx->device], sizeof(BitMat) * JUMP_LEVELS));
+      VKP_CUDA(cudaMemcpyAsync(g_jump_dev[ctx->device], g_jump_host, sizeof(BitMat) * JUMP_LEVELS,
+                               cudaMemcpyHostToDevice, ctx->stream));
+    }
+    r->jump = g_jump_dev[ctx->device];
+  }
+  VKP_CUDA(cudaMalloc(&r->state[0], 16ull * size));
+  VKP_CUDA(cudaMalloc(&r->state[1], 16ull * size));
+  VKP_CUDA(cudaMemcpyAsync(r->state[0], st.data(), 16ull * size, cudaMemcpyHostToDevice, ctx->stream));
+  VKP_CUDA(cudaStreamSynchronize(ctx->stream));  // `st` is pageable and about to go out of scope
+  *out = r;
+  return VKP_OK;
+}
+
+extern "C" int vkp_rng_destroy(vkp_rng* rng) {
+  if (!rng) return VKP_OK;
+  vkp_ctx* ctx = rng->ctx;
+  if (vkp_make_current(ctx) == VKP_OK) {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(rng->state[0]);
+    cudaFree(rng->state[1]);
+  }
+  delete rng;
+  return VKP_OK;
+}
+
+extern "C" int vkp_rng_state(vkp_rng* rng, uint32_t* host_out) {
+  VKP_CHECK(rng && host_out, "vkp_rng_state: null argument");
+  vkp_ctx* ctx = rng->ctx;
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  VKP_CUDA(cudaMemcpyAsync(host_out, rng->state[rng->cur], 16ull * rng->size, cudaMemcpyDeviceToHost, ctx->stream));
+  VKP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return VKP_OK;
+}
+
+template <int MODE>
+static int rng_generate(vkp_rng* rng, void* out, uint64_t n_out, float mean, float stddev, vkp_job** job) {
+  VKP_CHECK(rng && (out || n_out == 0), "vkp_rng: null argument");
+  vkp_ctx* ctx = rng->ctx;
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  void* bufs[1] = {out};
+  VKP_TRY(vkp_prepare_buffers(ctx, bufs, 1));
+  if (n_out > 0) {
+    const uint32_t size = rng->size;
+    const uint64_t n_draw = (MODE == MODE_NORMAL) ? ((n_out + 1) & ~1ull) : n_out;
+    int lpt;
+    // lanes per thread: prefer whole warps per segment (uniform jump-ahead), then wider stores
+    if (MODE == MODE_NORMAL) lpt = 2;  // caller guarantees an even size
+    else if (size % 128 == 0) lpt = 4;
+    else if (size % 64 == 0) lpt = 2;
+    else if (size % 32 == 0) lpt = 1;
+    else lpt = (size % 4 == 0) ? 4 : ((size % 2 == 0) ? 2 : 1);
+    const uint32_t groups = size / lpt;
+    const uint64_t draws_per_lane = (n_draw + size - 1) / size;
+    // segment length: power of two, >= 256 draws, giving about sms*1024 threads
+    uint64_t want_seg = ((uint64_t)ctx->sms * 1024 + groups - 1) / groups;
+    if (want_seg < 1) want_seg = 1;
+    uint64_t L = (draws_per_lane + want_seg - 1) / want_seg;
+    uint32_t log2L = 8;
+    while ((1ull << log2L) < L) log2L++;
+    const uint64_t nseg64 = (draws_per_lane + (1ull << log2L) - 1) >> log2L;
+    VKP_CHECK(nseg64 >= 1 && nseg64 < (1ull << 24), "vkp_rng: request too large");
+    const uint32_t nseg = (uint32_t)nseg64;
+    {
+      uint32_t top = 0;
+      while ((nseg - 1) >> top) top++;
+      VKP_CHECK(log2L + top <= JUMP_LEVELS, "vkp_rng: jump table too small for this request");
+    }
+    const uint64_t threads = (uint64_t)groups * nseg;
+    const unsigned grid = (unsigned)((threads + 127) / 128);
+    const uint4* sin_ = rng->state[rng->cur];
+    uint4* sout = rng->state[rng->cur ^ 1];
+#define LAUNCH(LPT)                                                                                  \
+  xoshiro_stream_kernel<LPT, MODE><<<grid, 128, 0, ctx->stream>>>(sin_, sout, (uint32_t*)out, rng->jump, \
+                                                                  size, n_draw, n_out, log2L, nseg, mean, stddev)
+    if (MODE == MODE_NORMAL) { LAUNCH(2); }
+    else if (lpt == 4) { LAUNCH(4); }
+    else if (lpt == 2) { LAUNCH(2); }
+    else { LAUNCH(1); }
+#undef LAUNCH
+    VKP_TRY(vkp_after_launch(ctx, "xoshiro128pp_stream"));
+    rng->cur ^= 1;
+  }
+  return vkp_finish_op(ctx, job);
+}
+
+extern "C" int vkp_rng_uint32(vkp_rng* rng, uint32_t* out, uint32_t n, vkp_job** job) {
+  return rng_generate<MODE_U32>(rng, out, n, 0.f, 1.f, job);
+}
+
+extern "C" int vkp_rng_float(vkp_rng* rng, float* out, uint32_t n, vkp_job** job) {
+  return rng_generate<MODE_F32>(rng, out, n, 0.f, 1.f, job);
+}
+
+extern "C" int vkp_rng_normal(vkp_rng* rng, float* out, uint32_t n, float mean, float stddev, vkp_job** job) {
+  VKP_CHECK(rng, "vkp_rng_normal: null argument");
+  VKP_CHECK(rng->size % 2 == 0,
+            "vkp_rng_normal: fused Box-Muller needs an even lane count; use random()+prng_box_muller");
+  return rng_generate<MODE_NORMAL>(rng, out, n, mean, stddev, job);
+}

@@ -1,0 +1,347 @@
+// vkp_reduce.cu -- full, axis and axis+rebroadcast reductions (sum / prod / maximum / minimum).
+//
+// Replaces sum.comp / sum_v1.3.comp / sum_axis.comp / sum_axis_rebroadcast.comp and the prod,
+// maximum, minimum variants (shader/sum.comp:18-30, sum_v1.3.comp:20-29, sum_axis.comp:20-32,
+// sum_axis_rebroadcast.comp:20-35) plus the host loop of vkarray.py:1246-1274.
+//
+// The reference runs ONE thread per output element with a serial loop over the axis (and, for
+// the full reduction, log64(n) dependent single-workgroup jobs that only cover n <= 4096,
+// SURVEY Q2).  Here an array viewed as [prev, axis, post] is reduced by one of two kernels:
+//   * post == 1  -> "row" kernels: lanes run along the contiguous axis with float4 loads;
+//                   short rows use a lane group per row, long rows a CTA per (row, split);
+//   * post  > 1  -> "column" kernel: threads run along `post` (coalesced, float4 when
+//                   post % 4 == 0), the axis is split over threadIdx.y and over CTAs.
+// When the output alone cannot fill 148 SMs the axis is split across CTAs; partials go to a
+// device workspace and a second launch of the same kernel folds them, in a fixed order
+// (deterministic, no atomics).  Accumulation is float32; the order differs from the
+// reference's serial k = 0..axis-1 order, the parity tolerance is stated in tests/.
+#include "vkp_common.cuh"
+
+int vkp_broadcast_copy_3d(vkp_ctx* ctx, const float* src, float* dst, uint32_t prev, uint32_t axis,
+                          uint32_t post);  // vkp_broadcast.cu
+
+namespace {
+
+template <int OP>
+struct Red;
+template <> struct Red<VKR_SUM> {
+  static __device__ __forceinline__ float id() { return 0.f; }
+  static __device__ __forceinline__ float op(float a, float b) { return a + b; }
+};
+template <> struct Red<VKR_PROD> {
+  static __device__ __forceinline__ float id() { return 1.f; }
+  static __device__ __forceinline__ float op(float a, float b) { return a * b; }
+};
+template <> struct Red<VKR_MAX> {
+  static __device__ __forceinline__ float id() { return -INFINITY; }
+  static __device__ __forceinline__ float op(float a, float b) { return fmaxf(a, b); }
+};
+template <> struct Red<VKR_MIN> {
+  static __device__ __forceinline__ float id() { return INFINITY; }
+  static __device__ __forceinline__ float op(float a, float b) { return fminf(a, b); }
+};
+
+template <int OP>
+__device__ __forceinline__ float warp_reduce(float v, int width = 32) {
+  for (int o = width >> 1; o > 0; o >>= 1) v = Red<OP>::op(v, __shfl_xor_sync(0xffffffffu, v, o, 32));
+  return v;
+}
+
+constexpr int RB_BLOCK = 256;
+
+// ---- long rows: one CTA per (row, split) ---------------------------------------------------
+// in: [nrows, len] contiguous; out[row * nsplit + split]
+template <int OP>
+__global__ void __launch_bounds__(RB_BLOCK)
+reduce_rows_block(const float* __restrict__ in, float* __restrict__ out, uint32_t nrows, uint64_t len,
+                  uint32_t nsplit, uint64_t seg /* multiple of 4 */) {
+  __shared__ float sm[RB_BLOCK / 32];
+  for (uint64_t job = blockIdx.x; job < (uint64_t)nrows * nsplit; job += gridDim.x) {
+    const uint64_t row = job / nsplit;
+    const uint32_t split = (uint32_t)(job - row * nsplit);
+    const uint64_t begin = (uint64_t)split * seg;
+    const uint64_t end = (begin + seg < len) ? begin + seg : len;
+    const float* p = in + row * len;
+    float acc0 = Red<OP>::id(), acc1 = Red<OP>::id(), acc2 = Red<OP>::id(), acc3 = Red<OP>::id();
+    if (begin < end) {
+      // peel to a 16-byte boundary, then float4
+      uint64_t i0 = begin;
+      const uint64_t addr = (uint64_t)(p + begin);
+      uint64_t head = ((16 - (addr & 15)) & 15) >> 2;
+      if (head > end - begin) head = end - begin;
+      if (threadIdx.x < head) acc0 = Red<OP>::op(acc0, p[begin + threadIdx.x]);
+      i0 += head;
+      const uint64_t nvec = (end - i0) >> 2;
+      const float4* pv = reinterpret_cast<const float4*>(p + i0);
+      uint64_t v = threadIdx.x;
+      for (; v + 3 * RB_BLOCK < nvec; v += 4 * RB_BLOCK) {
+        const float4 x0 = pv[v], x1 = pv[v + RB_BLOCK], x2 = pv[v + 2 * RB_BLOCK], x3 = pv[v + 3 * RB_BLOCK];
+        acc0 = Red<OP>::op(acc0, Red<OP>::op(Red<OP>::op(x0.x, x0.y), Red<OP>::op(x0.z, x0.w)));
+        acc1 = Red<OP>::op(acc1, Red<OP>::op(Red<OP>::op(x1.x, x1.y), Red<OP>::op(x1.z, x1.w)));
+        acc2 = Red<OP>::op(acc2, Red<OP>::op(Red<OP>::op(x2.x, x2.y), Red<OP>::op(x2.z, x2.w)));
+        acc3 = Red<OP>::op(acc3, Red<OP>::op(Red<OP>::op(x3.x, x3.y), Red<OP>::op(x3.z, x3.w)));
+      }
+      for (; v < nvec; v += RB_BLOCK) {
+        const float4 x0 = pv[v];
+        acc0 = Red<OP>::op(acc0, Red<OP>::op(Red<OP>::op(x0.x, x0.y), Red<OP>::op(x0.z, x0.w)));
+      }
+      const uint64_t t0 = i0 + (nvec << 2);
+      if (t0 + threadIdx.x < end) acc1 = Red<OP>::op(acc1, p[t0 + threadIdx.x]);
+    }
+    float acc = Red<OP>::op(Red<OP>::op(acc0, acc1), Red<OP>::op(acc2, acc3));
+    acc = warp_reduce<OP>(acc);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v2 = threadIdx.x < RB_BLOCK / 32 ? sm[threadIdx.x] : Red<OP>::id();
+      v2 = warp_reduce<OP>(v2, RB_BLOCK / 32);
+      if (threadIdx.x == 0) out[job] = v2;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- short rows: `lpr` lanes per row (power of two <= 32) -----------------------------------
+template <int OP>
+__global__ void __launch_bounds__(RB_BLOCK)
+reduce_rows_group(const float* __restrict__ in, float* __restrict__ out, uint32_t nrows, uint32_t len,
+                  int lpr) {
+  const uint32_t groups_per_block = RB_BLOCK / lpr;
+  const uint32_t g = threadIdx.x / lpr, l = threadIdx.x % lpr;
+  for (uint64_t row0 = (uint64_t)blockIdx.x * groups_per_block; row0 < nrows;
+       row0 += (uint64_t)gridDim.x * groups_per_block) {
+    const uint64_t row = row0 + g;
+    float acc = Red<OP>::id();
+    if (row < nrows) {
+      const float* p = in + row * len;
+      for (uint32_t i = l; i < len; i += lpr) acc = Red<OP>::op(acc, p[i]);
+    }
+    acc = warp_reduce<OP>(acc, lpr);
+    if (l == 0 && row < nrows) out[row] = acc;
+  }
+}
+
+// ---- column kernel: in [prev, axis, post] -> out [prev, nsplit, post] ------------------------
+// blockDim = (bx, by), bx * by == 256.  VEC = 4 needs post % 4 == 0.
+template <int OP, int VEC>
+__global__ void __launch_bounds__(256)
+reduce_cols(const float* __restrict__ in, float* __restrict__ out, uint32_t prev, uint32_t axis,
+            uint32_t post, uint32_t nsplit, uint32_t seg) {
+  __shared__ float sm[256 * VEC];
+  const uint32_t bx = blockDim.x, by = blockDim.y;
+  const uint32_t ctile = bx * VEC;
+  const uint32_t ntile = (post + ctile - 1) / ctile;
+  const uint64_t njobs = (uint64_t)prev * nsplit * ntile;
+  for (uint64_t job = blockIdx.x; job < njobs; job += gridDim.x) {
+    const uint32_t tile = (uint32_t)(job % ntile);
+    const uint64_t rest = job / ntile;
+    const uint32_t split = (uint32_t)(rest % nsplit);
+    const uint32_t i = (uint32_t)(rest / nsplit);
+    const uint32_t col = tile * ctile + threadIdx.x * VEC;
+    const uint32_t k0 = split * seg;
+    const uint32_t k1 = (k0 + seg < axis) ? k0 + seg : axis;
+    float acc[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; c++) acc[c] = Red<OP>::id();
+    if (col < post) {
+      const float* p = in + ((uint64_t)i * axis) * post + col;
+      uint32_t k = k0 + threadIdx.y;
+      if constexpr (VEC == 4) {
+        for (; k + 3 * by < k1; k += 4 * by) {
+          const float4 x0 = *reinterpret_cast<const float4*>(p + (uint64_t)k * post);
+          const float4 x1 = *reinterpret_cast<const float4*>(p + (uint64_t)(k + by) * post);
+          const float4 x2 = *reinterpret_cast<const float4*>(p + (uint64_t)(k + 2 * by) * post);
+          const float4 x3 = *reinterpret_cast<const float4*>(p + (uint64_t)(k + 3 * by) * post);
+          acc[0] = Red<OP>::op(Red<OP>::op(acc[0], x0.x), Red<OP>::op(Red<OP>::op(x1.x, x2.x), x3.x));
+          acc[1] = Red<OP>::op(Red<OP>::op(acc[1], x0.y), Red<OP>::op(Red<OP>::op(x1.y, x2.y), x3.y));
+          acc[2] = Red<OP>::op(Red<OP>::op(acc[2], x0.z), Red<OP>::op(Red<OP>::op(x1.z, x2.z), x3.z));
+          acc[3] = Red<OP>::op(Red<OP>::op(acc[3], x0.w), Red<OP>::op(Red<OP>::op(x1.w, x2.w), x3.w));
+        }
+        for (; k < k1; k += by) {
+          const float4 x0 = *reinterpret_cast<const float4*>(p + (uint64_t)k * post);
+          acc[0] = Red<OP>::op(acc[0], x0.x);
+          acc[1] = Red<OP>::op(acc[1], x0.y);
+          acc[2] = Red<OP>::op(acc[2], x0.z);
+          acc[3] = Red<OP>::op(acc[3], x0.w);
+        }
+      } else {
+        for (; k + 3 * by < k1; k += 4 * by) {
+          const float x0 = p[(uint64_t)k * post], x1 = p[(uint64_t)(k + by) * post];
+          const float x2 = p[(uint64_t)(k + 2 * by) * post], x3 = p[(uint64_t)(k + 3 * by) * post];
+          acc[0] = Red<OP>::op(Red<OP>::op(acc[0], x0), Red<OP>::op(Red<OP>::op(x1, x2), x3));
+        }
+        for (; k < k1; k += by) acc[0] = Red<OP>::op(acc[0], p[(uint64_t)k * post]);
+      }
+    }
+    // fold threadIdx.y in shared memory (fixed order)
+#pragma unroll
+    for (int c = 0; c < VEC; c++) sm[(threadIdx.y * bx + threadIdx.x) * VEC + c] = acc[c];
+    __syncthreads();
+    if (threadIdx.y == 0 && col < post) {
+      float r[VEC];
+#pragma unroll
+      for (int c = 0; c < VEC; c++) r[c] = acc[c];
+      for (uint32_t y = 1; y < by; y++) {
+#pragma unroll
+        for (int c = 0; c < VEC; c++) r[c] = Red<OP>::op(r[c], sm[(y * bx + threadIdx.x) * VEC + c]);
+      }
+      float* o = out + ((uint64_t)i * nsplit + split) * post + col;
+      if constexpr (VEC == 4) {
+        *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+      } else {
+        o[0] = r[0];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- literal sum.comp semantics for sizeB > 1: out[i] = reduce_{j = i, i+sizeB, ...} a[j] -----
+template <int OP>
+__global__ void reduce_strided(const float* __restrict__ in, float* __restrict__ out, uint32_t sizeA,
+                               uint32_t sizeB) {
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= sizeB) return;
+  float acc = Red<OP>::id();
+  for (uint64_t j = warp + (uint64_t)lane * sizeB; j < sizeA; j += 32ull * sizeB) acc = Red<OP>::op(acc, in[j]);
+  acc = warp_reduce<OP>(acc);
+  if (lane == 0) out[warp] = acc;
+}
+
+template <int OP>
+int reduce_rows(vkp_ctx* ctx, const float* in, float* out, uint32_t nrows, uint64_t len) {
+  if (nrows == 0) return VKP_OK;
+  if (len <= 1024) {
+    int lpr = 1;
+    while (lpr < 32 && (uint64_t)lpr * 4 < len) lpr <<= 1;
+    const unsigned gpb = RB_BLOCK / lpr;
+    const unsigned grid = vkp_grid_for(ctx, nrows, gpb, 8);
+    reduce_rows_group<OP><<<grid, RB_BLOCK, 0, ctx->stream>>>(in, out, nrows, (uint32_t)len, lpr);
+    return vkp_after_launch(ctx, "reduce_rows_group");
+  }
+  // long rows: split a row across CTAs when there are too few rows to fill the machine
+  const uint64_t target_ctas = (uint64_t)ctx->sms * 8;
+  uint32_t nsplit = 1;
+  if (nrows < target_ctas) {
+    uint64_t want = (target_ctas + nrows - 1) / nrows;
+    const uint64_t max_split = (len + 8191) / 8192;  // at least 8192 elements per CTA
+    if (want > max_split) want = max_split;
+    if (want > 1024) want = 1024;  // the second pass then always takes the lane-group kernel
+    nsplit = (uint32_t)(want < 1 ? 1 : want);
+  }
+  uint64_t seg = (len + nsplit - 1) / nsplit;
+  seg = (seg + 3) & ~3ull;
+  nsplit = (uint32_t)((len + seg - 1) / seg);
+  const uint64_t jobs = (uint64_t)nrows * nsplit;
+  const unsigned grid = (unsigned)(jobs < target_ctas * 4 ? jobs : target_ctas * 4);
+  if (nsplit == 1) {
+    reduce_rows_block<OP><<<grid, RB_BLOCK, 0, ctx->stream>>>(in, out, nrows, len, 1, seg);
+    return vkp_after_launch(ctx, "reduce_rows_block");
+  }
+  void* ws;
+  VKP_TRY(vkp_workspace(ctx, 0, jobs * sizeof(float), &ws));
+  reduce_rows_block<OP><<<grid, RB_BLOCK, 0, ctx->stream>>>(in, (float*)ws, nrows, len, nsplit, seg);
+  VKP_TRY(vkp_after_launch(ctx, "reduce_rows_block"));
+  return reduce_rows<OP>(ctx, (const float*)ws, out, nrows, nsplit);
+}
+
+template <int OP>
+int reduce_axis(vkp_ctx* ctx, const float* in, float* out, uint32_t prev, uint32_t axis, uint32_t post) {
+  if ((uint64_t)prev * post == 0) return VKP_OK;
+  if (post == 1) return reduce_rows<OP>(ctx, in, out, prev, axis);
+  const bool vec = (post % 4 == 0) && ((((uintptr_t)in) & 15) == 0) && ((((uintptr_t)out) & 15) == 0);
+  const uint32_t cols = vec ? post / 4 : post;
+  uint32_t bx = 1;
+  while (bx < 32 && bx < cols) bx <<= 1;
+  if (cols >= 64 && !vec) bx = 64;
+  const uint32_t by = 256 / bx;
+  const uint32_t ctile = bx * (vec ? 4 : 1);
+  const uint32_t ntile = (post + ctile - 1) / ctile;
+  const uint64_t base_jobs = (uint64_t)prev * ntile;
+  const uint64_t target_ctas = (uint64_t)ctx->sms * 8;
+  uint32_t nsplit = 1;
+  if (base_jobs < target_ctas) {
+    uint64_t want = (target_ctas + base_jobs - 1) / base_jobs;
+    const uint64_t max_split = (axis + by * 8 - 1) / (by * 8);  // >= 8 rows per thread
+    if (want > max_split) want = max_split;
+    nsplit = (uint32_t)(want < 1 ? 1 : want);
+  }
+  const uint32_t seg = (axis + nsplit - 1) / nsplit;
+  nsplit = seg ? (axis + seg - 1) / seg : 1;
+  if (nsplit < 1) nsplit = 1;
+  const uint64_t jobs = base_jobs * nsplit;
+  const unsigned grid = (unsigned)(jobs < target_ctas * 4 ? jobs : target_ctas * 4);
+  float* dst = out;
+  if (nsplit > 1) {
+    void* ws;
+    VKP_TRY(vkp_workspace(ctx, 0, (uint64_t)prev * nsplit * post * sizeof(float), &ws));
+    dst = (float*)ws;
+  }
+  dim3 block(bx, by);
+  if (vec)
+    reduce_cols<OP, 4><<<grid, block, 0, ctx->stream>>>(in, dst, prev, axis, post, nsplit, seg);
+  else
+    reduce_cols<OP, 1><<<grid, block, 0, ctx->stream>>>(in, dst, prev, axis, post, nsplit, seg);
+  VKP_TRY(vkp_after_launch(ctx, "reduce_cols"));
+  if (nsplit > 1) {
+    // second pass over [prev, nsplit, post]; nsplit is small so it never splits again
+    const uint64_t jobs2 = base_jobs;
+    const unsigned grid2 = (unsigned)(jobs2 < target_ctas * 4 ? jobs2 : target_ctas * 4);
+    if (vec)
+      reduce_cols<OP, 4><<<grid2, block, 0, ctx->stream>>>(dst, out, prev, nsplit, post, 1, nsplit);
+    else
+      reduce_cols<OP, 1><<<grid2, block, 0, ctx->stream>>>(dst, out, prev, nsplit, post, 1, nsplit);
+    VKP_TRY(vkp_after_launch(ctx, "reduce_cols(pass2)"));
+  }
+  return VKP_OK;
+}
+
+template <int OP>
+int reduce_dispatch(vkp_ctx* ctx, int fam, void* const* bufs, int nbuf, const void* params, size_t pbytes) {
+  switch (fam) {
+    case VKF_REDUCE: {  // A, B ; MultiVector<2>{sizeA, sizeB}
+      VKP_CHECK(nbuf == 2 && pbytes == sizeof(vkp_multivector2_params), "reduce: bad arguments");
+      const auto* p = static_cast<const vkp_multivector2_params*>(params);
+      if (p->size[1] == 0) return VKP_OK;
+      if (p->size[1] == 1) return reduce_rows<OP>(ctx, (const float*)bufs[0], (float*)bufs[1], 1, p->size[0]);
+      const unsigned blocks = (p->size[1] * 32u + 255u) / 256u;
+      reduce_strided<OP><<<blocks, 256, 0, ctx->stream>>>((const float*)bufs[0], (float*)bufs[1], p->size[0], p->size[1]);
+      return vkp_after_launch(ctx, "reduce_strided");
+    }
+    case VKF_REDUCE_SG: {  // A, B ; Vector{size}: whole array -> B[0]
+      VKP_CHECK(nbuf == 2 && pbytes == sizeof(vkp_vector_params), "reduce(v1.3): bad arguments");
+      const auto* p = static_cast<const vkp_vector_params*>(params);
+      return reduce_rows<OP>(ctx, (const float*)bufs[0], (float*)bufs[1], 1, p->size);
+    }
+    case VKF_REDUCE_AXIS: {  // A [prev,axis,post], B [prev,post]
+      VKP_CHECK(nbuf == 2 && pbytes == sizeof(vkp_axisreduction_params), "axis reduce: bad arguments");
+      const auto* p = static_cast<const vkp_axisreduction_params*>(params);
+      return reduce_axis<OP>(ctx, (const float*)bufs[0], (float*)bufs[1], p->prev_prod, p->axis_size, p->post_prod);
+    }
+    case VKF_REDUCE_AXIS_RB: {  // A [prev,axis,post], B same shape
+      VKP_CHECK(nbuf == 2 && pbytes == sizeof(vkp_axisreduction_params), "axis reduce: bad arguments");
+      const auto* p = static_cast<const vkp_axisreduction_params*>(params);
+      const uint64_t nout = (uint64_t)p->prev_prod * p->post_prod;
+      if (nout == 0 || p->axis_size == 0) return VKP_OK;
+      void* ws;  // reduced values; slot 1 (slot 0 may hold split partials)
+      VKP_TRY(vkp_workspace(ctx, 1, nout * sizeof(float), &ws));
+      float* red = static_cast<float*>(ws);
+      VKP_TRY(reduce_axis<OP>(ctx, (const float*)bufs[0], red, p->prev_prod, p->axis_size, p->post_prod));
+      return vkp_broadcast_copy_3d(ctx, red, (float*)bufs[1], p->prev_prod, p->axis_size, p->post_prod);
+    }
+  }
+  return vkp_set_error("vkp_launch_reduce: unknown family %d", fam);
+}
+
+}  // namespace
+
+int vkp_launch_reduce(vkp_ctx* ctx, int fam, int sub, void* const* bufs, int nbuf, const void* params,
+                      size_t pbytes) {
+  switch (sub) {
+    case VKR_SUM: return reduce_dispatch<VKR_SUM>(ctx, fam, bufs, nbuf, params, pbytes);
+    case VKR_PROD: return reduce_dispatch<VKR_PROD>(ctx, fam, bufs, nbuf, params, pbytes);
+    case VKR_MAX: return reduce_dispatch<VKR_MAX>(ctx, fam, bufs, nbuf, params, pbytes);
+    case VKR_MIN: return reduce_dispatch<VKR_MIN>(ctx, fam, bufs, nbuf, params, pbytes);
+  }
+  return vkp_set_error("vkp_launch_reduce: unknown reduction %d", sub);
+}

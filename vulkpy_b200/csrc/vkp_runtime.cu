@@ -1,0 +1,421 @@
+// vkp_runtime.cu -- context, stream-ordered managed-memory pool, jobs (pooled events), timers.
+//
+// Replaces class GPU / Buffer<T> / Job of the reference (vulkpy/_vkarray.cc:38-130,392-574).
+// Design differences (B200-first):
+//   * one in-order, non-blocking CUDA stream per device instead of a command pool + fence per op
+//     and a host-side wait on every dependency (_vkarray.cc:412-438);
+//   * buffers come from a size-bucketed pool of cudaMallocManaged blocks kept resident in HBM;
+//     the host sees the same pointer (reference: HOST_VISIBLE|HOST_COHERENT mapped buffers,
+//     _vkarray.cc:61-72) and pages migrate only when the host really touches them;
+//   * a Job is a pooled cudaEvent recorded after the op.
+#include "vkp_common.cuh"
+
+#include <chrono>
+#include <thread>
+
+static thread_local char g_err[1024] = "";
+
+int vkp_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return VKP_ERR;
+}
+
+static std::mutex g_ctx_mu;
+static vkp_ctx* g_ctx_by_device[64] = {nullptr};
+
+extern "C" int vkp_abi_version(void) { return VKP_ABI_VERSION; }
+extern "C" const char* vkp_last_error(void) { return g_err; }
+
+extern "C" int vkp_device_count(int* count) {
+  VKP_CHECK(count != nullptr, "vkp_device_count: null argument");
+  VKP_CUDA(cudaGetDeviceCount(count));
+  return VKP_OK;
+}
+
+int vkp_make_current(vkp_ctx* ctx) {
+  VKP_CUDA(cudaSetDevice(ctx->device));
+  return VKP_OK;
+}
+
+extern "C" int vkp_ctx_create(int device, float priority, vkp_ctx** out) {
+  VKP_CHECK(out != nullptr, "vkp_ctx_create: null argument");
+  std::lock_guard<std::mutex> g(g_ctx_mu);
+  int n = 0;
+  VKP_CUDA(cudaGetDeviceCount(&n));
+  VKP_CHECK(n > 0, "no CUDA device visible: the vulkpy B200 backend has no CPU fallback");
+  VKP_CHECK(device >= 0 && device < n && device < 64, "GPU index %d out of range (%d devices)", device, n);
+  if (g_ctx_by_device[device]) {  // GPU(idx) objects with the same index share one context
+    g_ctx_by_device[device]->refcount++;
+    *out = g_ctx_by_device[device];
+    return VKP_OK;
+  }
+  VKP_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  VKP_CUDA(cudaGetDeviceProperties(&prop, device));
+  VKP_CHECK(prop.major >= 10,
+            "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+            prop.major, prop.minor);
+  int concurrent = 0;
+  VKP_CUDA(cudaDeviceGetAttribute(&concurrent, cudaDevAttrConcurrentManagedAccess, device));
+  VKP_CHECK(concurrent, "device %d lacks concurrent managed access (needed for the host view)", device);
+  vkp_ctx* ctx = new vkp_ctx();
+  ctx->device = device;
+  ctx->sms = prop.multiProcessorCount;
+  int lo = 0, hi = 0;
+  VKP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = least priority (numerically largest)
+  float p = priority < 0.f ? 0.f : (priority > 1.f ? 1.f : priority);
+  int prio = lo + (int)((hi - lo) * p);
+  VKP_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio));
+  g_ctx_by_device[device] = ctx;
+  *out = ctx;
+  return VKP_OK;
+}
+
+static int sync_locked(vkp_ctx* ctx) {
+  uint64_t s = ctx->seq;
+  VKP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (s > ctx->done_seq) ctx->done_seq = s;
+  return VKP_OK;
+}
+
+extern "C" int vkp_ctx_sync(vkp_ctx* ctx) {
+  VKP_CHECK(ctx, "vkp_ctx_sync: null context");
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  return sync_locked(ctx);
+}
+
+static int trim_locked(vkp_ctx* ctx) {
+  VKP_TRY(sync_locked(ctx));
+  for (auto& kv : ctx->free_lists) {
+    for (vkp_block* b : kv.second) {
+      ctx->blocks.erase(b->ptr);
+      cudaFree(b->ptr);
+      ctx->pooled_bytes -= b->bytes;
+      delete b;
+    }
+    kv.second.clear();
+  }
+  return VKP_OK;
+}
+
+extern "C" int vkp_ctx_trim(vkp_ctx* ctx) {
+  VKP_CHECK(ctx, "vkp_ctx_trim: null context");
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  return trim_locked(ctx);
+}
+
+extern "C" int vkp_ctx_destroy(vkp_ctx* ctx) {
+  if (!ctx) return VKP_OK;
+  {
+    std::lock_guard<std::mutex> g(g_ctx_mu);
+    if (--ctx->refcount > 0) return VKP_OK;
+    // The context of a device stays cached for the life of the process: arrays that are
+    // still alive (NumPy views keep their buffer) may outlive every GPU object.
+    ctx->refcount = 0;
+  }
+  return VKP_OK;
+}
+
+extern "C" int vkp_ctx_device(vkp_ctx* ctx, int* device) {
+  VKP_CHECK(ctx && device, "vkp_ctx_device: null argument");
+  *device = ctx->device;
+  return VKP_OK;
+}
+
+extern "C" int vkp_ctx_sm_count(vkp_ctx* ctx, int* sms) {
+  VKP_CHECK(ctx && sms, "vkp_ctx_sm_count: null argument");
+  *sms = ctx->sms;
+  return VKP_OK;
+}
+
+extern "C" int vkp_ctx_set_debug_sync(vkp_ctx* ctx, int enable) {
+  VKP_CHECK(ctx, "vkp_ctx_set_debug_sync: null context");
+  ctx->debug_sync = enable != 0;
+  return VKP_OK;
+}
+
+extern "C" int vkp_ctx_launch_count(vkp_ctx* ctx, uint64_t* kernels) {
+  VKP_CHECK(ctx && kernels, "vkp_ctx_launch_count: null argument");
+  *kernels = ctx->kernel_launches;
+  return VKP_OK;
+}
+
+extern "C" int vkp_ctx_mem_info(vkp_ctx* ctx, size_t* pooled, size_t* live) {
+  VKP_CHECK(ctx, "vkp_ctx_mem_info: null context");
+  if (pooled) *pooled = ctx->pooled_bytes;
+  if (live) *live = ctx->live_bytes;
+  return VKP_OK;
+}
+
+// ---- allocator ------------------------------------------------------------------------
+static size_t size_class(size_t bytes) {
+  if (bytes < 512) return 512;
+  if (bytes <= (1u << 20)) {  // next power of two up to 1 MiB
+    size_t s = 512;
+    while (s < bytes) s <<= 1;
+    return s;
+  }
+  const size_t two_mib = 2u << 20;  // 2 MiB pages: keep large blocks page-granular
+  return (bytes + two_mib - 1) / two_mib * two_mib;
+}
+
+extern "C" int vkp_alloc(vkp_ctx* ctx, size_t bytes, void** ptr) {
+  VKP_CHECK(ctx && ptr, "vkp_alloc: null argument");
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  const size_t cls = size_class(bytes);
+  auto it = ctx->free_lists.find(cls);
+  if (it != ctx->free_lists.end() && !it->second.empty()) {
+    vkp_block* b = it->second.back();
+    it->second.pop_back();
+    b->in_use = true;
+    ctx->live_bytes += b->bytes;
+    *ptr = b->ptr;
+    return VKP_OK;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMallocManaged(&p, cls, cudaMemAttachGlobal);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    // release cached blocks and retry once
+    VKP_TRY(trim_locked(ctx));
+    e = cudaMallocManaged(&p, cls, cudaMemAttachGlobal);
+    if (e != cudaSuccess)
+      return vkp_set_error("cudaMallocManaged(%zu bytes) failed: %s", cls, cudaGetErrorString(e));
+  }
+  // populate the pages in HBM now; kernels then run at full rate without GPU page faults
+  VKP_CUDA(cudaMemPrefetchAsync(p, cls, ctx->device, ctx->stream));
+  vkp_block* b = new vkp_block();
+  b->ptr = p;
+  b->bytes = cls;
+  b->in_use = true;
+  ctx->blocks[p] = b;
+  ctx->pooled_bytes += cls;
+  ctx->live_bytes += cls;
+  *ptr = p;
+  return VKP_OK;
+}
+
+extern "C" int vkp_free(vkp_ctx* ctx, void* ptr) {
+  if (!ptr) return VKP_OK;
+  VKP_CHECK(ctx, "vkp_free: null context");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  auto it = ctx->blocks.find(ptr);
+  VKP_CHECK(it != ctx->blocks.end() && it->second->in_use, "vkp_free: %p is not a live buffer", ptr);
+  vkp_block* b = it->second;
+  b->in_use = false;
+  b->guard_seq = ctx->seq;  // kernels enqueued so far may still read or write it
+  ctx->live_bytes -= b->bytes;
+  ctx->free_lists[b->bytes].push_back(b);
+  return VKP_OK;
+}
+
+int vkp_prepare_buffers(vkp_ctx* ctx, void* const* bufs, int nbuf) {
+  for (int i = 0; i < nbuf; i++) {
+    if (!bufs[i]) continue;
+    auto it = ctx->blocks.find(bufs[i]);
+    if (it == ctx->blocks.end()) continue;
+    vkp_block* b = it->second;
+    if (b->host_dirty) {
+      VKP_CUDA(cudaMemPrefetchAsync(b->ptr, b->bytes, ctx->device, ctx->stream));
+      b->host_dirty = false;
+    }
+  }
+  return VKP_OK;
+}
+
+static int take_event(vkp_ctx* ctx, cudaEvent_t* ev) {
+  if (!ctx->event_pool.empty()) {
+    *ev = ctx->event_pool.back();
+    ctx->event_pool.pop_back();
+    return VKP_OK;
+  }
+  VKP_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+  return VKP_OK;
+}
+
+int vkp_finish_op(vkp_ctx* ctx, vkp_job** job) {
+  ctx->seq++;
+  if (job) {
+    cudaEvent_t ev;
+    VKP_TRY(take_event(ctx, &ev));
+    VKP_CUDA(cudaEventRecord(ev, ctx->stream));
+    vkp_job* j = new vkp_job{ctx, ev, ctx->seq};
+    *job = j;
+  }
+  return VKP_OK;
+}
+
+int vkp_after_launch(vkp_ctx* ctx, const char* what) {
+  ctx->kernel_launches++;
+  cudaError_t e = cudaPeekAtLastError();
+  if (e == cudaSuccess && ctx->debug_sync) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return vkp_set_error("kernel %s failed: %s", what, cudaGetErrorString(e));
+  }
+  return VKP_OK;
+}
+
+int vkp_workspace(vkp_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (bytes > ctx->workspace_bytes[slot]) {
+    if (ctx->workspace[slot]) {
+      VKP_CUDA(cudaStreamSynchronize(ctx->stream));
+      VKP_CUDA(cudaFree(ctx->workspace[slot]));
+      ctx->workspace[slot] = nullptr;
+      ctx->workspace_bytes[slot] = 0;
+    }
+    size_t want = bytes < (8u << 20) ? (8u << 20) : bytes;
+    VKP_CUDA(cudaMalloc(&ctx->workspace[slot], want));
+    ctx->workspace_bytes[slot] = want;
+  }
+  *out = ctx->workspace[slot];
+  return VKP_OK;
+}
+
+// ---- host <-> buffer ------------------------------------------------------------------
+extern "C" int vkp_upload(vkp_ctx* ctx, void* dst, const void* src_host, size_t bytes) {
+  VKP_CHECK(ctx && (bytes == 0 || (dst && src_host)), "vkp_upload: null argument");
+  if (bytes == 0) return VKP_OK;
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  void* bufs[1] = {dst};
+  VKP_TRY(vkp_prepare_buffers(ctx, bufs, 1));
+  // stream-ordered: earlier kernels that still use a recycled block finish first
+  VKP_CUDA(cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyDefault, ctx->stream));
+  ctx->seq++;
+  return VKP_OK;
+}
+
+extern "C" int vkp_download(vkp_ctx* ctx, void* dst_host, const void* src, size_t bytes) {
+  VKP_CHECK(ctx && (bytes == 0 || (dst_host && src)), "vkp_download: null argument");
+  if (bytes == 0) return VKP_OK;
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  VKP_CUDA(cudaMemcpyAsync(dst_host, src, bytes, cudaMemcpyDefault, ctx->stream));
+  ctx->seq++;
+  return sync_locked(ctx);
+}
+
+extern "C" int vkp_host_acquire(vkp_ctx* ctx, void* ptr, size_t bytes, int mode) {
+  VKP_CHECK(ctx && ptr, "vkp_host_acquire: null argument");
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  auto it = ctx->blocks.find(ptr);
+  VKP_CHECK(it != ctx->blocks.end(), "vkp_host_acquire: %p is not a buffer of this context", ptr);
+  vkp_block* b = it->second;
+  const bool prefetch = (mode & 1) != 0, writing = (mode & 2) != 0;
+  bool need_sync = b->guard_seq > ctx->done_seq;       // earlier tenant of a recycled block
+  if (writing && ctx->seq > ctx->done_seq) need_sync = true;  // readers of this array in flight
+  if (prefetch && !b->host_dirty && bytes > 0) {
+    size_t nbytes = bytes < b->bytes ? bytes : b->bytes;
+    VKP_CUDA(cudaMemPrefetchAsync(ptr, nbytes, cudaCpuDeviceId, ctx->stream));
+    ctx->seq++;
+    need_sync = true;
+  }
+  if (need_sync) VKP_TRY(sync_locked(ctx));
+  b->guard_seq = 0;
+  b->host_dirty = true;
+  return VKP_OK;
+}
+
+extern "C" int vkp_host_alloc(size_t bytes, void** ptr) {
+  VKP_CHECK(ptr, "vkp_host_alloc: null argument");
+  VKP_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
+  return VKP_OK;
+}
+
+extern "C" int vkp_host_free(void* ptr) {
+  if (ptr) VKP_CUDA(cudaFreeHost(ptr));
+  return VKP_OK;
+}
+
+// ---- jobs -------------------------------------------------------------------------------
+extern "C" int vkp_job_wait(vkp_job* job, uint64_t timeout_ns) {
+  VKP_CHECK(job, "vkp_job_wait: null job");
+  vkp_ctx* ctx = job->ctx;
+  if (ctx->done_seq >= job->seq) return VKP_OK;
+  VKP_TRY(vkp_make_current(ctx));
+  if (timeout_ns == UINT64_MAX) {
+    cudaError_t e = cudaEventSynchronize(job->ev);
+    if (e != cudaSuccess) return vkp_set_error("Error at Command Wait: %s", cudaGetErrorString(e));
+  } else {
+    auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+      cudaError_t e = cudaEventQuery(job->ev);
+      if (e == cudaSuccess) break;
+      if (e != cudaErrorNotReady) {
+        cudaGetLastError();
+        return vkp_set_error("Error at Command Wait: %s", cudaGetErrorString(e));
+      }
+      auto dt = std::chrono::duration_cast<std::chrono::nanoseconds>(
+                    std::chrono::steady_clock::now() - t0).count();
+      if ((uint64_t)dt >= timeout_ns) {
+        vkp_set_error("Timeout at Command Wait");
+        return VKP_TIMEOUT;
+      }
+      std::this_thread::yield();
+    }
+  }
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (job->seq > ctx->done_seq) ctx->done_seq = job->seq;
+  return VKP_OK;
+}
+
+extern "C" int vkp_job_done(vkp_job* job, int* done) {
+  VKP_CHECK(job && done, "vkp_job_done: null argument");
+  if (job->ctx->done_seq >= job->seq) { *done = 1; return VKP_OK; }
+  cudaError_t e = cudaEventQuery(job->ev);
+  if (e == cudaSuccess) { *done = 1; return VKP_OK; }
+  if (e == cudaErrorNotReady) { *done = 0; return VKP_OK; }
+  cudaGetLastError();
+  return vkp_set_error("cudaEventQuery failed: %s", cudaGetErrorString(e));
+}
+
+extern "C" int vkp_job_release(vkp_job* job) {
+  if (!job) return VKP_OK;
+  vkp_ctx* ctx = job->ctx;
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->event_pool.push_back(job->ev);  // re-recording a pooled event is legal
+  }
+  delete job;
+  return VKP_OK;
+}
+
+// ---- timers -------------------------------------------------------------------------------
+extern "C" int vkp_timer_create(vkp_ctx* ctx, vkp_timer** out) {
+  VKP_CHECK(ctx && out, "vkp_timer_create: null argument");
+  VKP_TRY(vkp_make_current(ctx));
+  cudaEvent_t ev;
+  VKP_CUDA(cudaEventCreate(&ev));
+  *out = new vkp_timer{ctx, ev};
+  return VKP_OK;
+}
+
+extern "C" int vkp_timer_record(vkp_timer* t) {
+  VKP_CHECK(t, "vkp_timer_record: null timer");
+  VKP_TRY(vkp_make_current(t->ctx));
+  VKP_CUDA(cudaEventRecord(t->ev, t->ctx->stream));
+  return VKP_OK;
+}
+
+extern "C" int vkp_timer_elapsed_ms(vkp_timer* start, vkp_timer* stop, float* ms) {
+  VKP_CHECK(start && stop && ms, "vkp_timer_elapsed_ms: null argument");
+  VKP_TRY(vkp_make_current(stop->ctx));
+  VKP_CUDA(cudaEventSynchronize(stop->ev));
+  VKP_CUDA(cudaEventElapsedTime(ms, start->ev, stop->ev));
+  return VKP_OK;
+}
+
+extern "C" int vkp_timer_destroy(vkp_timer* t) {
+  if (!t) return VKP_OK;
+  cudaEventDestroy(t->ev);
+  delete t;
+  return VKP_OK;
+}

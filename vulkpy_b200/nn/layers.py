@@ -1,0 +1,114 @@
+"""
+Layers (reference: vulkpy/nn/layers.py).
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, Optional
+
+from ..vkarray import GPU, Array, DataShape, BatchAffineParams
+from .core import Module, Optimizer, Regularizer
+from .parameters import Parameter
+from .initializers import HeNormal
+
+__all__ = ["Dense", "ReLU", "Sigmoid", "Softmax"]
+
+Init = Callable[[GPU, Iterable[int]], Array]
+
+
+class Dense(Module):
+    """Fully connected layer ``y = x W^T + b`` with ``W`` of shape ``(output_dim, input_dim)``
+    (reference: layers.py:18-155)."""
+
+    def __init__(self, gpu: GPU, input_dim: int, output_dim: int, *,
+                 w_init: Optional[Init] = None, b_init: Optional[Init] = None,
+                 w_opt: Optional[Optimizer] = None, b_opt: Optional[Optimizer] = None,
+                 w_reg: Optional[Regularizer] = None, b_reg: Optional[Regularizer] = None):
+        self.input_dim = int(input_dim)
+        self.output_dim = int(output_dim)
+        if w_init is None:
+            w_init = HeNormal(gpu, self.input_dim)
+        self.w = Parameter(gpu, shape=(self.output_dim, self.input_dim), initializer=w_init,
+                           opt=w_opt, regularizer=w_reg)
+        self.b = Parameter(gpu, shape=(self.output_dim,), initializer=b_init, opt=b_opt,
+                           regularizer=b_reg)
+
+    def forward(self, x: Array) -> Array:
+        """One ``batch_affine`` kernel: GEMM with the bias added in its epilogue
+        (reference: layers.py:71-102, batch_affine.comp:25-39)."""
+        batch = x.shape[0]
+        y = Array(x._gpu, shape=(batch, self.output_dim))
+        y.job = x._gpu._submit("batch_affine", 1, 64, 1, [self.w.value, self.b.value, x, y],
+                               DataShape(batch, self.output_dim, 1),
+                               BatchAffineParams(batch, x.shape[1], self.output_dim))
+        y._keep.extend([self.w.value, self.b.value, x])
+        return y
+
+    def backward(self, dy: Array) -> Array:
+        """db = sum_batch dy, dW = dy^T x, dx = dy W.
+
+        The reference forms dW by materialising ``dy[:, :, None] * x[:, None, :]``
+        (batch x out x in) and summing over the batch (layers.py:126-141); the same
+        contraction is one GEMM here."""
+        self.b.add_grad(dy.sum(axis=0))
+        x = self._x
+        dev = dy._gpu.gpu
+        dW = Array(dy._gpu, shape=(self.output_dim, self.input_dim))
+        dW.job = dev.gemm(True, False, self.output_dim, self.input_dim, dy.shape[0],
+                          dy.buffer, x.buffer, dW.buffer)
+        dW._keep = [dy, x]
+        self.w.add_grad(dW)
+        return dy @ self.w.value
+
+    def zero_grad(self):
+        self.w.zero_grad()
+        self.b.zero_grad()
+
+    def update(self):
+        self.w.update()
+        self.b.update()
+
+
+class ReLU(Module):
+    """max(x, 0); backward passes dy where the output is positive (reference: layers.py:158-210)."""
+
+    def forward(self, x: Array) -> Array:
+        return x.max(0.0)
+
+    def backward(self, dy: Array) -> Array:
+        dx = self._y.sign()
+        dx.max(0.0, inplace=True)
+        dx *= dy
+        return dx
+
+
+class Sigmoid(Module):
+    """1 / (1 + exp(-x)) (reference: layers.py:213-267)."""
+
+    def forward(self, x: Array) -> Array:
+        y = 0.0 - x
+        y.exp(inplace=True)
+        y += 1.0
+        return 1.0 / y
+
+    def backward(self, dy: Array) -> Array:
+        dx = 1.0 - self._y
+        dx *= self._y
+        dx *= dy
+        return dx
+
+
+class Softmax(Module):
+    """Row-wise softmax over axis 1 with the max subtracted first; backward uses the diagonal
+    of the Jacobian only, like the reference (layers.py:270-323)."""
+
+    def forward(self, x: Array) -> Array:
+        e = x - x.maximum(axis=1, rebroadcast=True)
+        e.exp(inplace=True)
+        e /= e.sum(axis=1, rebroadcast=True)
+        return e
+
+    def backward(self, dy: Array) -> Array:
+        dx = 1.0 - self._y
+        dx *= self._y
+        dx *= dy
+        return dx

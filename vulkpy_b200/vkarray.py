@@ -1,0 +1,527 @@
+"""
+Array core of the B200 backend (:mod:`vulkpy_b200.vkarray`)
+
+Same public surface as the reference's ``vulkpy.vkarray`` (reference: vulkpy/vkarray.py):
+``GPU``, ``Array`` (float32), ``U32Array`` / ``Shape`` (uint32) and ``zeros``.  Every operator
+allocates its result, enqueues ONE kernel on the device's in-order stream through
+``GPU._submit`` and returns immediately; the result carries the producing ``job`` and keeps
+its inputs alive in ``_keep`` until ``wait()`` (reference job model: vkarray.py:139-161).
+
+Differences that are supersets of the reference behaviour:
+in-place broadcasting follows NumPy for any rank (Q1), full reductions are correct for any
+size (Q2), ``__setitem__`` waits for pending work first (Q5) and ``a[:] = scalar`` is a device
+fill instead of a host loop (Q17).
+"""
+from __future__ import annotations
+
+import logging
+from typing import Iterable, List, Optional, Tuple, Union
+
+import numpy as np
+
+from . import _backend as _b
+from ._backend import (  # re-exported: nn code imports these from here (nn/layers.py:9)
+    createGPU, DataShape, Job, Buffer, Shape as U32Buffer,
+    VectorParams, MultiVector2Params, VectorScalarParams, VectorScalar2Params, MatMulParams,
+    AxisReductionParams, BroadcastParams, Multi3BroadcastParams, BatchAffineParams,
+    AxisGatherParams, VectorRangeParams,
+)
+from .vktyping import Resource
+
+__all__ = ["GPU", "U32Array", "Shape", "Array", "zeros"]
+
+logger = logging.getLogger("vulkpy")
+
+# host reads of at least this many bytes migrate in one bulk prefetch instead of page faults
+_PREFETCH_BYTES = 64 * 1024
+
+
+# op id -> index of the first shape binding (add_broadcast.comp binding 3, iadd_broadcast.comp
+# binding 2, broadcast.comp bindings 2-3)
+_SHAPE_BINDING = {}
+for _name, _id in list(_b.OPS.items()):
+    if _name == "broadcast" or (_name.endswith("_broadcast") and _name.startswith("i")):
+        _SHAPE_BINDING[_id] = 2
+    elif _name.endswith("_broadcast"):
+        _SHAPE_BINDING[_id] = 3
+
+
+def _full_slice(key) -> bool:
+    if key is Ellipsis:
+        return True
+    if isinstance(key, slice):
+        return key.start is None and key.stop is None and key.step is None
+    if isinstance(key, tuple):
+        return all(_full_slice(k) for k in key)
+    return False
+
+
+class GPU:
+    """
+    One B200 (reference: vkarray.py:68-137).
+
+    ``GPU(idx)`` selects CUDA device ``idx``; objects with the same index compare equal and
+    share one context / stream.
+    """
+
+    def __init__(self, idx: int = 0, priority: float = 0.0):
+        self._idx = idx
+        self.gpu = createGPU(idx, priority)
+        self.canSubgroupArithmetic = self.gpu.canSubgroupArithmetic()
+        logger.info("GPU %d: CUDA sm_100a backend, %d SMs", idx, self.gpu.sm_count())
+
+    def __eq__(self, other: object):
+        if not isinstance(other, GPU):
+            return NotImplemented
+        return self._idx == other._idx
+
+    def __hash__(self):
+        return hash(("vulkpy.GPU", self._idx))
+
+    def _submit(self, spv, local_size_x: int, local_size_y: int, local_size_z: int,
+                arrays: Iterable, shape, params) -> Job:
+        """Enqueue kernel ``spv`` over ``arrays`` (reference: vkarray.py:110-119).
+
+        Dependencies need no host-side wait: the stream is in order.  Bindings may be
+        ``Array``/``U32Array`` objects or, for broadcast shape bindings, host uint32 arrays.
+        """
+        infos = []
+        for a in arrays:
+            if isinstance(a, _GPUArray):
+                infos.append(a.buffer)
+            elif isinstance(a, np.ndarray):
+                infos.append(a)
+            else:
+                infos.append(a._info())
+        op = spv if isinstance(spv, int) else _b.op_id(spv)
+        first_shape = _SHAPE_BINDING.get(op)
+        if first_shape is not None:
+            # shape bindings are consumed on the host at submit time; accept Shape arrays too
+            arrays = list(arrays)
+            for i in range(first_shape, len(infos)):
+                if isinstance(infos[i], _b._BufferBase):
+                    arrays[i].wait()
+                    infos[i] = np.array(arrays[i].array, dtype=np.uint32).reshape(-1)
+        return self.gpu.submit(op, local_size_x, local_size_y, local_size_z, infos, shape, params)
+
+    def flush(self, arrays: Iterable["_GPUArray"]):
+        """No-op: host writes to managed memory are coherent (reference: vkarray.py:121-130)."""
+        self.gpu.flush([a.buffer.range() for a in arrays])
+
+    def wait(self):
+        """Wait for everything enqueued on this GPU."""
+        self.gpu.wait()
+
+
+class _GPUArray(Resource):
+    """Job / keep-alive / host-view plumbing shared by Array and U32Array."""
+    _np_dtype = np.float32
+
+    def __init__(self, gpu: GPU):
+        self._gpu: GPU = gpu
+        self.job: Optional[Job] = None
+        self._keep: List[Resource] = []
+        self._view: Optional[np.ndarray] = None
+
+    def _alloc(self, data, shape):
+        dev = self._gpu.gpu
+        if data is not None:
+            host = np.asarray(data)
+            self.shape = host.shape
+            host = np.ascontiguousarray(host, dtype=self._np_dtype)
+            self.buffer = self._create(dev, host.size)
+            if host.size:
+                self.buffer.upload(host.reshape(-1))
+        else:
+            if shape is None:
+                raise ValueError("`data` or `shape` must not be `None`.")
+            self.shape = tuple(int(s) for s in np.asarray(shape, dtype=int).reshape(-1))
+            self.buffer = self._create(dev, int(np.prod(self.shape, dtype=np.int64)))
+
+    def wait(self):
+        """Wait for the job that writes this array."""
+        job = self.job
+        if job is not None:
+            job.wait()
+            self.job = None
+        self._keep = []
+
+    def flush(self):
+        self._gpu.flush([self])
+
+    def _info(self):
+        return self.buffer.info()
+
+    # -- host view --------------------------------------------------------------------------
+    def _host(self, prefetch: bool, write: bool = False) -> np.ndarray:
+        self.buffer.host_acquire(prefetch and self.buffer.nbytes >= _PREFETCH_BYTES, write)
+        v = self._view
+        if v is None:
+            v = np.asarray(self.buffer)
+            v.shape = self.shape
+            self._view = v
+        return v
+
+    @property
+    def array(self) -> np.ndarray:
+        """Live NumPy view of the buffer (reference attribute ``array``: vkarray.py:430-431)."""
+        return self._host(False)
+
+    def __getitem__(self, key):
+        self.wait()
+        return self._host(True)[key]
+
+    def __setitem__(self, key, value):
+        if not isinstance(value, _GPUArray) and _full_slice(key) and np.ndim(value) == 0:
+            # whole-array scalar assignment: device fill, ordered on the stream
+            bits = int(np.asarray(value, dtype=self._np_dtype).view(np.uint32))
+            self.job = self._gpu.gpu.fill(self.buffer, bits)
+            self._keep = []
+            return
+        self.wait()
+        self._host(False, write=True)[key] = value
+
+    def __repr__(self) -> str:
+        return f"<{self.__class__.__name__}(shape={tuple(self.shape)})>"
+
+    def __str__(self) -> str:
+        self.wait()
+        return str(self._host(True))
+
+    def __array__(self, dtype=None, copy=None) -> np.ndarray:
+        self.wait()
+        v = self._host(True)
+        if dtype is not None and np.dtype(dtype) != v.dtype:
+            return v.astype(dtype)
+        return v.copy() if copy else v
+
+    def _set_shape(self, shape):
+        shape = tuple(int(s) for s in (shape if np.ndim(shape) else (shape,)))
+        n = self.buffer.size()
+        if shape.count(-1) == 1:
+            rest = -int(np.prod(shape, dtype=np.int64))
+            if rest > 0 and n % rest == 0:
+                shape = tuple(n // rest if s == -1 else s for s in shape)
+        if any(s < 0 for s in shape) or int(np.prod(shape, dtype=np.int64)) != n:
+            raise ValueError(f"cannot reshape array of size {n} into shape {shape}")
+        self.shape = shape
+        if self._view is not None:
+            self._view = self._view.reshape(shape)
+
+
+class U32Array(_GPUArray):
+    """uint32 array for indices / labels / shapes (reference: vkarray.py:191-257)."""
+    _np_dtype = np.uint32
+
+    def __init__(self, gpu: GPU, *, data: Optional[Iterable[int]] = None,
+                 shape: Optional[Iterable[int]] = None):
+        super().__init__(gpu)
+        if data is None and shape is None:
+            raise ValueError("One of `data` or `shape` must be specified.")
+        self._alloc(data, shape)
+
+    @staticmethod
+    def _create(dev, n):
+        return dev.createU32Buffer(n)
+
+    def to_onehot(self, num_classes: int) -> "Array":
+        """Rows of the identity selected by the labels (reference: vkarray.py:239-253)."""
+        return Array(self._gpu, data=np.identity(num_classes, dtype=np.float32)).gather(self, axis=0)
+
+
+class Shape(U32Array):
+    """uint32 vector holding a shape (reference: vkarray.py:259-278)."""
+
+    def __init__(self, gpu: GPU, *, data: Optional[Iterable[int]] = None, ndim: Optional[int] = None):
+        super().__init__(gpu, data=data, shape=(ndim,) if ndim is not None else None)
+
+
+_BINARY = ("add", "sub", "mul", "div", "max", "min", "pow")
+_UNARY = ("abs", "sign", "sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh",
+          "asinh", "acosh", "atanh", "exp", "log", "exp2", "log2", "sqrt", "invsqrt")
+_REDUCE = ("sum", "prod", "maximum", "minimum")
+
+Scalar = Union[int, float]
+
+
+class Array(_GPUArray):
+    """float32 device array (reference: vkarray.py:281-1521)."""
+
+    def __init__(self, gpu: GPU, *, data=None, shape: Optional[Iterable[int]] = None):
+        super().__init__(gpu)
+        self._alloc(data, shape)
+
+    @staticmethod
+    def _create(dev, n):
+        return dev.createBuffer(n)
+
+    # -- submit helpers -----------------------------------------------------------------------
+    def _check_shape(self, other):
+        if tuple(self.shape) != tuple(other.shape):
+            raise ValueError(f"Incompatible shapes: {self.shape} vs {other.shape}")
+
+    def _new(self, shape=None) -> "Array":
+        return Array(self._gpu, shape=self.shape if shape is None else shape)
+
+    def _run(self, ret: "Array", spv: str, arrays, params, keep) -> "Array":
+        n = ret.buffer.size()
+        ret.job = self._gpu._submit(spv, 64, 1, 1, arrays, DataShape(n, 1, 1), params)
+        ret._keep = keep
+        return ret
+
+    def _op(self, other, name: str) -> "Array":
+        """Out-of-place binary op: same shape, scalar or broadcast (reference: vkarray.py:492-519)."""
+        n = self.buffer.size()
+        if not isinstance(other, Array):
+            ret = self._new()
+            return self._run(ret, name + "_scalar", [self, ret], VectorScalarParams(n, float(other)), [self])
+        if tuple(self.shape) == tuple(other.shape):
+            ret = self._new()
+            return self._run(ret, name, [self, other, ret], VectorParams(n), [self, other])
+        shape = np.broadcast_shapes(self.shape, other.shape)  # ValueError if incompatible
+        ndim = len(shape)
+        sh = np.ones(3 * ndim, dtype=np.uint32)
+        sh[ndim - len(self.shape):ndim] = self.shape
+        sh[2 * ndim - len(other.shape):2 * ndim] = other.shape
+        sh[2 * ndim:] = shape
+        ret = self._new(shape)
+        p = Multi3BroadcastParams(n, other.buffer.size(), ret.buffer.size(), ndim)
+        return self._run(ret, name + "_broadcast", [self, other, ret, sh], p, [self, other])
+
+    def _iop(self, other, name: str) -> "Array":
+        """In-place binary op (reference: vkarray.py:533-559; NumPy rules for any rank, Q1)."""
+        n = self.buffer.size()
+        if not isinstance(other, Array):
+            return self._run(self, "i" + name + "_scalar", [self], VectorScalarParams(n, float(other)), [])
+        if tuple(self.shape) == tuple(other.shape):
+            return self._run(self, "i" + name, [self, other], VectorParams(n), [other])
+        shape = np.broadcast_shapes(self.shape, other.shape)
+        if tuple(shape) != tuple(self.shape):
+            raise ValueError(f"Incompatible shape. {shape} vs {self.shape}")
+        ndim = len(shape)
+        sh = np.ones(2 * ndim, dtype=np.uint32)
+        sh[:ndim] = shape
+        if len(other.shape) > 0:
+            sh[2 * ndim - len(other.shape):] = other.shape
+        p = BroadcastParams(n, other.buffer.size(), ndim)
+        return self._run(self, "i" + name + "_broadcast", [self, other, sh], p, [other])
+
+    def _rop(self, other: Scalar, name: str) -> "Array":
+        ret = self._new()
+        return self._run(ret, name + "_scalar", [self, ret], VectorScalarParams(self.buffer.size(), float(other)),
+                         [self])
+
+    def _unary(self, name: str, inplace: bool) -> "Array":
+        p = VectorParams(self.buffer.size())
+        if inplace:
+            return self._run(self, "i" + name, [self], p, [])
+        ret = self._new()
+        return self._run(ret, name, [self, ret], p, [self])
+
+    # -- arithmetic operators (reference: vkarray.py:521-583, 1100-1108) -------------------------
+    def __add__(self, other): return self._op(other, "add")
+    def __sub__(self, other): return self._op(other, "sub")
+    def __mul__(self, other): return self._op(other, "mul")
+    def __truediv__(self, other): return self._op(other, "div")
+    def __pow__(self, other): return self._op(other, "pow")
+    def __iadd__(self, other): return self._iop(other, "add")
+    def __isub__(self, other): return self._iop(other, "sub")
+    def __imul__(self, other): return self._iop(other, "mul")
+    def __itruediv__(self, other): return self._iop(other, "div")
+    def __ipow__(self, other): return self._iop(other, "pow")
+    def __radd__(self, other): return self._rop(other, "add")
+    def __rsub__(self, other): return self._rop(other, "rsub")
+    def __rmul__(self, other): return self._rop(other, "mul")
+    def __rtruediv__(self, other): return self._rop(other, "rdiv")
+    def __rpow__(self, other): return self._rop(other, "rpow")
+
+    def max(self, other: Union["Array", float], inplace: bool = False) -> "Array":
+        """Element-wise maximum with an array (broadcast) or a scalar."""
+        return self._iop(other, "max") if inplace else self._op(other, "max")
+
+    def min(self, other: Union["Array", float], inplace: bool = False) -> "Array":
+        """Element-wise minimum with an array (broadcast) or a scalar."""
+        return self._iop(other, "min") if inplace else self._op(other, "min")
+
+    def __matmul__(self, other: "Array") -> "Array":
+        """1-D / 2-D matrix product, fp32 (reference: vkarray.py:585-605)."""
+        if len(self.shape) > 3 or len(other.shape) > 3 or self.shape[-1] != other.shape[0]:
+            raise ValueError(f"Incompatible shapes: {self.shape} vs {other.shape}")
+        shape = tuple(self.shape)[:-1] + tuple(other.shape)[1:]
+        if len(shape) == 0:
+            shape = (1,)
+        rowA = self.shape[0] if len(self.shape) > 1 else 1
+        contract = self.shape[-1]
+        colB = other.shape[1] if len(other.shape) > 1 else 1
+        ret = self._new(shape)
+        ret.job = self._gpu._submit("matmul", 1, 64, 1, [self, other, ret], DataShape(rowA, colB, 1),
+                                    MatMulParams(rowA, contract, colB))
+        ret._keep = [self, other]
+        return ret
+
+    def reshape(self, shape: Iterable[int]):
+        """Reshape in place; ``ValueError`` if the size does not match (reference: vkarray.py:607-622)."""
+        self._set_shape(shape)
+
+    # -- clamp (reference: vkarray.py:1110-1191) ---------------------------------------------------
+    def clamp(self, min: Union["Array", float], max: Union["Array", float], inplace: bool = False) -> "Array":
+        """``min(max(x, lo), hi)`` with array (broadcast) or scalar bounds."""
+        lo, hi = min, max
+        lo_arr, hi_arr = isinstance(lo, Array), isinstance(hi, Array)
+        src = self
+        if lo_arr or hi_arr:
+            shapes = [self.shape] + ([lo.shape] if lo_arr else []) + ([hi.shape] if hi_arr else [])
+            shape = tuple(np.broadcast_shapes(*shapes))
+            if shape != tuple(self.shape):
+                if inplace:
+                    raise ValueError("Incompatible shape")
+                src = self.broadcast_to(shape)
+            if lo_arr and tuple(lo.shape) != shape:
+                lo = lo.broadcast_to(shape)
+            if hi_arr and tuple(hi.shape) != shape:
+                hi = hi.broadcast_to(shape)
+        n = src.buffer.size()
+        ret = self if inplace else src._new()
+        tail = [] if inplace else [ret]
+        pre = "i" if inplace else ""
+        keep = [] if inplace else [src]
+        if lo_arr and hi_arr:
+            return src._run(ret, pre + "clamp", [src, lo, hi] + tail, VectorParams(n), keep + [lo, hi])
+        if hi_arr:
+            return src._run(ret, pre + "clamp_sv", [src, hi] + tail, VectorScalarParams(n, float(lo)), keep + [hi])
+        if lo_arr:
+            return src._run(ret, pre + "clamp_vs", [src, lo] + tail, VectorScalarParams(n, float(hi)), keep + [lo])
+        return src._run(ret, pre + "clamp_ss", [src] + tail, VectorScalar2Params(n, float(lo), float(hi)), keep)
+
+    # -- reductions (reference: vkarray.py:1194-1432) -----------------------------------------------
+    def _norm_axis(self, axis) -> List[int]:
+        nd = len(self.shape)
+        ax = np.unique(np.asarray(axis, dtype=int).reshape(-1))
+        out = sorted({int(a) + nd if a < 0 else int(a) for a in ax}, reverse=True)
+        for a in out:
+            if not 0 <= a < nd:
+                raise ValueError(f"axis {a} is out of bounds for array of dimension {nd}")
+        return out
+
+    def _reduce(self, name: str, axis, keepdims: bool, rebroadcast: bool) -> "Array":
+        if rebroadcast:
+            if not isinstance(axis, (int, np.integer)):
+                raise ValueError("When `rebroadcast` is specified, `axis` must be `int`")
+            (a,) = self._norm_axis(axis)
+            prev = int(np.prod(self.shape[:a], dtype=np.int64))
+            post = int(np.prod(self.shape[a + 1:], dtype=np.int64))
+            ret = self._new()
+            ret.job = self._gpu._submit(name + "_axis_rebroadcast", 1, 64, 1, [self, ret],
+                                        DataShape(prev, post, 1),
+                                        AxisReductionParams(prev, int(self.shape[a]), post))
+            ret._keep = [self]
+            return ret
+        if axis is None:
+            # one launch pair replaces the reference's log64(n) dependent jobs (vkarray.py:1246-1274)
+            ret = self._new((1,))
+            n = self.buffer.size()
+            ret.job = self._gpu._submit(name, 64, 1, 1, [self, ret], DataShape(64, 1, 1),
+                                        MultiVector2Params(n, 1))
+            ret._keep = [self]
+            if keepdims:
+                ret.reshape((1,) * len(self.shape))
+            return ret
+        axes = self._norm_axis(axis)
+        tmp = self
+        for a in axes:  # descending, one pass per axis like the reference (vkarray.py:1194-1222)
+            prev = int(np.prod(tmp.shape[:a], dtype=np.int64))
+            post = int(np.prod(tmp.shape[a + 1:], dtype=np.int64))
+            ret = self._new(tuple(tmp.shape[:a]) + tuple(tmp.shape[a + 1:]))
+            ret.job = self._gpu._submit(name + "_axis", 1, 64, 1, [tmp, ret], DataShape(prev, post, 1),
+                                        AxisReductionParams(prev, int(tmp.shape[a]), post))
+            ret._keep = [tmp]
+            tmp = ret
+        if keepdims:
+            shape = list(self.shape)
+            for a in axes:
+                shape[a] = 1
+            tmp.reshape(shape)
+        return tmp
+
+    def sum(self, axis=None, keepdims: bool = False, rebroadcast: bool = False) -> "Array":
+        """Sum over all elements, one axis or several axes."""
+        return self._reduce("sum", axis, keepdims, rebroadcast)
+
+    def prod(self, axis=None, keepdims: bool = False, rebroadcast: bool = False) -> "Array":
+        """Product over all elements, one axis or several axes."""
+        return self._reduce("prod", axis, keepdims, rebroadcast)
+
+    def maximum(self, axis=None, keepdims: bool = False, rebroadcast: bool = False) -> "Array":
+        """Maximum over all elements, one axis or several axes."""
+        return self._reduce("maximum", axis, keepdims, rebroadcast)
+
+    def minimum(self, axis=None, keepdims: bool = False, rebroadcast: bool = False) -> "Array":
+        """Minimum over all elements, one axis or several axes."""
+        return self._reduce("minimum", axis, keepdims, rebroadcast)
+
+    def mean(self, axis=None, keepdims: bool = False, rebroadcast: bool = False) -> "Array":
+        """Mean = sum, then one scalar rescale exactly as the reference does (vkarray.py:1420-1432)."""
+        n_before = self.buffer.size()
+        ret = self.sum(axis, keepdims, rebroadcast)
+        if rebroadcast:
+            (a,) = self._norm_axis(axis)
+            ret /= self.shape[a]
+        else:
+            ret *= (ret.buffer.size() / n_before)
+        return ret
+
+    # -- broadcast / gather (reference: vkarray.py:1434-1521) ----------------------------------------
+    def broadcast_to(self, shape: Iterable[int]) -> "Array":
+        """Materialise the array broadcast to ``shape``; ``ValueError`` if not broadcastable."""
+        shape = tuple(int(s) for s in np.asarray(shape, dtype=int).reshape(-1))
+        if tuple(np.broadcast_shapes(self.shape, shape)) != shape:
+            raise ValueError(f"Cannot broadcast to {shape}")
+        ret = self._new(shape)
+        shA = np.ones(len(shape), dtype=np.uint32)
+        if len(self.shape):
+            shA[len(shape) - len(self.shape):] = self.shape
+        shB = np.asarray(shape, dtype=np.uint32)
+        p = BroadcastParams(self.buffer.size(), ret.buffer.size(), len(shape))
+        return self._run(ret, "broadcast", [self, ret, shA, shB], p, [self])
+
+    def gather(self, indices: U32Array, axis: Optional[int] = None) -> "Array":
+        """``a.flat[indices]`` or, with ``axis``, ``take(a, indices, axis)`` with the index
+        dimensions leading: result shape ``indices.shape + prev + post``."""
+        size = indices.buffer.size()
+        if axis is None:
+            ret = self._new(indices.shape)
+            ret.job = self._gpu._submit("gather", 64, 1, 1, [self, indices, ret], DataShape(size, 1, 1),
+                                        VectorParams(size))
+        else:
+            (a,) = self._norm_axis(axis)
+            prev_shape, post_shape = tuple(self.shape[:a]), tuple(self.shape[a + 1:])
+            ret = self._new(tuple(indices.shape) + prev_shape + post_shape)
+            prev = int(np.prod(prev_shape, dtype=np.int64))
+            post = int(np.prod(post_shape, dtype=np.int64))
+            ret.job = self._gpu._submit("gather_axis", 1, 64, 1, [self, indices, ret],
+                                        DataShape(prev, post, size),
+                                        AxisGatherParams(prev, post, int(self.shape[a]), size))
+        ret._keep = [self, indices]
+        return ret
+
+
+def _install_unary(name: str):
+    def method(self, inplace: bool = False) -> Array:
+        return self._unary(name, inplace)
+    method.__name__ = name
+    method.__qualname__ = f"Array.{name}"
+    method.__doc__ = (f"Element-wise ``{name}`` (reference shader {name}.comp / i{name}.comp). "
+                      "With ``inplace=True`` the array is overwritten and returned.")
+    setattr(Array, name, method)
+
+
+for _n in _UNARY:
+    _install_unary(_n)
+del _n
+
+
+def zeros(gpu: GPU, shape: Iterable[int]) -> Array:
+    """Zero-initialised array (reference: vkarray.py:1524-1542); the fill runs on the device."""
+    z = Array(gpu, shape=shape)
+    z[:] = 0.0
+    return z
