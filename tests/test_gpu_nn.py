@@ -1,0 +1,239 @@
+"""GPU tests of vulkpy.nn (layers, losses, optimizers, regularizers, Sequence): known answers in
+the style of the reference's test/test_nn.py with its tolerances (rtol = atol = 1e-7 against
+float64 for activations and losses) plus oracle-backed checks of Dense and of a training step."""
+import numpy as np
+import pytest
+
+import vulkpy_b200 as vk
+from vulkpy_b200 import nn
+from vulkpy_b200.nn.parameters import Parameter
+from oracle import vulkpy_oracle as orc
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+TOL = dict(rtol=1e-7, atol=1e-7)
+
+
+def A(gpu, x):
+    return vk.Array(gpu, data=x)
+
+
+def softmax64(x):
+    e = np.exp(x - x.max(axis=1, keepdims=True))
+    return e / e.sum(axis=1, keepdims=True)
+
+
+def test_relu_sigmoid(gpu):
+    x = np.asarray([[-0.2, 0.0, 0.2], [1.5, -3.0, 0.1]])
+    relu = nn.ReLU()
+    np.testing.assert_allclose(relu(A(gpu, x)), np.maximum(x, 0), **TOL)
+    dy = np.asarray([[0.7, 0.8, 0.9], [1.0, 1.1, 1.2]])
+    np.testing.assert_allclose(relu.backward(A(gpu, dy)), dy * (x > 0), **TOL)
+    sig = nn.Sigmoid()
+    y = 1 / (1 + np.exp(-x))
+    np.testing.assert_allclose(sig(A(gpu, x)), y, **TOL)
+    np.testing.assert_allclose(sig.backward(A(gpu, dy)), dy * y * (1 - y), **TOL)
+    with pytest.raises(ValueError):
+        relu(A(gpu, [1, 2, 3]))       # modules need at least 2-D input (core.py:247-275)
+
+
+def test_softmax(gpu):
+    sm = nn.Softmax()
+    x = np.asarray([[1.0, 1.0]])
+    np.testing.assert_allclose(sm(A(gpu, x)), [[0.5, 0.5]], **TOL)
+    x = np.asarray([[0.0, 100.0]])
+    np.testing.assert_allclose(sm(A(gpu, x)), [[0.0, 1.0]], **TOL)
+    x = np.asarray([[0.1, 0.7, -1.3, 2.0], [3.0, 3.0, 2.0, -8.0]])
+    y = softmax64(x)
+    np.testing.assert_allclose(sm(A(gpu, x)), y, **TOL)
+    dy = np.asarray([[0.1, 0.2, 0.3, 0.4], [1.0, -1.0, 0.5, 2.0]])
+    # diagonal of the Jacobian only, as the reference (layers.py:302-323)
+    np.testing.assert_allclose(sm.backward(A(gpu, dy)), dy * y * (1 - y), **TOL)
+
+
+def test_dense_forward_known_answers(gpu):
+    d = nn.Dense(gpu, 2, 3, w_init=nn.Constant(0.0), b_init=nn.Constant(0.0))
+    np.testing.assert_allclose(d(A(gpu, [[1, 2], [3, 4]])), np.zeros((2, 3)))
+    d = nn.Dense(gpu, 2, 3, w_init=nn.Constant(0.0), b_init=nn.Constant(1.5))
+    np.testing.assert_allclose(d(A(gpu, [[1, 2], [3, 4]])), np.full((2, 3), 1.5))
+    d = nn.Dense(gpu, 2, 2, w_init=lambda g, s: vk.Array(g, data=[[1, 2], [3, 4]]), b_init=nn.Constant(0.5))
+    np.testing.assert_allclose(d(A(gpu, [[1, 1], [2, 0]])), [[3.5, 7.5], [2.5, 6.5]])
+
+
+def test_dense_backward_known_answers(gpu):
+    W = np.asarray([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]])           # (out=2, in=3)
+    d = nn.Dense(gpu, 3, 2, w_init=lambda g, s: vk.Array(g, data=W), b_init=nn.Constant(0.0),
+                 w_opt=nn.SGD(0.1), b_opt=nn.SGD(0.1))
+    x = np.asarray([[1.0, 0.0, -1.0], [2.0, 1.0, 0.5]])
+    dy = np.asarray([[1.0, -1.0], [0.5, 2.0]])
+    d(A(gpu, x))
+    dx = d.backward(A(gpu, dy))
+    np.testing.assert_allclose(dx, dy @ W, rtol=1e-6)
+    np.testing.assert_allclose(d.w.grad, dy.T @ x, rtol=1e-6)
+    np.testing.assert_allclose(d.b.grad, dy.sum(axis=0), rtol=1e-6)
+    assert d._x.shape == (2, 3)
+    d.update()
+    np.testing.assert_allclose(d.w.value, W - 0.1 * (dy.T @ x), rtol=1e-6)
+    d.zero_grad()
+    np.testing.assert_array_equal(np.asarray(d.w.grad), np.zeros((2, 3)))
+
+
+def test_dense_vs_oracle(gpu, rs):
+    w = rs.normal(size=(37, 53)).astype(F)
+    b = rs.normal(size=37).astype(F)
+    x = rs.normal(size=(29, 53)).astype(F)
+    d = nn.Dense(gpu, 53, 37, w_init=lambda g, s: vk.Array(g, data=w), b_init=lambda g, s: vk.Array(g, data=b))
+    np.testing.assert_allclose(d(A(gpu, x)), orc.batch_affine(w, b, x), rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("reduce", ["mean", "sum"])
+def test_cross_entropy(gpu, reduce):
+    x = np.asarray([[0.5, 0.5], [0.2, 0.8], [0.9, 0.1]])
+    y = np.asarray([[1.0, 0.0], [0.0, 1.0], [1.0, 0.0]])
+    L = nn.CrossEntropyLoss(reduce=reduce)
+    want = -(y * np.log(x + 1e-8)).sum(axis=1)
+    want = want.mean() if reduce == "mean" else want.sum()
+    np.testing.assert_allclose(L(A(gpu, x), A(gpu, y)), want, rtol=1e-6)
+    g = -y / (x + 1e-8)
+    np.testing.assert_allclose(L.grad(), g / 3 if reduce == "mean" else g, rtol=1e-6)
+    np.testing.assert_allclose(nn.CrossEntropyLoss()(A(gpu, [[0.5, 0.5]]), A(gpu, [[1, 0]])), 0.6931472, rtol=1e-6)
+
+
+@pytest.mark.parametrize("reduce", ["mean", "sum"])
+def test_softmax_cross_entropy(gpu, reduce):
+    x = np.asarray([[1.0, 2.0, 3.0], [1.0, 1.0, 1.0]])
+    y = np.asarray([[0.0, 0.0, 1.0], [1.0, 0.0, 0.0]])
+    L = nn.SoftmaxCrossEntropyLoss(reduce=reduce)
+    p = softmax64(x)
+    want = -(y * np.log(p + 1e-8)).sum(axis=1)
+    want = want.mean() if reduce == "mean" else want.sum()
+    np.testing.assert_allclose(L(A(gpu, x), A(gpu, y)), want, rtol=1e-6)
+    g = p - y
+    np.testing.assert_allclose(L.grad(), g / 2 if reduce == "mean" else g, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("reduce", ["mean", "sum"])
+def test_mse_and_huber(gpu, reduce):
+    x = np.asarray([[1.0, 2.0], [0.5, -3.0], [4.0, 4.0]])
+    y = np.asarray([[1.5, 0.0], [0.5, -1.0], [0.0, 4.5]])
+    red = (lambda v: v.mean()) if reduce == "mean" else (lambda v: v.sum())
+    scale = 1 / 3 if reduce == "mean" else 1.0
+    L = nn.MSELoss(reduce=reduce)
+    np.testing.assert_allclose(L(A(gpu, x), A(gpu, y)), red(((y - x) ** 2).sum(axis=1)), **TOL)
+    np.testing.assert_allclose(L.grad(), 2 * (x - y) * scale, rtol=1e-6)
+    H = nn.HuberLoss(reduce=reduce)
+    d = np.abs(y - x)
+    np.testing.assert_allclose(H(A(gpu, x), A(gpu, y)), red((0.5 * np.minimum(d, d ** 2)).sum(axis=1)), rtol=1e-6)
+    np.testing.assert_allclose(H.grad(), np.clip(x - y, -1, 1) * scale, rtol=1e-6)
+
+
+def test_mix_loss(gpu):
+    x, y = A(gpu, [[1.0, 2.0]]), A(gpu, [[0.0, 0.0]])
+    m = nn.MixLoss([(0.5, nn.MSELoss()), (2.0, nn.HuberLoss())])
+    np.testing.assert_allclose(m(x, y), 0.5 * 5.0 + 2.0 * (0.5 * (1 + 2)), rtol=1e-6)
+    np.testing.assert_allclose(m.grad(), 0.5 * np.asarray([[2.0, 4.0]]) + 2.0 * np.asarray([[1.0, 1.0]]), rtol=1e-6)
+    with pytest.raises(ValueError):
+        nn.MixLoss([])
+
+
+def test_optimizers(gpu):
+    g = A(gpu, [1.0, -2.0, 0.5])
+    np.testing.assert_allclose(nn.SGD(0.01).init_state((3,)).grad2diff(g), [-0.01, 0.02, -0.005], rtol=1e-6)
+    ada = nn.AdaGrad(gpu, lr=0.1, tau=0.0, eps=1e-8).init_state((3,))
+    np.testing.assert_allclose(ada.grad2diff(g), [-0.1, 0.1, -0.1], rtol=1e-5)
+    np.testing.assert_allclose(ada.h, [1.0, 4.0, 0.25], rtol=1e-6)
+    st = nn.Adam(gpu, lr=0.001).init_state((3,))
+    d1 = np.asarray(st.grad2diff(g)).copy()
+    np.testing.assert_allclose(d1, [-0.001, 0.001, -0.001], rtol=1e-4)   # first step: -lr * sign(g)
+    np.testing.assert_allclose(st.m, 0.1 * np.asarray([1.0, -2.0, 0.5]), rtol=1e-6)
+    np.testing.assert_allclose(st.v, 0.001 * np.asarray([1.0, 4.0, 0.25]), rtol=1e-5)
+    assert abs(st.beta1t - 0.9) < 1e-12 and abs(st.beta2t - 0.999) < 1e-12
+
+
+def test_adam_matches_float32_restatement(gpu, rs):
+    """Every intermediate of optimizers.py:235-253 is rounded to float32 where the reference does."""
+    g = rs.normal(size=257).astype(F)
+    st = nn.Adam(gpu, lr=1e-3).init_state((257,))
+    m = np.zeros(257, F)
+    v = np.zeros(257, F)
+    b1t = b2t = 1.0
+    for _ in range(3):
+        got = np.asarray(st.grad2diff(A(gpu, g))).copy()
+        m = (m * F(0.9)).astype(F)
+        m = (m + (g * F(1 - 0.9)).astype(F)).astype(F)
+        v = (v * F(0.999)).astype(F)
+        v = (v + (orc.scalar("pow", g, 2.0) * F(1 - 0.999)).astype(F)).astype(F)
+        b1t *= 0.9
+        b2t *= 0.999
+        mhat = (m / F(1 - b1t)).astype(F)
+        vhat = (v / F(1 - b2t)).astype(F)
+        vhat = (np.sqrt(vhat).astype(F) + F(1e-8)).astype(F)
+        want = ((mhat * F(-1e-3)).astype(F) / vhat).astype(F)
+        np.testing.assert_array_equal(got, want)
+
+
+def test_parameter_and_regularizers(gpu):
+    p = Parameter(gpu, shape=(2, 2), opt=nn.SGD(0.5), initializer=nn.Constant(1.0), regularizer=nn.Ridge(0.1))
+    assert p.is_trainable()
+    p.add_grad(A(gpu, [[1, 2], [3, 4]]))
+    p.regular_grad()                    # + 2 * 0.1 * value
+    np.testing.assert_allclose(p.grad, [[1.2, 2.2], [3.2, 4.2]], rtol=1e-6)
+    np.testing.assert_allclose(p.regular_loss(), [0.4], rtol=1e-6)
+    p.update()
+    np.testing.assert_allclose(p.value, 1 - 0.5 * np.asarray([[1.2, 2.2], [3.2, 4.2]]), rtol=1e-6)
+    p.zero_grad()
+    np.testing.assert_array_equal(np.asarray(p.grad), np.zeros((2, 2)))
+    q = Parameter(gpu, shape=(2,), trainable=False)
+    assert not q.is_trainable() and q.opt_state is None
+    np.testing.assert_allclose(q.regular_loss(), [0.0])
+    w = A(gpu, [-2.0, 0.0, 3.0])
+    np.testing.assert_allclose(nn.Lasso(2.0).loss(w), [10.0])
+    np.testing.assert_allclose(nn.Lasso(2.0).grad(w), [-2.0, 0.0, 2.0])
+    np.testing.assert_allclose(nn.Ridge(0.5).loss(w), [6.5])
+    np.testing.assert_allclose(nn.Ridge(0.5).grad(w), [-2.0, 0.0, 3.0])
+    np.testing.assert_allclose(nn.Elastic(1.0, 1.0).loss(w), [18.0])
+    np.testing.assert_allclose(nn.Elastic(1.0, 1.0).grad(w), [-5.0, 0.0, 7.0])
+
+
+def test_sequence_trains(gpu, rs):
+    opt = nn.Adam(gpu, lr=1e-2)
+    net = nn.Sequence([nn.Dense(gpu, 4, 32, w_opt=opt, b_opt=opt), nn.ReLU(),
+                       nn.Dense(gpu, 32, 3, w_opt=opt, b_opt=opt), nn.Softmax()], nn.CrossEntropyLoss())
+    x = rs.normal(size=(96, 4)).astype(F)
+    labels = (x[:, 0] > 0).astype(np.uint32) + (x[:, 1] > 0.5).astype(np.uint32)
+    X, Y = A(gpu, x), vk.U32Array(gpu, data=labels).to_onehot(3)
+    _, first = net.train(X, Y)
+    first = float(np.asarray(first).reshape(-1)[0])
+    for _ in range(60):
+        pred, loss = net.train(X, Y)
+    last = float(np.asarray(loss).reshape(-1)[0])
+    assert last < 0.6 * first
+    p, l2 = net.predict(X, Y)
+    assert np.asarray(p).shape == (96, 3) and np.asarray(net.predict(X)).shape == (96, 3)
+    np.testing.assert_allclose(np.asarray(p).sum(axis=1), np.ones(96), rtol=1e-5)
+    acc = (np.asarray(p).argmax(axis=1) == labels).mean()
+    assert acc > 0.7
+
+
+def test_one_training_step_matches_float64_model(gpu, rs):
+    """Forward + backward + SGD update of Dense-ReLU-Dense-Softmax/CE against a float64 NumPy model."""
+    W1, b1 = rs.normal(size=(16, 8)) * 0.5, rs.normal(size=16) * 0.1
+    W2, b2 = rs.normal(size=(4, 16)) * 0.5, rs.normal(size=4) * 0.1
+    x = rs.normal(size=(32, 8))
+    y = np.eye(4)[rs.integers(0, 4, 32)]
+    sgd = nn.SGD(0.1)
+    mk = lambda v: (lambda g, s: vk.Array(g, data=v))
+    d1 = nn.Dense(gpu, 8, 16, w_init=mk(W1), b_init=mk(b1), w_opt=sgd, b_opt=sgd)
+    d2 = nn.Dense(gpu, 16, 4, w_init=mk(W2), b_init=mk(b2), w_opt=sgd, b_opt=sgd)
+    net = nn.Sequence([d1, nn.ReLU(), d2, nn.Softmax()], nn.CrossEntropyLoss())
+    pred, loss = net.train(A(gpu, x), A(gpu, y))
+    h = np.maximum(x @ W1.T + b1, 0)
+    p = softmax64(h @ W2.T + b2)
+    np.testing.assert_allclose(pred, p, rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(loss, -(y * np.log(p + 1e-8)).sum(axis=1).mean(), rtol=2e-5)
+    dp = -y / (p + 1e-8) / 32
+    dz2 = dp * p * (1 - p)                      # the reference's diagonal softmax backward
+    np.testing.assert_allclose(d2.w.value, W2 - 0.1 * dz2.T @ h, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(d2.b.value, b2 - 0.1 * dz2.sum(axis=0), rtol=1e-4, atol=1e-5)
+    dz1 = (dz2 @ W2) * (h > 0)
+    np.testing.assert_allclose(d1.w.value, W1 - 0.1 * dz1.T @ x, rtol=1e-4, atol=1e-5)

@@ -1,0 +1,137 @@
+"""GPU parity of vulkpy.random.Xoshiro128pp: the uint32 stream, lane layout, tail chunks, state
+persistence and the [0,1) mapping are BIT-EXACT against the oracle / golden fixtures; Box-Muller
+within the stated tolerance.  Also the structural tests of the reference (test/test_random.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import vulkpy_b200 as vk
+from oracle import vulkpy_oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_docstring_vectors(gpu):
+    vec = json.load(open(os.path.join(GOLDEN, "reference_vectors.json")))
+    r = vk.random.Xoshiro128pp(gpu, seed=0)
+    np.testing.assert_array_equal(np.asarray(r.random(shape=(3,))), np.asarray(vec["random_3"], dtype=np.float32))
+    np.testing.assert_allclose(np.asarray(r.normal(shape=(3,))),
+                               np.asarray(vec["normal_3_after_random_3"], dtype=np.float32), rtol=3e-7)
+
+
+def test_golden_streams(gpu):
+    g = np.load(os.path.join(GOLDEN, "prng_streams.npz"))
+    groups = {}
+    for key in g.files:
+        size, seed = key.split("_")[0][1:], key.split("_")[1][4:]
+        groups.setdefault((int(size), int(seed)), []).append(key)
+    assert len(groups) >= 6
+    for (size, seed), keys in sorted(groups.items()):
+        r = vk.random.Xoshiro128pp(gpu, size, seed=seed)
+        calls = sorted((k for k in keys if "_call" in k), key=lambda k: int(k.split("_call")[1].split("_")[0]))
+        for k in calls:
+            kind, n = k.split("_")[-2], int(k.split("_")[-1])
+            out = r.randint(shape=(n,)) if kind == "u32" else r.random(shape=(n,))
+            np.testing.assert_array_equal(np.asarray(out), g[k], err_msg=k)
+        np.testing.assert_array_equal(r.rng.state(), g[f"s{size}_seed{seed}_final_state"])
+
+
+@pytest.mark.parametrize("size,n", [(64, 1), (64, 63), (64, 64), (64, 65), (64, 64 * 300), (64, 64 * 5000 + 33),
+                                    (2, 1001), (1, 300), (5, 1234), (96, 10 ** 5), (128, 128 * 4096 + 127),
+                                    (4096, 4096 * 600 + 1), (1 << 14, (1 << 22) + 12345)])
+def test_stream_bit_exact_vs_oracle(gpu, size, n):
+    r = vk.random.Xoshiro128pp(gpu, size, seed=77)
+    o = orc.Xoshiro128pp(size, 77)
+    np.testing.assert_array_equal(r.rng.state(), o.state)          # seeding incl. the jump quirk
+    np.testing.assert_array_equal(np.asarray(r.randint(shape=(n,))), o.randint(n))
+    np.testing.assert_array_equal(np.asarray(r.random(shape=(7,))), o.random(7))   # state carried over
+    np.testing.assert_array_equal(np.asarray(r.random(shape=(n,))), o.random(n))
+    np.testing.assert_array_equal(r.rng.state(), o.state)
+
+
+def test_literal_single_dispatch_shader(gpu):
+    """prng_xoshiro128pp_uint32 through vkp_submit: one draw per lane with a shift."""
+    from vulkpy_b200._backend import ShiftVectorParams, DataShape
+    st = vk.U32Array(gpu, data=orc.seed_states(64, 3).reshape(-1))
+    out = vk.U32Array(gpu, shape=(100,))
+    out[:] = 0
+    out.job = gpu._submit("prng_xoshiro128pp_uint32", 64, 1, 1, [st, out], DataShape(40, 1, 1), ShiftVectorParams(10, 40))
+    o = orc.Xoshiro128pp(64, 3)
+    want = np.zeros(100, np.uint32)
+    want[10:50] = orc.next_lanes(o.state, 40)
+    np.testing.assert_array_equal(np.asarray(out), want)
+    np.testing.assert_array_equal(np.asarray(st).reshape(64, 4), o.state)
+
+
+@pytest.mark.parametrize("size", [64, 2, 3, 256])
+@pytest.mark.parametrize("n", [1, 2, 3, 10, 11, 127, 128, 129, 100001, 100002])
+def test_normal_vs_oracle(gpu, size, n):
+    r = vk.random.Xoshiro128pp(gpu, size, seed=5)
+    o = orc.Xoshiro128pp(size, 5)
+    got = np.asarray(r.normal(shape=(n,), mean=1.5, stddev=2.0))
+    want = o.normal(n, 1.5, 2.0)
+    # fp32 log (CR), sqrt (IEEE), sin/cos (<= 2 ulp) with one rounding per shader operation
+    # (prng_box_muller.comp:26-31); the mean shifts the result, so compare absolutely
+    np.testing.assert_allclose(got, want, rtol=0, atol=4e-6)
+    # both consumed n (even) or n+1 (odd) uniforms: the streams stay in lock step
+    np.testing.assert_array_equal(np.asarray(r.randint(shape=(9,))), o.randint(9))
+
+
+def test_reference_structural_tests(gpu):
+    for shape in [(3,), (17,), (65,), (5, 5, 5)]:
+        a = vk.random.Xoshiro128pp(gpu).random(shape=shape)
+        a.wait()
+        v = np.asarray(a)
+        assert v.shape == shape and (0 <= v).all() and (v < 1.0).all()
+    a = np.asarray(vk.random.Xoshiro128pp(gpu, seed=0).random(shape=(5,)))
+    b = np.asarray(vk.random.Xoshiro128pp(gpu, seed=0).random(shape=(5,)))
+    np.testing.assert_array_equal(a, b)
+    buf = vk.Array(gpu, shape=(5,))
+    out = vk.random.Xoshiro128pp(gpu).random(buffer=buf)
+    assert out is buf and np.asarray(out).shape == (5,)
+    for n in (10, 11):
+        a1 = vk.random.Xoshiro128pp(gpu, seed=0).normal(shape=(n,))
+        a2 = vk.random.Xoshiro128pp(gpu, seed=0).normal(shape=(n,), mean=5, stddev=3)
+        np.testing.assert_allclose((a2 - 5) / a1, np.full((n,), 3), rtol=1e-5)
+    u = vk.random.Xoshiro128pp(gpu).randint(shape=(5,))
+    assert u.shape == (5,) and np.asarray(u).dtype == np.uint32
+    np.testing.assert_array_equal(np.asarray(vk.random.Xoshiro128pp(gpu).randrange(shape=(5,), low=3, high=4)), [3] * 5)
+    with pytest.raises(ValueError):
+        vk.random.Xoshiro128pp(gpu).random()
+    r = vk.random.Xoshiro128pp(gpu)
+    for kw in ({"low": -1}, {"high": 2 ** 32 + 1}, {"low": 5, "high": 5}):
+        with pytest.raises(ValueError):
+            r.randrange(shape=(3,), **kw)
+    with pytest.raises(ValueError):
+        r.randrange(low=1, high=9)
+
+
+def test_randrange_bit_exact(gpu):
+    for low, high in [(0, 10), (3, 1000), (100, 1 << 26), (0, 1 << 32)]:
+        r = vk.random.Xoshiro128pp(gpu, seed=9)
+        o = orc.Xoshiro128pp(64, 9)
+        np.testing.assert_array_equal(np.asarray(r.randrange(shape=(1000,), low=low, high=high)),
+                                      o.randrange(1000, low, high))
+
+
+def test_unfused_box_muller_ops(gpu):
+    """The two Box-Muller shaders through vkp_submit agree with the fused generator."""
+    base = vk.random.PRNG.normal
+    for n in (10, 11):
+        r1 = vk.random.Xoshiro128pp(gpu, seed=4)
+        r2 = vk.random.Xoshiro128pp(gpu, seed=4)
+        fused = np.asarray(r1.normal(shape=(n,), mean=0.5, stddev=1.5))
+        unfused = np.asarray(base(r2, shape=(n,), mean=0.5, stddev=1.5))
+        np.testing.assert_array_equal(fused, unfused)
+
+
+def test_he_normal_initializer(gpu):
+    # test/test_nn.py:18-27: HeNormal(seed) is Xoshiro128pp(seed).normal with stddev sqrt(2/in)
+    from vulkpy_b200 import nn
+    w = nn.HeNormal(gpu, 8, seed=3)(gpu, (4, 8))
+    ref = vk.random.Xoshiro128pp(gpu, seed=3).normal(shape=(4, 8), stddev=np.sqrt(2 / 8))
+    np.testing.assert_array_equal(np.asarray(w), np.asarray(ref))
+    np.testing.assert_allclose(np.asarray(nn.Constant(0.25)(gpu, (3, 2))), np.full((3, 2), 0.25))

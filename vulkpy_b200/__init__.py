@@ -18,5 +18,6 @@ from .vkarray import GPU, U32Array, Shape, Array, zeros
 from . import random
 from . import nn
 from . import util
+from ._backend import pinned_empty, device_count
 
 __version__ = "0.1.0"

@@ -289,6 +289,13 @@ extern "C" int vkp_upload(vkp_ctx* ctx, void* dst, const void* src_host, size_t 
   // stream-ordered: earlier kernels that still use a recycled block finish first
   VKP_CUDA(cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyDefault, ctx->stream));
   ctx->seq++;
+  // Contract: the source may be reused as soon as this returns (the reference's Buffer::set is a
+  // plain memcpy).  Pageable sources are already staged by the runtime; page-locked ones are
+  // read by DMA asynchronously, so wait for them.
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, src_host) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered)
+    return sync_locked(ctx);
+  cudaGetLastError();
   return VKP_OK;
 }
 

@@ -195,6 +195,18 @@ class _GPUArray(Resource):
             return v.astype(dtype)
         return v.copy() if copy else v
 
+    def to_host(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Copy the contents into host memory with one stream-ordered device-to-host transfer
+        (additive helper: unlike ``np.asarray(array)`` no managed page migrates, so the array
+        stays resident in HBM; pass a ``pinned_empty`` buffer as ``out`` for full PCIe rate)."""
+        if out is None:
+            out = np.empty(self.shape, dtype=self._np_dtype)
+        assert out.nbytes == self.buffer.nbytes and out.flags.c_contiguous
+        _b._check(_b.lib.vkp_download(self._gpu.gpu._ctx, out.ctypes.data, self.buffer.ptr, out.nbytes))
+        self.job = None
+        self._keep = []
+        return out
+
     def _set_shape(self, shape):
         shape = tuple(int(s) for s in (shape if np.ndim(shape) else (shape,)))
         n = self.buffer.size()
