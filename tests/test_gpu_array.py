@@ -193,8 +193,12 @@ def test_unary_vs_oracle_ragged(gpu, rs, name, n):
     x = rs.uniform(lo, hi, n).astype(F)
     got = np.asarray(getattr(A(gpu, x), name)())
     want = orc.unary(name, x)
-    if name in ("abs", "sign", "sqrt", "invsqrt"):
+    if name in ("abs", "sign", "sqrt"):
         np.testing.assert_array_equal(got, want)       # IEEE operations: bit exact
+    elif name == "invsqrt":
+        # 1 / sqrt(x) as two correctly rounded IEEE operations: <= 1 ulp from the CR value
+        np.testing.assert_allclose(got, want, rtol=1.2e-7, atol=0)
+        np.testing.assert_array_equal(got, (np.float32(1) / np.sqrt(x)).astype(F))
     elif name in ("exp", "log", "exp2", "log2"):
         # binary64 evaluation rounded once: <= 0.5001 ulp, i.e. at most 1 ulp from the CR value
         np.testing.assert_allclose(got, want, rtol=1.2e-7, atol=0)
@@ -332,7 +336,9 @@ def test_full_reduce_sizes(gpu, rs, n):
     if n <= 4096:  # where the reference's own multi-pass result is defined
         np.testing.assert_allclose(a.sum(), orc.reduce_full_reference("sum", x), rtol=n * 1.2e-7)
     y = rs.uniform(0.999, 1.001, n).astype(F)
-    np.testing.assert_allclose(A(gpu, y).prod(), [orc.reduce_full_exact("prod", y)], rtol=1e-4)
+    # n-1 float32 multiplications, each within 2^-24: observed drift ~1e-9 * n (NumPy's own
+    # float32 product drifts the same way); bound used here: n * 2^-26
+    np.testing.assert_allclose(A(gpu, y).prod(), [orc.reduce_full_exact("prod", y)], rtol=max(1e-5, n * 1.5e-8))
 
 
 def test_literal_strided_sum_shader(gpu, rs):

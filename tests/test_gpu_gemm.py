@@ -1,0 +1,104 @@
+"""tcgen05 3xTF32 GEMM (vkp_gemm) against float64 NumPy and against the SIMT fp32 kernel.
+
+Tolerance: each fp32 operand is split into two TF32 numbers with round-to-nearest
+(|x - hi - lo| <= 2^-22 |x|) and the lo*lo term is dropped (<= 2^-22 |a b|), so every product
+is within ~3 * 2^-22 = 7.2e-7 of exact; the tensor core then adds the products of a k-step into
+the fp32 TMEM accumulator with a truncating, exponent-aligned add (measured: up to ~4e-6 of
+sum|a||b| at K = 8192).  The reference accumulates serially in fp32 (matmul.comp:29-31; bound
+K * 2^-24 * sum|a||b|, i.e. 4.9e-4 at K = 8192).  Bound used here, element-wise:
+|C - C_exact| <= TOL * (|A| |B|) with TOL = 6e-6."""
+import numpy as np
+import pytest
+
+import vulkpy_b200 as vk
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+SIMT, TC, ACC = 1, 2, 4
+TOL = 6e-6
+
+
+def gemm(gpu, a, b, ta=False, tb=False, bias=None, flags=0, c0=None):
+    A, B = vk.Array(gpu, data=a), vk.Array(gpu, data=b)
+    M = a.shape[1] if ta else a.shape[0]
+    K = a.shape[0] if ta else a.shape[1]
+    N = b.shape[0] if tb else b.shape[1]
+    C = vk.Array(gpu, data=c0) if c0 is not None else vk.Array(gpu, shape=(M, N))
+    bb = vk.Array(gpu, data=bias) if bias is not None else None
+    C.job = gpu.gpu.gemm(ta, tb, M, N, K, A.buffer, B.buffer, C.buffer, bb.buffer if bb is not None else None, flags)
+    return np.asarray(C)
+
+
+def exact(a, b, ta, tb):
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    a64 = a64.T if ta else a64
+    b64 = b64.T if tb else b64
+    return a64 @ b64, np.abs(a64) @ np.abs(b64)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 64), (256, 128, 96), (128, 256, 128), (384, 512, 160),
+                                   (1024, 1024, 1024), (132, 260, 36), (1000, 136, 500), (4096, 256, 64)])
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
+def test_tc_gemm_vs_float64(gpu, rs, M, N, K, ta, tb):
+    a = rs.uniform(-1, 1, (K, M) if ta else (M, K)).astype(F)
+    b = rs.uniform(-1, 1, (N, K) if tb else (K, N)).astype(F)
+    got = gemm(gpu, a, b, ta, tb, flags=TC)
+    want, mag = exact(a, b, ta, tb)
+    err = np.abs(got - want) / mag
+    assert err.max() < TOL, err.max()
+    simt = gemm(gpu, a, b, ta, tb, flags=SIMT)
+    assert (np.abs(simt - want) / mag).max() < 2e-6
+    # the tensor core accumulates each k-step into TMEM with its own (truncating) fp32 add, so its
+    # error exceeds the FFMA kernel's by a small factor while staying far inside the bound above
+    assert np.abs(got - simt).max() < TOL * mag.max()
+
+
+def test_tc_gemm_bias_and_accumulate(gpu, rs):
+    M, N, K = 256, 384, 128
+    a = rs.normal(size=(M, K)).astype(F)
+    b = rs.normal(size=(N, K)).astype(F)
+    bias = rs.normal(size=N).astype(F)
+    c0 = rs.normal(size=(M, N)).astype(F)
+    want, mag = exact(a, b, False, True)
+    got = gemm(gpu, a, b, False, True, bias=bias, flags=TC)
+    assert (np.abs(got - (want + bias)) / (mag + 1)).max() < TOL
+    got = gemm(gpu, a, b, False, True, bias=bias, flags=TC | ACC, c0=c0)
+    assert (np.abs(got - (want + bias + c0)) / (mag + 2)).max() < TOL
+    got = gemm(gpu, a, b, False, True, flags=SIMT | ACC, c0=c0)
+    assert (np.abs(got - (want + c0)) / (mag + 1)).max() < 2e-6
+
+
+def test_tc_gemm_wide_dynamic_range(gpu, rs):
+    """3xTF32 keeps fp32 accuracy when magnitudes vary by many orders (plain TF32 would lose 13 bits)."""
+    M = N = K = 256
+    a = (rs.normal(size=(M, K)) * np.exp2(rs.integers(-20, 20, (M, K)))).astype(F)
+    b = (rs.normal(size=(N, K)) * np.exp2(rs.integers(-20, 20, (N, K)))).astype(F)
+    got = gemm(gpu, a, b, False, True, flags=TC)
+    want, mag = exact(a, b, False, True)
+    assert (np.abs(got - want) / mag).max() < TOL
+    sp = np.array([[np.inf, 1.0], [np.nan, 2.0]], dtype=F)
+    big_a = np.zeros((128, 32), F); big_a[:2, :2] = sp
+    big_b = np.zeros((128, 32), F); big_b[:, 0] = 1.0
+    out = gemm(gpu, big_a, big_b, False, True, flags=TC)
+    assert np.isinf(out[0, 0]) and np.isnan(out[1, 0]) and out[2, 0] == 0
+
+
+def test_matmul_and_dense_use_the_tensor_core_path(gpu, rs):
+    """`@` and nn.Dense at tile-aligned sizes dispatch to the tcgen05 kernel and stay fp32-accurate."""
+    from vulkpy_b200 import nn
+    a = rs.uniform(-1, 1, (512, 256)).astype(F)
+    b = rs.uniform(-1, 1, (256, 384)).astype(F)
+    got = np.asarray(vk.Array(gpu, data=a) @ vk.Array(gpu, data=b))
+    want, mag = exact(a, b, False, False)
+    assert (np.abs(got - want) / mag).max() < TOL
+    w = rs.normal(size=(256, 128)).astype(F)
+    bias = rs.normal(size=256).astype(F)
+    x = rs.normal(size=(512, 128)).astype(F)
+    d = nn.Dense(gpu, 128, 256, w_init=lambda g, s: vk.Array(g, data=w), b_init=lambda g, s: vk.Array(g, data=bias))
+    y = np.asarray(d(vk.Array(gpu, data=x)))
+    want = x.astype(np.float64) @ w.astype(np.float64).T + bias
+    assert np.abs(y - want).max() < 2e-4
+    dy = rs.normal(size=(512, 256)).astype(F)
+    dx = np.asarray(d.backward(vk.Array(gpu, data=dy)))
+    assert np.abs(dx - dy.astype(np.float64) @ w).max() < 5e-4
+    assert np.abs(np.asarray(d.w.grad) - dy.astype(np.float64).T @ x).max() < 1e-3

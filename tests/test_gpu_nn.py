@@ -196,23 +196,26 @@ def test_parameter_and_regularizers(gpu):
 
 
 def test_sequence_trains(gpu, rs):
+    """Dense-ReLU-Dense trained with SoftmaxCrossEntropyLoss (exact gradient softmax(x) - y) learns a
+    separable toy problem; Softmax + CrossEntropyLoss keeps the reference's diagonal-only backward
+    (layers.py:302-323), which is checked step-wise in the next test instead."""
     opt = nn.Adam(gpu, lr=1e-2)
-    net = nn.Sequence([nn.Dense(gpu, 4, 32, w_opt=opt, b_opt=opt), nn.ReLU(),
-                       nn.Dense(gpu, 32, 3, w_opt=opt, b_opt=opt), nn.Softmax()], nn.CrossEntropyLoss())
+    net = nn.Sequence([nn.Dense(gpu, 4, 32, w_opt=opt, b_opt=opt, w_init=nn.HeNormal(gpu, 4, seed=1)), nn.ReLU(),
+                       nn.Dense(gpu, 32, 3, w_opt=opt, b_opt=opt, w_init=nn.HeNormal(gpu, 32, seed=2))],
+                      nn.SoftmaxCrossEntropyLoss())
     x = rs.normal(size=(96, 4)).astype(F)
     labels = (x[:, 0] > 0).astype(np.uint32) + (x[:, 1] > 0.5).astype(np.uint32)
     X, Y = A(gpu, x), vk.U32Array(gpu, data=labels).to_onehot(3)
     _, first = net.train(X, Y)
     first = float(np.asarray(first).reshape(-1)[0])
-    for _ in range(60):
+    for _ in range(150):
         pred, loss = net.train(X, Y)
     last = float(np.asarray(loss).reshape(-1)[0])
-    assert last < 0.6 * first
+    assert last < 0.5 * first
     p, l2 = net.predict(X, Y)
     assert np.asarray(p).shape == (96, 3) and np.asarray(net.predict(X)).shape == (96, 3)
-    np.testing.assert_allclose(np.asarray(p).sum(axis=1), np.ones(96), rtol=1e-5)
     acc = (np.asarray(p).argmax(axis=1) == labels).mean()
-    assert acc > 0.7
+    assert acc > 0.8
 
 
 def test_one_training_step_matches_float64_model(gpu, rs):

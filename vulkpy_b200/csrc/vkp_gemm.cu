@@ -13,7 +13,7 @@
 #include "vkp_common.cuh"
 
 int vkp_gemm_tc_supported(int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
-                          const float* B, float* C);
+                          const float* B, float* C, int forced);
 int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
                 const float* B, float* C, const float* bias, int accumulate);
 
@@ -109,7 +109,7 @@ int vkp_launch_gemm(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N
   if (M == 0 || N == 0) return VKP_OK;
   const int accumulate = (flags & VKP_GEMM_ACCUMULATE) ? 1 : 0;
   const bool force_simt = flags & VKP_GEMM_FORCE_SIMT, force_tc = flags & VKP_GEMM_FORCE_TC;
-  const bool tc_ok = !force_simt && vkp_gemm_tc_supported(transA, transB, M, N, K, A, B, C);
+  const bool tc_ok = !force_simt && vkp_gemm_tc_supported(transA, transB, M, N, K, A, B, C, force_tc);
   VKP_CHECK(!(force_tc && !tc_ok), "vkp_gemm: tensor-core path forced but the shape (%u,%u,%u) is not supported", M, N, K);
   if (tc_ok) return vkp_gemm_tc(ctx, transA, transB, M, N, K, A, B, C, bias, accumulate);
   return gemm_simt(ctx, transA, transB, M, N, K, A, B, C, bias, accumulate);

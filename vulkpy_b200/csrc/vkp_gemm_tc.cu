@@ -1,12 +1,423 @@
-// vkp_gemm_tc.cu -- tcgen05 3xTF32 GEMM (placeholder until the kernel lands: reports "unsupported"
-// so that every shape takes the SIMT kernel).
+// vkp_gemm_tc.cu -- float32 GEMM on the 5th-generation tensor cores: tcgen05.mma kind::tf32 with a
+// 3xTF32 split, accumulators in TMEM, operands staged by TMA.
+//
+//   C[M,N] (+)= A[M,K] * Bt[N,K]^T (+ bias[N])        both operands K-major in shared memory
+//
+// Every fp32 operand x is split as x = hi + lo with hi = x with the low 13 mantissa bits cleared
+// (exactly a TF32 number) and lo = x - hi (exact in fp32, then cut to TF32), and
+//   a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi      (the dropped a_lo*b_lo term is ~2^-22 |a b|)
+// is accumulated in fp32 in TMEM, i.e. 3 tensor-core MMAs per k-step.
+//
+// CTA = 12 warps, one CTA per SM, persistent over output tiles (BM=128 x BN):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled fp32 tiles of A and Bt (the "hi"
+//               tiles are the raw fp32 data) into a STAGES-deep ring, completion on mbarriers
+//   warps 8-11  converters: read each landed tile, rewrite hi (low bits cleared) and write the lo
+//               tile at the same (swizzled) offsets, fence.proxy.async, signal the MMA warp
+//   warp 1      MMA issuer: one elected lane issues 4 k-steps x 3 tcgen05.mma (M=128, N=BN, K=8)
+//               per stage; tcgen05.commit releases the stage / publishes the accumulator
+//   warp 2      TMEM allocator (2 x BN fp32 columns: double-buffered accumulators)
+//   warps 4-7   epilogue: tcgen05.ld 32 lanes x 32 columns per warp, + bias / + C, 128-byte
+//               row segments stored straight to global memory
+// Inputs that are not K-major (A given as [K,M], B given as [K,N]) are transposed once into a
+// device workspace by a tiled transpose kernel (<2% of the GEMM time at 8192^3).
 #include "vkp_common.cuh"
 
-int vkp_gemm_tc_supported(int, int, uint32_t, uint32_t, uint32_t, const float*, const float*, float*) {
-  return 0;
+#include <cuda.h>
+#include <cstdlib>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;            // 32 fp32 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 8;         // kind::tf32
+constexpr int NUM_THREADS = 384;
+constexpr int A_TILE_BYTES = BM * BK * 4;   // 16 KiB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// spin with a watchdog: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; spin++) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
-int vkp_gemm_tc(vkp_ctx*, int, int, uint32_t, uint32_t, uint32_t, const float*, const float*, float*,
-                const float*, int) {
-  return vkp_set_error("vkp_gemm_tc: not built");
+// K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);        // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset
+  d |= (uint64_t)1 << 46;                            // descriptor version
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // hi + lo of A and B
+  static constexpr int STAGES = (BN == 128) ? 3 : 2;
+  static constexpr int TMEM_COLS = 2 * BN;                                  // two accumulators
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// split a landed fp32 tile: hi = x & ~0x1fff (in place), lo = tf32(x - hi) at the same offset
+__device__ __forceinline__ void split_tile(uint8_t* hi, uint8_t* lo, int bytes, int tid, int nthreads) {
+  for (int off = tid * 16; off < bytes; off += nthreads * 16) {
+    uint4 x = *reinterpret_cast<uint4*>(hi + off);
+    uint4 h, l;
+    // round to nearest TF32 (add half an ulp of the 10-bit mantissa, clear 13 bits): |x-hi| <= 2^-11|x|
+    h.x = (x.x + 0x1000u) & 0xffffe000u; h.y = (x.y + 0x1000u) & 0xffffe000u;
+    h.z = (x.z + 0x1000u) & 0xffffe000u; h.w = (x.w + 0x1000u) & 0xffffe000u;
+    l.x = (__float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x)) + 0x1000u) & 0xffffe000u;
+    l.y = (__float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y)) + 0x1000u) & 0xffffe000u;
+    l.z = (__float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z)) + 0x1000u) & 0xffffe000u;
+    l.w = (__float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w)) + 0x1000u) & 0xffffe000u;
+    *reinterpret_cast<uint4*>(hi + off) = h;
+    *reinterpret_cast<uint4*>(lo + off) = l;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               float* __restrict__ C, const float* __restrict__ bias, uint32_t M, uint32_t N, uint32_t K,
+               int accumulate) {
+  using cfg = Cfg<BN>;
+  constexpr int STAGES = cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                  // [STAGES] TMA landed
+  uint64_t* conv_bar = bars + STAGES;         // [STAGES] lo tiles written
+  uint64_t* empty_bar = bars + 2 * STAGES;    // [STAGES] MMAs that read the stage retired
+  uint64_t* tfull_bar = bars + 3 * STAGES;    // [2] accumulator complete
+  uint64_t* tempty_bar = bars + 3 * STAGES + 2;  // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
+  const uint32_t num_tiles = m_blocks * n_blocks;
+  const uint32_t k_blocks = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&conv_bar[s]), 4);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // GROUP_M consecutive m-blocks share their B tiles in L2
+  constexpr uint32_t GROUP_M = 16;
+  auto tile_coords = [&](uint32_t tile, uint32_t& mb, uint32_t& nb) {
+    const uint32_t per_group = GROUP_M * n_blocks;
+    const uint32_t g = tile / per_group;
+    const uint32_t first_m = g * GROUP_M;
+    const uint32_t gsz = (m_blocks - first_m) < GROUP_M ? (m_blocks - first_m) : GROUP_M;
+    const uint32_t r = tile - g * per_group;
+    mb = first_m + r % gsz;
+    nb = r / gsz;
+  };
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        uint32_t mb, nb;
+        tile_coords(tile, mb, nb);
+        for (uint32_t kb = 0; kb < k_blocks; kb++) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          uint8_t* st = smem + stage * cfg::STAGE_BYTES;
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_arrive_expect_tx(fb, A_TILE_BYTES + cfg::B_TILE_BYTES);
+          tma_load_2d(smem_u32(st), &tmA, fb, (int)(kb * BK), (int)(mb * BM));
+          tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES), &tmB, fb, (int)(kb * BK), (int)(nb * BN));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 @17, M>>4 @24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (uint32_t kb = 0; kb < k_blocks; kb++) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          mbar_wait(smem_u32(&conv_bar[stage]), phase);
+          tcgen05_fence_after();
+          uint8_t* st = smem + stage * cfg::STAGE_BYTES;
+          const uint64_t a_hi = make_desc(smem_u32(st));
+          const uint64_t a_lo = make_desc(smem_u32(st + A_TILE_BYTES));
+          const uint64_t b_hi = make_desc(smem_u32(st + 2 * A_TILE_BYTES));
+          const uint64_t b_lo = make_desc(smem_u32(st + 2 * A_TILE_BYTES + cfg::B_TILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; k++) {
+            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);   // 32 bytes per k-step
+            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+          }
+          tcgen05_commit(smem_u32(&empty_bar[stage]));
+          if (kb == k_blocks - 1) tcgen05_commit(smem_u32(&tfull_bar[acc]));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================================== converters =======================================
+    const int ctid = threadIdx.x - 256;   // 0..127
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (uint32_t kb = 0; kb < k_blocks; kb++) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        uint8_t* st = smem + stage * cfg::STAGE_BYTES;
+        split_tile(st, st + A_TILE_BYTES, A_TILE_BYTES, ctid, 128);
+        split_tile(st + 2 * A_TILE_BYTES, st + 2 * A_TILE_BYTES + cfg::B_TILE_BYTES, cfg::B_TILE_BYTES, ctid, 128);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&conv_bar[stage]));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue =========================================
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    uint32_t acc = 0, acc_phase = 0;
+    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      uint32_t mb, nb;
+      tile_coords(tile, mb, nb);
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t row = mb * BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        const uint32_t col0 = nb * BN + c;
+        if (row < M && col0 < N) {
+          float* dst = C + (size_t)row * N + col0;
+          const int ncol = (N - col0) < 32u ? (int)(N - col0) : 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j < ncol) {   // N % 4 == 0 is required by the host wrapper
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                     __uint_as_float(v[j + 3]));
+              if (bias) {
+                const float4 bv = *reinterpret_cast<const float4*>(bias + col0 + j);
+                o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+              }
+              if (accumulate) {
+                const float4 cv = *reinterpret_cast<const float4*>(dst + j);
+                o.x += cv.x; o.y += cv.y; o.z += cv.z; o.w += cv.w;
+              }
+              *reinterpret_cast<float4*>(dst + j) = o;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// out[c, r] = in[r, c]   (in: rows x cols)
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                        uint32_t rows, uint32_t cols) {
+  __shared__ float tile[32][33];
+  const uint32_t bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (uint32_t j = ty; j < 32; j += 8) {
+    const uint32_t r = by + j, c = bx + tx;
+    tile[j][tx] = (r < rows && c < cols) ? in[(size_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (uint32_t j = ty; j < 32; j += 8) {
+    const uint32_t c = bx + j, r = by + tx;
+    if (c < cols && r < rows) out[(size_t)c * rows + r] = tile[tx][j];
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// row-major [rows, K] fp32 matrix, box = BK x box_rows, 128B swizzle, zero fill out of bounds
+int make_map(CUtensorMap* map, const float* ptr, uint32_t rows, uint32_t K, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  VKP_CHECK(enc, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {K, rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+  cuuint32_t box[2] = {BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VKP_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return VKP_OK;
+}
+
+template <int BN>
+int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, float* C, const float* bias, uint32_t M, uint32_t N,
+              uint32_t K, int accumulate) {
+  using cfg = Cfg<BN>;
+  CUtensorMap tmA, tmB;
+  VKP_TRY(make_map(&tmA, A, M, K, BM));
+  VKP_TRY(make_map(&tmB, Bt, N, K, BN));
+  VKP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+  const uint32_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const unsigned grid = tiles < (uint32_t)ctx->sms ? tiles : (unsigned)ctx->sms;
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, cfg::SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, bias, M, N, K, accumulate);
+  return vkp_after_launch(ctx, "gemm_tc(tcgen05 3xTF32)");
+}
+
+}  // namespace
+
+int vkp_gemm_tc_supported(int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
+                          const float* B, float* C, int forced) {
+  (void)transA; (void)transB;
+  if (!forced) {
+    if (getenv("VKP_DISABLE_TC")) return 0;
+    if (M < 128 || N < 128 || K < 32) return 0;               // small problems: SIMT kernel
+    if ((uint64_t)M * N * K < (1ull << 22)) return 0;
+  }
+  if (K == 0) return 0;
+  if (K % 4 || N % 4 || M % 4) return 0;                      // 16-byte global strides for TMA / float4 stores
+  if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return 0;
+  return 1;
+}
+
+int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
+                const float* B, float* C, const float* bias, int accumulate) {
+  // bring both operands to K-major: A as [M,K], B as [N,K]
+  const float* Ak = A;
+  const float* Bk = B;
+  size_t need = 0;
+  if (transA) need += (size_t)M * K * 4;
+  if (!transB) need += (size_t)N * K * 4;
+  if (need) {
+    void* ws;
+    VKP_TRY(vkp_workspace(ctx, 1, need, &ws));
+    float* w = static_cast<float*>(ws);
+    if (transA) {   // A stored [K, M] -> [M, K]
+      dim3 g((M + 31) / 32, (K + 31) / 32);
+      transpose_kernel<<<g, 256, 0, ctx->stream>>>(A, w, K, M);
+      VKP_TRY(vkp_after_launch(ctx, "transpose(A)"));
+      Ak = w;
+      w += (size_t)M * K;
+    }
+    if (!transB) {  // B stored [K, N] -> [N, K]
+      dim3 g((N + 31) / 32, (K + 31) / 32);
+      transpose_kernel<<<g, 256, 0, ctx->stream>>>(B, w, K, N);
+      VKP_TRY(vkp_after_launch(ctx, "transpose(B)"));
+      Bk = w;
+    }
+  }
+  if (bias && (((uintptr_t)bias) & 15)) return vkp_set_error("vkp_gemm_tc: bias must be 16-byte aligned");
+  const bool wide = getenv("VKP_TC_BN128") == nullptr && (N % 256 == 0 || N >= 1024);
+  if (wide) return launch_tc<256>(ctx, Ak, Bk, C, bias, M, N, K, accumulate);
+  return launch_tc<128>(ctx, Ak, Bk, C, bias, M, N, K, accumulate);
 }
