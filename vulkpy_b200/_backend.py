@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(_HERE, "libvulkpy_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
-        f"{LIB_PATH} is missing: build it with `python -m vulkpy_b200.build` "
+        f"{LIB_PATH} is missing: build it with `python vulkpy_b200/build.py` "
         "(nvcc, sm_100a). vulkpy_b200 has no CPU fallback.")
 
 lib = C.CDLL(LIB_PATH)
@@ -87,7 +87,7 @@ for _name, (_res, _args) in PROTOTYPES.items():
 
 ABI_VERSION = 1
 if lib.vkp_abi_version() != ABI_VERSION:
-    raise ImportError("libvulkpy_b200.so ABI version mismatch; rebuild with `python -m vulkpy_b200.build`")
+    raise ImportError("libvulkpy_b200.so ABI version mismatch; rebuild with `python vulkpy_b200/build.py`")
 
 UINT64_MAX = (1 << 64) - 1
 COMM_ID_BYTES = 128

@@ -1,6 +1,6 @@
 """Build libvulkpy_b200.so in-tree with nvcc for sm_100a.
 
-Usage: python -m vulkpy_b200.build [--force]
+Usage: python vulkpy_b200/build.py [--force] [-v]   (run as a script: importing the package needs the library)
 
 The reference builds its pybind11 extension and compiles 121 GLSL shaders with glslc
 (setup.py:10-85); this backend has one shared library made of hand-written CUDA.

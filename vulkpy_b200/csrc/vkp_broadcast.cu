@@ -55,9 +55,8 @@ __global__ void __launch_bounds__(BC_BLOCK)
 bcast_vec_kernel(F f, const __grid_constant__ BcastDesc d, const float* A, const float* B, float* C,
                  uint32_t nvec) {
   const uint32_t lv = d.inner >> 2;
-  const uint32_t ntiles = (nvec + BC_TILE - 1) / BC_TILE;
-  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const uint32_t base = tile * BC_TILE + threadIdx.x;
+  {  // one tile per CTA (profiles/r01_micro_stream_variants.txt)
+    const uint32_t base = blockIdx.x * BC_TILE + threadIdx.x;
     float4 a[BC_UNROLL], b[BC_UNROLL];
 #pragma unroll
     for (int u = 0; u < BC_UNROLL; u++) {
@@ -122,7 +121,7 @@ int launch_bcast(vkp_ctx* ctx, const char* name, const BcastDesc& d, const void*
   if (n == 0) return VKP_OK;
   if (d.inner % 4 == 0) {
     const uint32_t nvec = n / 4;
-    const unsigned grid = vkp_grid_for(ctx, nvec, BC_TILE, 8);
+    const unsigned grid = (nvec + BC_TILE - 1) / BC_TILE;
     bcast_vec_kernel<F, HAS_B><<<grid, BC_BLOCK, 0, ctx->stream>>>(F(), d, (const float*)A, (const float*)B,
                                                                    (float*)C, nvec);
   } else {

@@ -125,6 +125,11 @@ __device__ __forceinline__ void split_tile(uint8_t* hi, uint8_t* lo, int bytes, 
     l.y = (__float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y)) + 0x1000u) & 0xffffe000u;
     l.z = (__float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z)) + 0x1000u) & 0xffffe000u;
     l.w = (__float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w)) + 0x1000u) & 0xffffe000u;
+    // inf / nan: keep x as hi and a zero lo (inf - inf would otherwise turn an infinity into nan)
+    if ((x.x & 0x7f800000u) == 0x7f800000u) { h.x = x.x; l.x = 0u; }
+    if ((x.y & 0x7f800000u) == 0x7f800000u) { h.y = x.y; l.y = 0u; }
+    if ((x.z & 0x7f800000u) == 0x7f800000u) { h.z = x.z; l.z = 0u; }
+    if ((x.w & 0x7f800000u) == 0x7f800000u) { h.w = x.w; l.w = 0u; }
     *reinterpret_cast<uint4*>(hi + off) = h;
     *reinterpret_cast<uint4*>(lo + off) = l;
   }
