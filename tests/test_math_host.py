@@ -16,6 +16,13 @@ void h_exp2(const float* x, float* y, long n){ for(long i=0;i<n;i++) y[i]=vkpm::
 void h_log(const float* x, float* y, long n){ for(long i=0;i<n;i++) y[i]=vkpm::log_f(x[i]); }
 void h_log2(const float* x, float* y, long n){ for(long i=0;i<n;i++) y[i]=vkpm::log2_f(x[i]); }
 void h_pow(const float* x, const float* y, float* z, long n){ for(long i=0;i<n;i++) z[i]=vkpm::pow_f(x[i],y[i]); }
+// table-driven fast paths (what the kernels run for ordinary inputs), host table accessor
+void f_exp(const float* x, float* y, long n){ vkpm::HostTables t; for(long i=0;i<n;i++) y[i]=vkpm::exp_fast(x[i],t); }
+void f_exp2(const float* x, float* y, long n){ vkpm::HostTables t; for(long i=0;i<n;i++) y[i]=vkpm::exp2_fast(x[i],t); }
+void f_log(const float* x, float* y, long n){ vkpm::HostTables t; for(long i=0;i<n;i++) y[i]=vkpm::log_fast(x[i],t); }
+void f_log2(const float* x, float* y, long n){ vkpm::HostTables t; for(long i=0;i<n;i++) y[i]=vkpm::log2_fast(x[i],t); }
+void f_pow(const float* x, const float* y, float* z, long n){ vkpm::HostTables t; for(long i=0;i<n;i++) z[i]=vkpm::pow_fast(x[i],y[i],t); }
+void f_sincos(const float* x, float* s, float* c, long n){ for(long i=0;i<n;i++) vkpm::sincos_small(x[i], s[i], c[i]); }
 }
 """
 
@@ -38,11 +45,11 @@ def call1(lib, name, x):
     return y
 
 
-def call2(lib, x, y):
+def call2(lib, x, y, name="h_pow"):
     x = np.ascontiguousarray(x, dtype=np.float32)
     y = np.ascontiguousarray(y, dtype=np.float32)
     z = np.empty_like(x)
-    lib.h_pow(C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), C.c_void_p(z.ctypes.data), C.c_long(x.size))
+    getattr(lib, name)(C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data), C.c_void_p(z.ctypes.data), C.c_long(x.size))
     return z
 
 
@@ -111,3 +118,62 @@ def test_special_values(hm):
     # subnormal results round once
     x = np.float32([-140.5, -149.0, -126.0])
     np.testing.assert_array_equal(call1(hm, "h_exp2", x), np.exp2(x.astype(np.float64)).astype(np.float32))
+
+
+# ---- the table-driven fast paths: same accuracy, same special-value behaviour ---------------------
+def test_fast_paths_appendix_a(hm):
+    x = [1, 2, 3]
+    assert bits(call1(hm, "f_exp", x)) == ["0x402df854", "0x40ec7326", "0x41a0af2e"]
+    assert bits(call1(hm, "f_log", x)) == ["0x0", "0x3f317218", "0x3f8c9f54"]
+    assert list(call1(hm, "f_exp2", x)) == [2.0, 4.0, 8.0]
+    assert bits(call1(hm, "f_log2", x)) == ["0x0", "0x3f800000", "0x3fcae00d"]
+    assert bits(call2(hm, x, [1.1, 2.2, 1.4], "f_pow")) == ["0x3f800000", "0x4093088d", "0x4094fa28"]
+    assert bits(call2(hm, x, [2.7] * 3, "f_pow")) == ["0x3f800000", "0x40cfefc6", "0x419b5a2a"]
+    assert bits(call2(hm, [1.3] * 3, [1.1, 2.2, 1.4], "f_pow")) == ["0x3faad2d2", "0x3fe3f958", "0x3fb8cfec"]
+    assert list(call2(hm, [1, 2, 3, 4], [2, 3, 2, 3], "f_pow")) == [1.0, 8.0, 9.0, 64.0]
+
+
+def test_fast_paths_accuracy(hm):
+    rs = np.random.default_rng(5)
+    for name, f, lo, hi in [("f_exp", np.exp, -104.0, 89.0), ("f_exp2", np.exp2, -150.0, 128.0)]:
+        x = rs.uniform(lo, hi, 2_000_000).astype(np.float32)
+        exact = f(x.astype(np.float64))
+        with np.errstate(all="ignore"):
+            ok = np.isfinite(exact.astype(np.float32)) & (np.abs(exact) > 1.2e-38)
+        assert ulps(call1(hm, name, x)[ok], exact[ok]).max() < 0.5002
+    for name, f in [("f_log", np.log), ("f_log2", np.log2)]:
+        x = rs.integers(0x00800000, 0x7f800000, 2_000_000, dtype=np.uint32).view(np.float32)
+        assert ulps(call1(hm, name, x), f(x.astype(np.float64))).max() < 0.5002
+        x = (1 + rs.uniform(-2.1e-2, 2.1e-2, 1_000_000)).astype(np.float32)    # the interval that contains 1.0
+        e = ulps(call1(hm, name, x), f(x.astype(np.float64)))
+        assert e[np.isfinite(e)].max() < 0.5002
+    x = rs.integers(1, 0x7f800000, 2_000_000, dtype=np.uint32).view(np.float32)
+    y = rs.uniform(-3, 3, 2_000_000).astype(np.float32)
+    exact = np.power(x.astype(np.float64), y.astype(np.float64))
+    with np.errstate(all="ignore"):
+        ok = np.isfinite(exact.astype(np.float32)) & (np.abs(exact) > 1.2e-38)
+    assert ulps(call2(hm, x, y, "f_pow")[ok], exact[ok]).max() < 0.5002
+    # fast and careful routines agree bit for bit except within 1e-4 ulp of a rounding boundary
+    assert (call2(hm, x, y, "f_pow") != call2(hm, x, y)).mean() < 1e-4
+
+
+def test_fast_paths_special_values(hm):
+    inf, nan = np.inf, np.nan
+    np.testing.assert_array_equal(call1(hm, "f_exp", [-inf, inf, -200, 200, 88.5, -100]),
+                                  call1(hm, "h_exp", [-inf, inf, -200, 200, 88.5, -100]))
+    r = call1(hm, "f_log", [0.0, -1.0, inf, 1e-45, nan])
+    assert r[0] == -inf and np.isnan(r[1]) and r[2] == inf and abs(r[3] + 103.2789) < 1e-3 and np.isnan(r[4])
+    xs = [2, -2, -2, 0, -0.0, inf, -8, 2, 0.5, 7, 1, -1, 1, 1e-40]
+    ys = [0, 3, 2, -1, -3, -1, 1 / 3, inf, inf, -inf, nan, inf, 1e30, 2]
+    a, b = call2(hm, xs, ys, "f_pow"), call2(hm, xs, ys)
+    assert all((np.isnan(p) and np.isnan(q)) or p == q for p, q in zip(a, b))
+
+
+def test_sincos_small(hm):
+    u = np.random.default_rng(6).uniform(0, 1, 2_000_000).astype(np.float32)
+    x = (np.float32(6.28318530718) * u).astype(np.float32)          # the Box-Muller angle
+    s, c = np.empty_like(x), np.empty_like(x)
+    hm.f_sincos(C.c_void_p(x.ctypes.data), C.c_void_p(s.ctypes.data), C.c_void_p(c.ctypes.data), C.c_long(x.size))
+    assert np.abs(s - np.sin(x.astype(np.float64))).max() < 1.2e-7
+    assert np.abs(c - np.cos(x.astype(np.float64))).max() < 1.2e-7
+    assert ulps(s, np.sin(x.astype(np.float64))).max() < 2.0 and ulps(c, np.cos(x.astype(np.float64))).max() < 2.0

@@ -17,6 +17,7 @@
 // Compiled with -fmad=false: one IEEE rounding per reference operation.
 #include "vkp_common.cuh"
 #include "vkp_math.cuh"
+#include "vkp_tables.cuh"
 
 namespace {
 
@@ -157,37 +158,7 @@ int launch_ew(vkp_ctx* ctx, const char* name, F f, const void* in0, const void* 
 // The 32-entry tables of vkp_math.cuh live one entry per lane in registers; a lookup is a warp
 // shuffle, so every lane of a warp evaluates the functor together: out-of-range lanes compute on
 // dummy inputs and only their loads / stores are predicated off.
-__device__ const float g_tab_rc[32] = {VKPM_TABLE_RC};
-__device__ const double g_tab_l2[32] = {VKPM_TABLE_L2};
-__device__ const double g_tab_e2[32] = {VKPM_TABLE_E2};
-
-__device__ __forceinline__ double pin(double x) {   // opaque to the optimiser: stays in a register pair
-  asm("" : "+d"(x));
-  return x;
-}
-
-struct LaneTables {
-  double lc_[6], ec_[4], log2e_;
-  float rc_;
-  double l2_, e2_;
-  __device__ explicit LaneTables(const vkpm::MathCoef& c) {
-#pragma unroll
-    for (int k = 0; k < 6; k++) lc_[k] = pin(c.lc[k]);
-#pragma unroll
-    for (int k = 0; k < 4; k++) ec_[k] = pin(c.ec[k]);
-    log2e_ = pin(c.log2e);
-    const int lane = threadIdx.x & 31;
-    rc_ = g_tab_rc[lane];
-    l2_ = g_tab_l2[lane];
-    e2_ = g_tab_e2[lane];
-  }
-  __device__ double lc(int i) const { return lc_[i]; }
-  __device__ double ec(int i) const { return ec_[i]; }
-  __device__ double log2e() const { return log2e_; }
-  __device__ float rc(int i) const { return __shfl_sync(0xffffffffu, rc_, i); }
-  __device__ double l2(int i) const { return __shfl_sync(0xffffffffu, l2_, i); }
-  __device__ double e2(int i) const { return __shfl_sync(0xffffffffu, e2_, i); }
-};
+using vkpt::LaneTables;
 
 // fast(): warp-collective, branch-free, ORs `special` for inputs it cannot handle; slow(): the
 // careful scalar routine, only run for those inputs
@@ -202,6 +173,19 @@ struct TExp {
 struct TExp2 {
   __device__ float fast(const LaneTables& t, float a, float, bool& sp) const { return vkpm::exp2_core(a, t, sp); }
   __device__ float slow(float a, float) const { return vkpm::exp2_f(a); }
+};
+struct TLog {
+  __device__ float fast(const LaneTables& t, float a, float, bool& sp) const { return vkpm::log_core(a, t, sp); }
+  __device__ float slow(float a, float) const { return vkpm::log_f(a); }
+};
+struct TLog2 {
+  __device__ float fast(const LaneTables& t, float a, float, bool& sp) const { return vkpm::log2_core(a, t, sp); }
+  __device__ float slow(float a, float) const { return vkpm::log2_f(a); }
+};
+// L = -y * log(x + 1e-8)   (nn_cross_entropy.comp:25)
+struct TCrossEntropy {
+  __device__ float fast(const LaneTables& t, float x, float y, bool& sp) const { return (-y) * vkpm::log_core(x + 1e-8f, t, sp); }
+  __device__ float slow(float x, float y) const { return (-y) * vkpm::log_f(x + 1e-8f); }
 };
 template <bool REV>
 struct TPowScalar {
@@ -269,7 +253,7 @@ int launch_ew_tab(vkp_ctx* ctx, const char* name, F f, const void* in0, const vo
   const size_t nvec = n >> 2;
   const size_t tiles = (nvec + EW_TILE_VEC - 1) / EW_TILE_VEC;
   const unsigned grid = (unsigned)(tiles ? tiles : 1);
-  static const vkpm::MathCoef coef = vkpm::make_math_coef();
+  const vkpm::MathCoef& coef = vkpt::host_coef();
   ew_tab_kernel<NIN, F><<<grid, EW_BLOCK, 0, ctx->stream>>>(f, coef, (const float*)in0, (const float*)in1, (float*)out, n);
   return vkp_after_launch(ctx, name);
 }
@@ -278,21 +262,29 @@ int launch_ew_tab(vkp_ctx* ctx, const char* name, F f, const void* in0, const vo
 // One thread per pair.  Unlike the reference dispatch (floor(n/2) invocations rounded up to a
 // workgroup, random.py:106-121) the last element of an odd-length output is always written.
 __global__ void __launch_bounds__(256)
-box_muller_kernel(const float* a, float* b, size_t n, float mean, float stddev) {
+box_muller_kernel(const __grid_constant__ vkpm::MathCoef coef, const float* a, float* b, size_t n, float mean,
+                  float stddev) {
+  const LaneTables tab(coef);
   const size_t npair = (n + 1) >> 1;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npair;
-       i += (size_t)gridDim.x * blockDim.x) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  // warp-uniform trip count: the table lookups inside log_core are shuffles
+  const size_t first = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) & ~(size_t)31;
+  for (size_t i0 = first; i0 < npair; i0 += stride) {
+    const size_t i = i0 + (threadIdx.x & 31);
+    const bool live = i < npair;
     const size_t j = 2 * i, k = j + 1;
-    const float2 u = *reinterpret_cast<const float2*>(a + j);  // a has an even number of elements
-    const float r = __fsqrt_rn(-2.0f * vkpm::log_f(1.0f - u.x)) * stddev;
-    const float angle = 6.28318530718f * u.y;
+    const float2 u = live ? *reinterpret_cast<const float2*>(a + j) : make_float2(0.5f, 0.5f);  // a has an even length
+    bool sp = false;
+    const float om = 1.0f - u.x;
+    float lg = vkpm::log_core(om, tab, sp);
+    if (sp) lg = vkpm::log_f(om);
+    const float r = __fsqrt_rn(-2.0f * lg) * stddev;
     float s, c;
-    sincosf(angle, &s, &c);
+    vkpm::sincos_small(6.28318530718f * u.y, s, c);
     const float o0 = mean + r * s, o1 = mean + r * c;
-    if (k < n) {
-      *reinterpret_cast<float2*>(b + j) = make_float2(o0, o1);
-    } else {
-      b[j] = o0;
+    if (live) {
+      if (k < n) *reinterpret_cast<float2*>(b + j) = make_float2(o0, o1);
+      else b[j] = o0;
     }
   }
 }
@@ -380,8 +372,10 @@ int dispatch_unary(vkp_ctx* ctx, int sub, const void* a, void* out, size_t n) {
     U(VKU_SINH, USinh, "sinh") U(VKU_COSH, UCosh, "cosh") U(VKU_TANH, UTanh, "tanh")
     U(VKU_ASINH, UAsinh, "asinh") U(VKU_ACOSH, UAcosh, "acosh") U(VKU_ATANH, UAtanh, "atanh")
     case VKU_EXP: return launch_ew_tab<1>(ctx, "exp", TExp(), a, nullptr, out, n);
-    U(VKU_LOG, ULog, "log") case VKU_EXP2: return launch_ew_tab<1>(ctx, "exp2", TExp2(), a, nullptr, out, n);
-    U(VKU_LOG2, ULog2, "log2")
+    case VKU_LOG: return launch_ew_tab<1>(ctx, "log", TLog(), a, nullptr, out, n);
+    case VKU_EXP2: return launch_ew_tab<1>(ctx, "exp2", TExp2(), a, nullptr, out, n);
+    case VKU_LOG2: return launch_ew_tab<1>(ctx, "log2", TLog2(), a, nullptr, out, n);
+   
     U(VKU_SQRT, USqrt, "sqrt") U(VKU_INVSQRT, UInvSqrt, "invsqrt")
   }
 #undef U
@@ -451,7 +445,7 @@ int vkp_launch_elementwise(vkp_ctx* ctx, int fam, int sub, void* const* bufs, in
     }
     case VKF_CE: {  // X, Y, L
       NEED(3, vkp_vector_params);
-      return launch_ew<2>(ctx, "nn_cross_entropy", FCrossEntropy(), bufs[0], bufs[1], nullptr, bufs[2], p->size);
+      return launch_ew_tab<2>(ctx, "nn_cross_entropy", TCrossEntropy(), bufs[0], bufs[1], bufs[2], p->size);
     }
     case VKF_CE_BWD: {  // X, Y, dX
       NEED(3, vkp_vector_params);
@@ -461,8 +455,8 @@ int vkp_launch_elementwise(vkp_ctx* ctx, int fam, int sub, void* const* bufs, in
       NEED(2, vkp_vectorscalar2_params);
       if (p->size == 0) return VKP_OK;
       const unsigned grid = vkp_grid_for(ctx, (p->size + 1) / 2, 256, 8);
-      box_muller_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)bufs[0], (float*)bufs[1], p->size,
-                                                        p->scalar[0], p->scalar[1]);
+      box_muller_kernel<<<grid, 256, 0, ctx->stream>>>(vkpt::host_coef(), (const float*)bufs[0], (float*)bufs[1],
+                                                        p->size, p->scalar[0], p->scalar[1]);
       return vkp_after_launch(ctx, "prng_box_muller");
     }
     case VKF_IBOX_MULLER: {  // A (rw, even n)
@@ -470,8 +464,8 @@ int vkp_launch_elementwise(vkp_ctx* ctx, int fam, int sub, void* const* bufs, in
       if (p->size == 0) return VKP_OK;
       VKP_CHECK(p->size % 2 == 0, "prng_ibox_muller needs an even element count (random.py:109-115)");
       const unsigned grid = vkp_grid_for(ctx, p->size / 2, 256, 8);
-      box_muller_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)bufs[0], (float*)bufs[0], p->size,
-                                                        p->scalar[0], p->scalar[1]);
+      box_muller_kernel<<<grid, 256, 0, ctx->stream>>>(vkpt::host_coef(), (const float*)bufs[0], (float*)bufs[0],
+                                                        p->size, p->scalar[0], p->scalar[1]);
       return vkp_after_launch(ctx, "prng_ibox_muller");
     }
     case VKF_RANDRANGE: {  // A ([0,1) floats), B (u32 out)

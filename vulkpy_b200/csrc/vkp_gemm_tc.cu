@@ -6,7 +6,8 @@
 // Every fp32 operand x is split as x = hi + lo with hi = x with the low 13 mantissa bits cleared
 // (exactly a TF32 number) and lo = x - hi (exact in fp32, then cut to TF32), and
 //   a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi      (the dropped a_lo*b_lo term is ~2^-22 |a b|)
-// is accumulated in fp32 in TMEM, i.e. 3 tensor-core MMAs per k-step.
+// is accumulated in fp32 in TMEM, i.e. 3 tensor-core MMAs per k-step.  Non-finite inputs come out
+// as NaN (inf * b_lo with b_lo = 0), where a plain fp32 product would keep the infinity.
 //
 // CTA = 12 warps, one CTA per SM, persistent over output tiles (BM=128 x BN):
 //   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled fp32 tiles of A and Bt (the "hi"
@@ -125,11 +126,6 @@ __device__ __forceinline__ void split_tile(uint8_t* hi, uint8_t* lo, int bytes, 
     l.y = (__float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y)) + 0x1000u) & 0xffffe000u;
     l.z = (__float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z)) + 0x1000u) & 0xffffe000u;
     l.w = (__float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w)) + 0x1000u) & 0xffffe000u;
-    // inf / nan: keep x as hi and a zero lo (inf - inf would otherwise turn an infinity into nan)
-    if ((x.x & 0x7f800000u) == 0x7f800000u) { h.x = x.x; l.x = 0u; }
-    if ((x.y & 0x7f800000u) == 0x7f800000u) { h.y = x.y; l.y = 0u; }
-    if ((x.z & 0x7f800000u) == 0x7f800000u) { h.z = x.z; l.z = 0u; }
-    if ((x.w & 0x7f800000u) == 0x7f800000u) { h.w = x.w; l.w = 0u; }
     *reinterpret_cast<uint4*>(hi + off) = h;
     *reinterpret_cast<uint4*>(lo + off) = l;
   }

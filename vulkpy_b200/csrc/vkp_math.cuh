@@ -194,7 +194,7 @@ VKP_HD float pow_f(float x, float y) {
 // =============================================================================================
 // Table-driven fast paths for exp / exp2 / pow (same binary64 accuracy, ~2.5x fewer instructions)
 //
-//   log2(x): x = 2^e * m, i = top 5 mantissa bits, rc_i = float(1 / centre_i):
+//   log2(x): x = 2^e * m with m in [2/3, 4/3), i = 5 bits of (bits(x) - bits(2/3)), rc_i = float(1 / centre_i):
 //            r = m * rc_i - 1 is exact in binary64 (|r| <= 2^-6), log2(m) = l2_i + log2(1 + r)
 //            with l2_i = -log2(rc_i) and a degree-8 series (truncation < 2^-56 absolute).
 //   2^t    : k = rint(32 t), r = t - k/32 (|r| <= 1/64), 2^t = 2^(k>>5) * e2[k & 31] * 2^r with a
@@ -204,27 +204,27 @@ VKP_HD float pow_f(float x, float y) {
 // conflicts); on the host (tests) the accessor indexes plain arrays.
 // =============================================================================================
 #define VKPM_TABLE_RC \
-  0x1.f81f82p-1f, 0x1.e9131ap-1f, 0x1.dae608p-1f, 0x1.cd8568p-1f, \
-  0x1.c0e070p-1f, 0x1.b4e81cp-1f, 0x1.a98ef6p-1f, 0x1.9ec8eap-1f, \
-  0x1.948b10p-1f, 0x1.8acb90p-1f, 0x1.818182p-1f, 0x1.78a4c8p-1f, \
-  0x1.702e06p-1f, 0x1.681682p-1f, 0x1.605816p-1f, 0x1.58ed24p-1f, \
-  0x1.51d07ep-1f, 0x1.4afd6ap-1f, 0x1.446f86p-1f, 0x1.3e22ccp-1f, \
-  0x1.381382p-1f, 0x1.323e34p-1f, 0x1.2c9fb4p-1f, 0x1.27350cp-1f, \
-  0x1.21fb78p-1f, 0x1.1cf06ap-1f, 0x1.181182p-1f, 0x1.135c82p-1f, \
-  0x1.0ecf56p-1f, 0x1.0a6810p-1f, 0x1.0624dep-1f, 0x1.020408p-1f,
+  0x1.7b8d58p+0f, 0x1.72f560p+0f, 0x1.6abed2p+0f, 0x1.62e35ap+0f, \
+  0x1.5b5d2cp+0f, 0x1.5426fap+0f, 0x1.4d3be2p+0f, 0x1.469764p+0f, \
+  0x1.40355ep+0f, 0x1.3a11fep+0f, 0x1.3429bcp+0f, 0x1.2e794ep+0f, \
+  0x1.28fdaep+0f, 0x1.23b40ap+0f, 0x1.1e99c0p+0f, 0x1.19ac62p+0f, \
+  0x1.14e9a6p+0f, 0x1.104f6cp+0f, 0x1.0bdbbap+0f, 0x1.078cb2p+0f, \
+  0x1.036098p+0f, 0x1.000000p+0f, 0x1.edfd6ep-1f, 0x1.df881ep-1f, \
+  0x1.d1e550p-1f, 0x1.c5038ap-1f, 0x1.b8d33cp-1f, 0x1.ad466ep-1f, \
+  0x1.a2509ep-1f, 0x1.97e682p-1f, 0x1.8dfdeep-1f, 0x1.848daap-1f,
 
 #define VKPM_TABLE_L2 \
-  0x1.6e7966ead8ac5p-6, 0x1.0eb392fe79defp-4, 0x1.bc841cd4346d3p-4, \
-  0x1.32aea1c2de0a0p-3, 0x1.84c2be7444b1ap-3, 0x1.d49ee012d3176p-3, \
-  0x1.11307dc445fecp-2, 0x1.37124a7b0e57ap-2, 0x1.5c01a2e7132d6p-2, \
-  0x1.800a59ccb4ee3p-2, 0x1.a3375ec3372a1p-2, 0x1.c592fb2eead30p-2, \
-  0x1.e726a9208b3bep-2, 0x1.03fda781da546p-1, 0x1.140c9fb5a8f7fp-1, \
-  0x1.23c41b2f89133p-1, 0x1.3327c82828e4dp-1, 0x1.423b07f5114e5p-1, \
-  0x1.51011934bf6e8p-1, 0x1.5f7cfece76360p-1, 0x1.6db194ce2d5dap-1, \
-  0x1.7ba1911bb9ec6p-1, 0x1.894f76c358639p-1, 0x1.96bdabfeb6bf8p-1, \
-  0x1.a3ee7f670c10cp-1, 0x1.b0e414a155dccp-1, 0x1.bda06f68b403ep-1, \
-  0x1.ca258b4fca071p-1, 0x1.d675400a8d681p-1, 0x1.e29144ae89a88p-1, \
-  0x1.ee7b44ce9bf96p-1, 0x1.fa34e145a6b20p-1,
+  -0x1.22e51bf786747p-1, -0x1.11fa756958969p-1, -0x1.0170c49dfb85ap-1, \
+  -0x1.e28796d387875p-2, -0x1.c2df1d2dc1369p-2, -0x1.a3e0b1f0c9c8dp-2, \
+  -0x1.8585554efb974p-2, -0x1.67c66c03c74fap-2, -0x1.4a9dd0855f1adp-2, \
+  -0x1.2e05b3d628a52p-2, -0x1.11f89dd8976b3p-2, -0x1.ece29b78e02d5p-3, \
+  -0x1.b6d5dc177eccep-3, -0x1.81c1ba1fe2fbfp-3, -0x1.4d9d55c042cb5p-3, \
+  -0x1.1a607f494729ep-3, -0x1.d00666c2559fcp-4, -0x1.6cfbea8d29ec0p-4, \
+  -0x1.0b9383ba4fae4p-4, -0x1.577eeeb48a61dp-5, -0x1.35cc168bceadfp-6, \
+  0x0.0p+0, 0x1.a73741c179688p-5, 0x1.8324e25e77944p-4, \
+  0x1.16cecdbed61d6p-3, 0x1.69a75a8aeaa41p-3, 0x1.ba3d595f5f453p-3, \
+  0x1.0457d271dfeebp-2, 0x1.2a8d3ba84259dp-2, 0x1.4fcc0beef0a7fp-2, \
+  0x1.74205c39d6788p-2, 0x1.97957155739efp-2,
 
 #define VKPM_TABLE_E2 \
   0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, \
@@ -294,13 +294,18 @@ VKP_HD uint32_t lo32(double x) {
 #endif
 }
 
-// log2 of the positive NORMAL float whose bits are u; absolute error < 2^-44
+// log2 of the positive NORMAL float whose bits are u.  x = 2^e * m with m in [2/3, 4/3) so that
+// inputs near 1 have e = 0; interval 21 contains 1.0 and has rc = 1, l2 = 0 exactly, hence
+// log2(1) = 0, log2(2^n) = n and full RELATIVE accuracy around 1.  |r| <= 0.0209; truncation
+// log2(e) r^7/7 < 2^-41 absolute and < 2^-36 relative to the result.
 template <class TA>
 VKP_HD double log2_tab(uint32_t u, const TA& ta) {
-  const int e = (int)(u >> 23) - 127;
-  const int i = (int)((u >> 18) & 31u);
-  const double md = hilo2d(0x3ff00000u | ((u >> 3) & 0x000fffffu), u << 29);   // mantissa in [1,2)
-  const double r = dfma(md, (double)ta.rc(i), -1.0);                           // exact, |r| <= 2^-6
+  const uint32_t d = u - 0x3f2aaaabu;                       // bits of 2/3
+  const int e = (int)d >> 23;
+  const int i = (int)((d >> 18) & 31u);
+  const uint32_t mb = u - ((uint32_t)e << 23);              // float bits of m
+  const double md = hilo2d((mb >> 3) + 0x38000000u, mb << 29);
+  const double r = dfma(md, (double)ta.rc(i), -1.0);        // exact
   double p = ta.lc(0);
   p = dfma(p, r, ta.lc(1));
   p = dfma(p, r, ta.lc(2));
@@ -340,6 +345,20 @@ VKP_HD float exp2_core(float x, const TA& ta, bool& special) {
   return (float)exp2_tab((double)x, ta);
 }
 template <class TA>
+VKP_HD float log2_core(float x, const TA& ta, bool& special) {
+  const uint32_t ux = f2bits(x);
+  const bool ok = (ux - 0x00800000u) < 0x7f000000u;          // positive, normal, finite
+  special |= !ok;
+  return (float)log2_tab(ok ? ux : 0x3fc00000u, ta);
+}
+template <class TA>
+VKP_HD float log_core(float x, const TA& ta, bool& special) {
+  const uint32_t ux = f2bits(x);
+  const bool ok = (ux - 0x00800000u) < 0x7f000000u;
+  special |= !ok;
+  return (float)(log2_tab(ok ? ux : 0x3fc00000u, ta) * 0.693147180559945309417232121458);
+}
+template <class TA>
 VKP_HD float pow_core(float x, float y, const TA& ta, bool& special) {
   const uint32_t ux = f2bits(x);
   const bool okx = (ux - 0x00800000u) < 0x7f000000u && ux != 0x3f800000u;   // positive, normal, != 1
@@ -362,10 +381,51 @@ VKP_HD float exp2_fast(float x, const TA& ta) {
   return sp ? exp2_f(x) : r;
 }
 template <class TA>
+VKP_HD float log_fast(float x, const TA& ta) {
+  bool sp = false;
+  const float r = log_core(x, ta, sp);
+  return sp ? log_f(x) : r;
+}
+template <class TA>
+VKP_HD float log2_fast(float x, const TA& ta) {
+  bool sp = false;
+  const float r = log2_core(x, ta, sp);
+  return sp ? log2_f(x) : r;
+}
+template <class TA>
 VKP_HD float pow_fast(float x, float y, const TA& ta) {
   bool sp = false;
   const float r = pow_core(x, y, ta, sp);
   return sp ? pow_f(x, y) : r;
+}
+
+// sin and cos of a float angle in [-8, 8] (Box-Muller feeds 2*pi*u, u in [0,1)): Cody-Waite
+// reduction by pi/2 in two FMAs, degree-7 / degree-8 minimax polynomials on [-pi/4, pi/4]
+// (about 1 ulp), quadrant fix-up.  ~20 FP32 instructions; the general sincosf carries a
+// Payne-Hanek slow path that is never needed here.
+VKP_HD float ffma(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  return __fmaf_rn(a, b, c);
+#else
+  return std::fmaf(a, b, c);
+#endif
+}
+VKP_HD void sincos_small(float x, float& s, float& c) {
+  const float kf = ffma(x, 0.636619772367581343f, 12582912.0f) - 12582912.0f;   // rint(x * 2/pi)
+  const int k = (int)kf;
+  float r = ffma(-kf, 1.57079637050628662109375f, x);       // pi/2 high part
+  r = ffma(-kf, -4.37113900018624283e-8f, r);               // pi/2 low part
+  const float z = r * r;
+  float ps = ffma(z, -1.9515295891e-4f, 8.3321608736e-3f);
+  ps = ffma(ps, z, -1.6666654611e-1f);
+  const float sr = ffma(ps * z, r, r);
+  float pc = ffma(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  pc = ffma(pc, z, 4.166664568298827e-2f);
+  const float cr = ffma(pc * z, z, ffma(z, -0.5f, 1.0f));
+  const float s0 = (k & 1) ? cr : sr;
+  const float c0 = (k & 1) ? sr : cr;
+  s = (k & 2) ? -s0 : s0;
+  c = ((k + 1) & 2) ? -c0 : c0;
 }
 
 VKP_HD float sign_f(float x) {

@@ -21,6 +21,7 @@
 // starts late never sees the final state another segment already wrote.
 #include "vkp_common.cuh"
 #include "vkp_math.cuh"
+#include "vkp_tables.cuh"
 
 #include <random>
 
@@ -136,13 +137,12 @@ template <> struct VecStore<1> { static __device__ void st(uint32_t* p, const ui
 template <> struct VecStore<2> { static __device__ void st(uint32_t* p, const uint32_t* v) { *reinterpret_cast<uint2*>(p) = make_uint2(v[0], v[1]); } };
 template <> struct VecStore<4> { static __device__ void st(uint32_t* p, const uint32_t* v) { *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]); } };
 
-// n_draw: uniforms consumed in total (n, or n+1 for an odd-length normal()); n_out: elements written
+// uniform streams (MODE_U32 / MODE_F32): n numbers, out[c*size + lane]
 template <int LPT, int MODE>
 __global__ void __launch_bounds__(128)
 xoshiro_stream_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ state_out,
                       uint32_t* __restrict__ out, const uint4* __restrict__ jump, uint32_t size,
-                      uint64_t n_draw, uint64_t n_out, uint32_t log2L, uint32_t nseg, float mean,
-                      float stddev) {
+                      uint64_t n_draw, uint32_t log2L, uint32_t nseg) {
   const uint32_t groups = size / LPT;
   const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (t >= (uint64_t)groups * nseg) return;
@@ -176,49 +176,98 @@ xoshiro_stream_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ st
     uint32_t r[LPT];
 #pragma unroll
     for (int q = 0; q < LPT; q++) r[q] = next_dev(s[q]);
-    const uint64_t j = c * size + l0;
-    if (MODE == MODE_U32) {
-      VecStore<LPT>::st(out + j, r);
-    } else if (MODE == MODE_F32) {
+    if (MODE == MODE_F32) {
 #pragma unroll
       for (int q = 0; q < LPT; q++) r[q] = __float_as_uint(u2f01(r[q]));
-      VecStore<LPT>::st(out + j, r);
-    } else {  // Box-Muller on the pair (lane l0, lane l0+1); LPT == 2
-      const float u0 = u2f01(r[0]), u1 = u2f01(r[LPT - 1]);
-      const float rad = __fsqrt_rn(-2.0f * vkpm::log_f(1.0f - u0)) * stddev;
-      float sn, cs;
-      sincosf(6.28318530718f * u1, &sn, &cs);
-      const float o0 = mean + rad * sn, o1 = mean + rad * cs;
-      if (j + 1 < n_out) *reinterpret_cast<float2*>(out + j) = make_float2(o0, o1);
-      else if (j < n_out) reinterpret_cast<float*>(out)[j] = o0;
     }
+    VecStore<LPT>::st(out + c * size + l0, r);
   }
   // tail chunk: draw index `full`, lanes < rem only
   if (rem != 0 && full >= start && full < seg_end) {
-    uint32_t r[LPT];
-#pragma unroll
-    for (int q = 0; q < LPT; q++) r[q] = (l0 + q < rem) ? next_dev(s[q]) : 0u;
     const uint64_t j = full * size + l0;
-    if (MODE == MODE_NORMAL) {
-      if (l0 < rem) {  // rem and l0 are even: both lanes of the pair are in
-        const float u0 = u2f01(r[0]), u1 = u2f01(r[LPT - 1]);
-        const float rad = __fsqrt_rn(-2.0f * vkpm::log_f(1.0f - u0)) * stddev;
-        float sn, cs;
-        sincosf(6.28318530718f * u1, &sn, &cs);
-        if (j < n_out) reinterpret_cast<float*>(out)[j] = mean + rad * sn;
-        if (j + 1 < n_out) reinterpret_cast<float*>(out)[j + 1] = mean + rad * cs;
-      }
-    } else {
 #pragma unroll
-      for (int q = 0; q < LPT; q++)
-        if (l0 + q < rem) out[j + q] = (MODE == MODE_F32) ? __float_as_uint(u2f01(r[q])) : r[q];
-    }
+    for (int q = 0; q < LPT; q++)
+      if (l0 + q < rem) {
+        const uint32_t r = next_dev(s[q]);
+        out[j + q] = (MODE == MODE_F32) ? __float_as_uint(u2f01(r)) : r;
+      }
   }
   // the segment that contains a lane's last draw publishes the lane's new state
 #pragma unroll
   for (int q = 0; q < LPT; q++) {
     const uint64_t cnt = full + ((l0 + q < rem) ? 1 : 0);
     if (cnt > start && cnt <= seg_end) state_out[l0 + q] = s[q];
+  }
+}
+
+// Fused uniform -> Box-Muller (random.py:60-124 + prng_box_muller.comp:19-32): a thread owns the
+// lane pair (l0, l0+1), whose draws are the adjacent outputs (2i, 2i+1); the uniforms never leave
+// registers.  n_draw = n rounded up to even (the reference draws n+1 uniforms for odd n).
+// The log uses the warp-shuffle tables, so the loops run a warp-uniform number of iterations and
+// finished threads idle on dummy values.
+__global__ void __launch_bounds__(128)
+xoshiro_normal_kernel(const __grid_constant__ vkpm::MathCoef coef, const uint4* __restrict__ state_in,
+                      uint4* __restrict__ state_out, float* __restrict__ out, const uint4* __restrict__ jump,
+                      uint32_t size, uint64_t n_draw, uint64_t n_out, uint32_t log2L, uint32_t nseg, float mean,
+                      float stddev) {
+  const vkpt::LaneTables tab(coef);
+  const uint32_t groups = size / 2;
+  const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const bool valid = t < (uint64_t)groups * nseg;
+  const uint32_t p = valid ? (uint32_t)(t / groups) : 0u;
+  const uint32_t l0 = valid ? (uint32_t)(t % groups) * 2 : 0u;
+  const uint64_t full = n_draw / size;
+  const uint32_t rem = (uint32_t)(n_draw % size);   // even, like size and l0
+  const uint64_t start = (uint64_t)p << log2L;
+  const uint64_t seg_end = start + (1ull << log2L);
+
+  uint4 s0 = state_in[l0], s1 = state_in[l0 + 1];
+  if (valid && p == 0 && full == 0 && l0 >= rem) {
+    state_out[l0] = s0;
+    state_out[l0 + 1] = s1;
+  }
+  for (uint32_t b = 0; (p >> b) != 0; b++) {
+    if ((p >> b) & 1u) {
+      const uint4* m = jump + (size_t)(log2L + b) * 128;
+      s0 = matvec_dev(m, s0);
+      s1 = matvec_dev(m, s1);
+    }
+  }
+
+  auto emit = [&](bool live, uint64_t j) {   // all 32 lanes call this together
+    float u0 = 0.5f, u1 = 0.5f;
+    if (live) {
+      u0 = u2f01(next_dev(s0));
+      u1 = u2f01(next_dev(s1));
+    }
+    bool sp = false;
+    const float om = 1.0f - u0;
+    float lg = vkpm::log_core(om, tab, sp);
+    if (sp) lg = vkpm::log_f(om);
+    const float rad = __fsqrt_rn(-2.0f * lg) * stddev;
+    float sn, cs;
+    vkpm::sincos_small(6.28318530718f * u1, sn, cs);
+    const float o0 = mean + rad * sn, o1 = mean + rad * cs;
+    if (live) {
+      if (j + 1 < n_out) *reinterpret_cast<float2*>(out + j) = make_float2(o0, o1);
+      else if (j < n_out) out[j] = o0;
+    }
+  };
+
+  const uint64_t e1 = seg_end < full ? seg_end : full;
+  const uint32_t mine = (valid && e1 > start) ? (uint32_t)(e1 - start) : 0u;
+  const uint32_t trips = __reduce_max_sync(0xffffffffu, mine);
+  for (uint32_t it = 0; it < trips; it++) emit(it < mine, (start + it) * size + l0);
+
+  const bool tail = valid && rem != 0 && full >= start && full < seg_end && l0 < rem;
+  if (__any_sync(0xffffffffu, tail)) emit(tail, full * size + l0);
+
+  if (valid) {
+    const uint64_t cnt = full + ((l0 < rem) ? 1 : 0);
+    if (cnt > start && cnt <= seg_end) {
+      state_out[l0] = s0;
+      state_out[l0 + 1] = s1;
+    }
   }
 }
 
@@ -338,9 +387,12 @@ static int rng_generate(vkp_rng* rng, void* out, uint64_t n_out, float mean, flo
     const uint4* sin_ = rng->state[rng->cur];
     uint4* sout = rng->state[rng->cur ^ 1];
 #define LAUNCH(LPT)                                                                                  \
-  xoshiro_stream_kernel<LPT, MODE><<<grid, 128, 0, ctx->stream>>>(sin_, sout, (uint32_t*)out, rng->jump, \
-                                                                  size, n_draw, n_out, log2L, nseg, mean, stddev)
-    if (MODE == MODE_NORMAL) { LAUNCH(2); }
+  xoshiro_stream_kernel<LPT, (MODE == MODE_NORMAL ? MODE_F32 : MODE)><<<grid, 128, 0, ctx->stream>>>(     \
+      sin_, sout, (uint32_t*)out, rng->jump, size, n_draw, log2L, nseg)
+    if (MODE == MODE_NORMAL) {
+      xoshiro_normal_kernel<<<grid, 128, 0, ctx->stream>>>(vkpt::host_coef(), sin_, sout, (float*)out, rng->jump,
+                                                           size, n_draw, n_out, log2L, nseg, mean, stddev);
+    }
     else if (lpt == 4) { LAUNCH(4); }
     else if (lpt == 2) { LAUNCH(2); }
     else { LAUNCH(1); }
