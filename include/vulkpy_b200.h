@@ -129,6 +129,9 @@ VKP_API int vkp_rng_float(vkp_rng* rng, float* out, uint32_t n, vkp_job** job);
  * consumes n (even) or n+1 (odd) uniforms exactly like the reference */
 VKP_API int vkp_rng_normal(vkp_rng* rng, float* out, uint32_t n, float mean, float stddev, vkp_job** job);
 VKP_API int vkp_rng_state(vkp_rng* rng, uint32_t* host_out /* 4*size words */);
+/* discard n draws exactly as vkp_rng_uint32(n) would consume them (GF(2) jump-ahead): lets every rank
+ * of a sharded generator start at its own chunk of the single-GPU stream */
+VKP_API int vkp_rng_advance(vkp_rng* rng, uint64_t n);
 
 /* ---- timing on the context stream (bench only) ------------------------------------ */
 VKP_API int vkp_timer_create(vkp_ctx* ctx, vkp_timer** out);

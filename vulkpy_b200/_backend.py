@@ -69,6 +69,7 @@ PROTOTYPES = {
     "vkp_rng_float": (C.c_int, [_vp, _vp, _u32, C.POINTER(_vp)]),
     "vkp_rng_normal": (C.c_int, [_vp, _vp, _u32, C.c_float, C.c_float, C.POINTER(_vp)]),
     "vkp_rng_state": (C.c_int, [_vp, _vp]),
+    "vkp_rng_advance": (C.c_int, [_vp, _u64]),
     "vkp_timer_create": (C.c_int, [_vp, C.POINTER(_vp)]),
     "vkp_timer_record": (C.c_int, [_vp]),
     "vkp_timer_elapsed_ms": (C.c_int, [_vp, _vp, C.POINTER(C.c_float)]),
@@ -367,6 +368,10 @@ class Xoshiro128pp:
         job = _vp()
         _check(lib.vkp_rng_normal(self._h, info.ptr, int(n), float(mean), float(stddev), C.byref(job)))
         return Job(job.value)
+
+    def advance(self, n: int):
+        """Discard ``n`` draws exactly as ``random_uint32(n)`` would consume them."""
+        _check(lib.vkp_rng_advance(self._h, int(n)))
 
     def state(self) -> np.ndarray:
         out = np.empty((self.size, 4), dtype=np.uint32)

@@ -271,6 +271,19 @@ xoshiro_normal_kernel(const __grid_constant__ vkpm::MathCoef coef, const uint4* 
   }
 }
 
+// discard n draws exactly as random(n) would consume them: every lane jumps floor(n/size) steps
+// ahead through the T^(2^k) matrices, the first n % size lanes take one more step
+__global__ void xoshiro_advance_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ state_out,
+                                       const uint4* __restrict__ jump, uint32_t size, uint64_t full, uint32_t rem) {
+  const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= size) return;
+  uint4 s = state_in[l];
+  for (uint32_t b = 0; (full >> b) != 0; b++)
+    if ((full >> b) & 1ull) s = matvec_dev(jump + (size_t)b * 128, s);
+  if (l < rem) next_dev(s);
+  state_out[l] = s;
+}
+
 }  // namespace
 
 struct vkp_rng {
@@ -416,4 +429,20 @@ extern "C" int vkp_rng_normal(vkp_rng* rng, float* out, uint32_t n, float mean, 
   VKP_CHECK(rng->size % 2 == 0,
             "vkp_rng_normal: fused Box-Muller needs an even lane count; use random()+prng_box_muller");
   return rng_generate<MODE_NORMAL>(rng, out, n, mean, stddev, job);
+}
+
+extern "C" int vkp_rng_advance(vkp_rng* rng, uint64_t n) {
+  VKP_CHECK(rng, "vkp_rng_advance: null argument");
+  if (n == 0) return VKP_OK;
+  vkp_ctx* ctx = rng->ctx;
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  const uint64_t full = n / rng->size;
+  VKP_CHECK((full >> (JUMP_LEVELS - 1)) == 0, "vkp_rng_advance: jump too long");
+  xoshiro_advance_kernel<<<(rng->size + 127) / 128, 128, 0, ctx->stream>>>(
+      rng->state[rng->cur], rng->state[rng->cur ^ 1], rng->jump, rng->size, full, (uint32_t)(n % rng->size));
+  VKP_TRY(vkp_after_launch(ctx, "xoshiro128pp_advance"));
+  rng->cur ^= 1;
+  ctx->seq++;
+  return VKP_OK;
 }
