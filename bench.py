@@ -152,6 +152,8 @@ def cpu_reference_pass(L, ptr, a, b, row, col, c, out, shapes):
 def cpu_arm(log2n_sample: int, steps: int, warmup: int):
     from oracle import cpu_ref
     L = cpu_ref.load()
+    # all host threads (torchrun exports OMP_NUM_THREADS=1; the baseline is "every core the box has")
+    L.ref_set_num_threads(len(os.sched_getaffinity(0)))
     rows = 1 << (log2n_sample // 2)
     cols = (1 << log2n_sample) // rows
     rs = np.random.default_rng(1234)

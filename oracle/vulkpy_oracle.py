@@ -180,6 +180,14 @@ def _cr(f, *xs):
         return np.asarray(f(*[np.asarray(x, dtype=F32).astype(np.float64) for x in xs])).astype(F32)
 
 
+def _ftz(r):
+    """Flush float32 subnormal results to zero: GPU Vulkan drivers do, and the reference's own
+    test relies on it (test/test_nn.py:120-126 expects softmax([100, 0]) == [1, 0] exactly, i.e.
+    exp(-100) = 3.8e-44 must be 0)."""
+    r = np.asarray(r, dtype=F32)
+    return np.where(np.abs(r) < F32(1.17549435e-38), np.copysign(F32(0), r), r).astype(F32)
+
+
 def _glsl_sign(x):
     return np.where(x > 0, 1.0, np.where(x < 0, -1.0, 0.0))
 
@@ -191,7 +199,7 @@ BINARY = {
     "div": lambda a, b: (a / b).astype(F32),
     "max": lambda a, b: np.maximum(a, b).astype(F32),
     "min": lambda a, b: np.minimum(a, b).astype(F32),
-    "pow": lambda a, b: _cr(np.power, a, b),
+    "pow": lambda a, b: _ftz(_cr(np.power, a, b)),
 }
 
 UNARY = {
@@ -203,8 +211,8 @@ UNARY = {
     "sinh": lambda a: _cr(np.sinh, a), "cosh": lambda a: _cr(np.cosh, a), "tanh": lambda a: _cr(np.tanh, a),
     "asinh": lambda a: _cr(np.arcsinh, a), "acosh": lambda a: _cr(np.arccosh, a),
     "atanh": lambda a: _cr(np.arctanh, a),
-    "exp": lambda a: _cr(np.exp, a), "log": lambda a: _cr(np.log, a),
-    "exp2": lambda a: _cr(np.exp2, a), "log2": lambda a: _cr(np.log2, a),
+    "exp": lambda a: _ftz(_cr(np.exp, a)), "log": lambda a: _cr(np.log, a),
+    "exp2": lambda a: _ftz(_cr(np.exp2, a)), "log2": lambda a: _cr(np.log2, a),
     "sqrt": lambda a: _cr(np.sqrt, a),
     "invsqrt": lambda a: _cr(lambda x: 1.0 / np.sqrt(x), a),
 }

@@ -43,6 +43,8 @@ def test_softmax(gpu):
     np.testing.assert_allclose(sm(A(gpu, x)), [[0.5, 0.5]], **TOL)
     x = np.asarray([[0.0, 100.0]])
     np.testing.assert_allclose(sm(A(gpu, x)), [[0.0, 1.0]], **TOL)
+    # exp(-100) is a float32 subnormal: flushed, so the result is EXACTLY [1, 0] (test/test_nn.py:120-126)
+    np.testing.assert_allclose(sm(A(gpu, [[100.0, 0.0]])), [[1.0, 0.0]], rtol=1e-7, atol=0)
     x = np.asarray([[0.1, 0.7, -1.3, 2.0], [3.0, 3.0, 2.0, -8.0]])
     y = softmax64(x)
     np.testing.assert_allclose(sm(A(gpu, x)), y, **TOL)

@@ -77,6 +77,21 @@ VKP_HD float rcp_seed(float d) {
 #endif
 }
 
+// binary64 -> binary32, round to nearest, subnormal results flushed to (signed) zero.  The
+// reference's test-suite expects softmax([100, 0]) == [1, 0] exactly (test/test_nn.py:120-126),
+// i.e. exp(-100) = 3.8e-44 must come out as 0: GPU Vulkan drivers flush float32 denormals.
+VKP_HD float d2f_ftz(double x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("cvt.rn.ftz.f32.f64 %0, %1;" : "=f"(r) : "d"(x));
+  return r;
+#else
+  const float r = (float)x;
+  if (r < 1.17549435e-38f && r > -1.17549435e-38f) return std::copysign(0.0f, r);
+  return r;
+#endif
+}
+
 VKP_HD double drint(double x) {
 #if defined(__CUDA_ARCH__)
   return rint(x);
@@ -140,14 +155,14 @@ VKP_HD float exp_f(float x) {
   if (!(x == x)) return x;
   double t = (double)x * 1.44269504088896340735992468100;
   t = t < -200.0 ? -200.0 : (t > 200.0 ? 200.0 : t);
-  return (float)exp2_core(t);
+  return d2f_ftz(exp2_core(t));
 }
 
 VKP_HD float exp2_f(float x) {
   if (!(x == x)) return x;
   double t = (double)x;
   t = t < -200.0 ? -200.0 : (t > 200.0 ? 200.0 : t);
-  return (float)exp2_core(t);
+  return d2f_ftz(exp2_core(t));
 }
 
 // kind 0: natural log, 1: log2.  Returns binary64 so pow() can reuse it.
@@ -187,7 +202,7 @@ VKP_HD float pow_f(float x, float y) {
   if (ax == 1.0f) return sign;                                 // (-1)^y, y integer or inf
   double t = (double)y * log_d<1>(ax);                         // +-inf handled by clamp
   t = t < -200.0 ? -200.0 : (t > 200.0 ? 200.0 : t);
-  return sign * (float)exp2_core(t);
+  return sign * d2f_ftz(exp2_core(t));
 }
 
 
@@ -337,12 +352,12 @@ VKP_HD double exp2_tab(double t, const TA& ta) {
 template <class TA>
 VKP_HD float exp_core(float x, const TA& ta, bool& special) {
   special |= !((f2bits(x) & 0x7fffffffu) < 0x42b00000u);     // |x| >= 88, inf, nan
-  return (float)exp2_tab((double)x * ta.log2e(), ta);
+  return d2f_ftz(exp2_tab((double)x * ta.log2e(), ta));
 }
 template <class TA>
 VKP_HD float exp2_core(float x, const TA& ta, bool& special) {
   special |= !((f2bits(x) & 0x7fffffffu) < 0x42fc0000u);     // |x| >= 126, inf, nan
-  return (float)exp2_tab((double)x, ta);
+  return d2f_ftz(exp2_tab((double)x, ta));
 }
 template <class TA>
 VKP_HD float log2_core(float x, const TA& ta, bool& special) {
@@ -364,7 +379,7 @@ VKP_HD float pow_core(float x, float y, const TA& ta, bool& special) {
   const bool okx = (ux - 0x00800000u) < 0x7f000000u && ux != 0x3f800000u;   // positive, normal, != 1
   const double t = (double)y * log2_tab(okx ? ux : 0x3fc00000u, ta);
   special |= !(okx && (hi32(t) & 0x7fffffffu) < 0x4062c000u);               // or |t| >= 150 / nan
-  return (float)exp2_tab(t, ta);
+  return d2f_ftz(exp2_tab(t, ta));
 }
 
 // convenience wrappers (host tests, single-element callers)
