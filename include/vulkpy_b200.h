@@ -114,6 +114,22 @@ VKP_API int vkp_gemm(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t 
              const float* A, const float* B, float* C, const float* bias, int flags,
              vkp_job** job);
 
+/* ---- fused vulkpy.nn steps: same float32 operations, order and roundings as the
+ * reference's op-by-op compositions, one kernel each ------------------------------------------- */
+/* AdamState.grad2diff (nn/optimizers.py:235-253): updates m, v in place, writes the parameter
+ * update to diff.  All scalars are the float32 values the reference would pass op by op. */
+VKP_API int vkp_nn_adam(vkp_ctx* ctx, const float* grad, float* m, float* v, float* diff, size_t n,
+                        float beta1, float one_minus_beta1, float beta2, float one_minus_beta2,
+                        float one_minus_beta1t, float one_minus_beta2t, float eps, float neg_lr,
+                        vkp_job** job);
+/* kind 0: ReLU.backward dx = max(sign(y),0)*dy (nn/layers.py:207-210);
+ * kind 1: Sigmoid/Softmax.backward dx = ((1-y)*y)*dy (nn/layers.py:262-267,320-323) */
+VKP_API int vkp_nn_activation_backward(vkp_ctx* ctx, int kind, const float* y, const float* dy, float* dx,
+                                       size_t n, vkp_job** job);
+/* Softmax.forward over axis 1 of [rows, cols] (nn/layers.py:297-300) */
+VKP_API int vkp_nn_softmax_forward(vkp_ctx* ctx, const float* x, float* y, uint32_t rows, uint32_t cols,
+                                   vkp_job** job);
+
 /* ---- jobs: Job::wait (_vkarray.cc:446-456, :876-879) ------------------------------ */
 VKP_API int vkp_job_wait(vkp_job* job, uint64_t timeout_ns);   /* timeout_ns==UINT64_MAX: forever; 2 = timeout */
 VKP_API int vkp_job_done(vkp_job* job, int* done);

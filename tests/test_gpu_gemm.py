@@ -103,3 +103,22 @@ def test_matmul_and_dense_use_the_tensor_core_path(gpu, rs):
     dx = np.asarray(d.backward(vk.Array(gpu, data=dy)))
     assert np.abs(dx - dy.astype(np.float64) @ w).max() < 5e-4
     assert np.abs(np.asarray(d.w.grad) - dy.astype(np.float64).T @ x).max() < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(16, 1024, 8192, True, False), (8192, 16, 1024, False, True),
+                                         (8192, 1024, 16, False, False), (1024, 1024, 8192, True, False),
+                                         (256, 512, 4096, False, True), (3, 5, 5000, False, False)])
+def test_skinny_and_split_k(gpu, rs, M, N, K, ta, tb):
+    """Shapes of the MLP step (C = 16 classes, batch 8192): few output tiles and a long K are split
+    over K (SIMT: blockIdx.z slices, tcgen05: (tile, split) work items) and reduced in a fixed order."""
+    a = rs.uniform(-1, 1, (K, M) if ta else (M, K)).astype(F)
+    b = rs.uniform(-1, 1, (N, K) if tb else (K, N)).astype(F)
+    bias = rs.normal(size=N).astype(F)
+    c0 = rs.normal(size=(M, N)).astype(F)
+    want, mag = exact(a, b, ta, tb)
+    got = gemm(gpu, a, b, ta, tb)
+    assert (np.abs(got - want) / mag).max() < TOL
+    got = gemm(gpu, a, b, ta, tb, bias=bias, flags=ACC, c0=c0)
+    assert (np.abs(got - (want + bias + c0)) / (mag + 2)).max() < TOL
+    got2 = gemm(gpu, a, b, ta, tb, bias=bias, flags=ACC, c0=c0)
+    np.testing.assert_array_equal(got, got2)          # deterministic

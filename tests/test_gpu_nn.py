@@ -242,3 +242,30 @@ def test_one_training_step_matches_float64_model(gpu, rs):
     np.testing.assert_allclose(d2.b.value, b2 - 0.1 * dz2.sum(axis=0), rtol=1e-4, atol=1e-5)
     dz1 = (dz2 @ W2) * (h > 0)
     np.testing.assert_allclose(d1.w.value, W1 - 0.1 * dz1.T @ x, rtol=1e-4, atol=1e-5)
+
+
+def test_fused_kernels_match_the_op_by_op_compositions(gpu, rs, monkeypatch):
+    """vkp_nn_adam / activation backward are bit-identical to the reference-ordered op chains; the
+    fused softmax agrees with the float64 model and (up to the summation order) with the chain."""
+    from vulkpy_b200.nn import optimizers as O
+    g = rs.normal(size=1000).astype(F)
+    y = rs.uniform(-1, 1, (37, 19)).astype(F)
+    dy = rs.normal(size=(37, 19)).astype(F)
+    x = rs.normal(size=(65, 40)).astype(F) * 3
+    res = {}
+    for unfused in (True, False):
+        monkeypatch.setattr(O, "UNFUSED", unfused)
+        st = nn.Adam(gpu, lr=1e-3).init_state((1000,))
+        outs = [np.asarray(st.grad2diff(A(gpu, g * (k + 1)))).copy() for k in range(3)]
+        relu, sig, sm = nn.ReLU(), nn.Sigmoid(), nn.Softmax()
+        relu._y = sig._y = sm._y = A(gpu, y)
+        res[unfused] = (outs, np.asarray(st.m).copy(), np.asarray(st.v).copy(),
+                        np.asarray(relu.backward(A(gpu, dy))).copy(), np.asarray(sig.backward(A(gpu, dy))).copy(),
+                        np.asarray(sm.backward(A(gpu, dy))).copy(), np.asarray(sm.forward(A(gpu, x))).copy(), x)
+    a, b = res[True], res[False]
+    for u, f in zip(a[0], b[0]):
+        np.testing.assert_array_equal(u, f)
+    for k, what in ((1, "adam m"), (2, "adam v"), (3, "relu backward"), (4, "sigmoid backward"), (5, "softmax backward")):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=what)
+    np.testing.assert_allclose(b[6], softmax64(b[7].astype(np.float64)), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(a[6], b[6], rtol=1e-6, atol=1e-9)

@@ -60,6 +60,9 @@ PROTOTYPES = {
     "vkp_fill_u32": (C.c_int, [_vp, _vp, _sz, _u32, C.POINTER(_vp)]),
     "vkp_gemm": (C.c_int, [_vp, C.c_int, C.c_int, _u32, _u32, _u32, _vp, _vp, _vp, _vp, C.c_int,
                            C.POINTER(_vp)]),
+    "vkp_nn_adam": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz] + [C.c_float] * 8 + [C.POINTER(_vp)]),
+    "vkp_nn_activation_backward": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz, C.POINTER(_vp)]),
+    "vkp_nn_softmax_forward": (C.c_int, [_vp, _vp, _vp, _u32, _u32, C.POINTER(_vp)]),
     "vkp_job_wait": (C.c_int, [_vp, _u64]),
     "vkp_job_done": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "vkp_job_release": (C.c_int, [_vp]),
@@ -296,6 +299,21 @@ class Device:
         job = _vp()
         _check(lib.vkp_gemm(self._ctx, int(transA), int(transB), M, N, K, A.ptr, B.ptr, Cbuf.ptr,
                             bias.ptr if bias is not None else None, flags, C.byref(job)))
+        return Job(job.value)
+
+    def nn_adam(self, grad: Buffer, m: Buffer, v: Buffer, diff: Buffer, *scalars: float) -> Job:
+        job = _vp()
+        _check(lib.vkp_nn_adam(self._ctx, grad.ptr, m.ptr, v.ptr, diff.ptr, grad.size(), *scalars, C.byref(job)))
+        return Job(job.value)
+
+    def nn_activation_backward(self, kind: int, y: Buffer, dy: Buffer, dx: Buffer) -> Job:
+        job = _vp()
+        _check(lib.vkp_nn_activation_backward(self._ctx, kind, y.ptr, dy.ptr, dx.ptr, y.size(), C.byref(job)))
+        return Job(job.value)
+
+    def nn_softmax_forward(self, x: Buffer, y: Buffer, rows: int, cols: int) -> Job:
+        job = _vp()
+        _check(lib.vkp_nn_softmax_forward(self._ctx, x.ptr, y.ptr, rows, cols, C.byref(job)))
         return Job(job.value)
 
     def wait(self):

@@ -25,7 +25,10 @@ constexpr int TM = 64, TN = 64, TK = 16;
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
-                 const float* __restrict__ bias, uint32_t M, uint32_t N, uint32_t K, int accumulate) {
+                 const float* __restrict__ bias, uint32_t M, uint32_t N, uint32_t K, int accumulate,
+                 uint32_t k_per_split) {
+  // blockIdx.z selects a K slice (split-K for skinny problems); with more than one slice C is a
+  // [splits][M][N] partial buffer and bias / accumulate are applied by simt_splitk_reduce.
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const uint32_t tid = threadIdx.x;
@@ -37,7 +40,10 @@ gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, float
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
 
-  for (uint32_t k0 = 0; k0 < K; k0 += TK) {
+  const uint32_t k_begin = blockIdx.z * k_per_split;
+  const uint32_t k_end = (k_begin + k_per_split < K) ? k_begin + k_per_split : K;
+  C += (size_t)blockIdx.z * M * N;
+  for (uint32_t k0 = k_begin; k0 < k_end; k0 += TK) {
     // stage A tile (TM x TK) and B tile (TK x TN); the fast thread index follows the
     // contiguous direction of the source
 #pragma unroll
@@ -47,7 +53,7 @@ gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, float
       if (TA) { m = e % TM; k = e / TM; } else { k = e % TK; m = e / TK; }
       const uint32_t gm = m0 + m, gk = k0 + k;
       float v = 0.f;
-      if (gm < M && gk < K) v = TA ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk];
+      if (gm < M && gk < k_end) v = TA ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk];
       As[k][m] = v;
     }
 #pragma unroll
@@ -57,7 +63,7 @@ gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, float
       if (TB) { k = e % TK; n = e / TK; } else { n = e % TN; k = e / TN; }
       const uint32_t gn = n0 + n, gk = k0 + k;
       float v = 0.f;
-      if (gn < N && gk < K) v = TB ? B[(size_t)gn * K + gk] : B[(size_t)gk * N + gn];
+      if (gn < N && gk < k_end) v = TB ? B[(size_t)gn * K + gk] : B[(size_t)gk * N + gn];
       Bs[k][n] = v;
     }
     __syncthreads();
@@ -91,15 +97,55 @@ gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, float
   }
 }
 
+__global__ void __launch_bounds__(256)
+simt_splitk_reduce(const float* __restrict__ part, float* __restrict__ C, const float* __restrict__ bias, uint32_t M,
+                   uint32_t N, uint32_t splits, int accumulate) {
+  const size_t mn = (size_t)M * N;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < mn; i += (size_t)gridDim.x * blockDim.x) {
+    float acc = part[i];
+    for (uint32_t s = 1; s < splits; s++) acc += part[s * mn + i];   // fixed order: deterministic
+    if (bias) acc += bias[i % N];
+    C[i] = accumulate ? (C[i] + acc) : acc;
+  }
+}
+
 int gemm_simt(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
               const float* B, float* C, const float* bias, int accumulate) {
-  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
+  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, 1);
   VKP_CHECK(grid.y <= 65535, "gemm_simt: M too large for the fallback kernel");
-  if (!transA && !transB) gemm_simt_kernel<false, false><<<grid, 256, 0, ctx->stream>>>(A, B, C, bias, M, N, K, accumulate);
-  else if (!transA && transB) gemm_simt_kernel<false, true><<<grid, 256, 0, ctx->stream>>>(A, B, C, bias, M, N, K, accumulate);
-  else if (transA && !transB) gemm_simt_kernel<true, false><<<grid, 256, 0, ctx->stream>>>(A, B, C, bias, M, N, K, accumulate);
-  else gemm_simt_kernel<true, true><<<grid, 256, 0, ctx->stream>>>(A, B, C, bias, M, N, K, accumulate);
-  return vkp_after_launch(ctx, "gemm_simt");
+  // skinny problems (few output tiles, long K): split K over blockIdx.z so that every SM has work
+  uint32_t splits = 1;
+  const uint64_t tiles = (uint64_t)grid.x * grid.y;
+  if (tiles < 2ull * ctx->sms && K >= 512) {
+    uint64_t want = (4ull * ctx->sms + tiles - 1) / tiles;
+    if (want > K / 128) want = K / 128;
+    if (want > 256) want = 256;
+    splits = (uint32_t)(want < 1 ? 1 : want);
+  }
+  uint32_t k_per = (K + splits - 1) / splits;
+  k_per = (k_per + TK - 1) / TK * TK;
+  splits = K ? (K + k_per - 1) / k_per : 1;
+  if (splits < 1) splits = 1;
+  grid.z = splits;
+  float* dst = C;
+  if (splits > 1) {
+    void* ws;
+    VKP_TRY(vkp_workspace(ctx, 0, (size_t)splits * M * N * sizeof(float), &ws));
+    dst = static_cast<float*>(ws);
+  }
+  const float* kb = splits > 1 ? nullptr : bias;
+  const int ka = splits > 1 ? 0 : accumulate;
+  if (!transA && !transB) gemm_simt_kernel<false, false><<<grid, 256, 0, ctx->stream>>>(A, B, dst, kb, M, N, K, ka, k_per);
+  else if (!transA && transB) gemm_simt_kernel<false, true><<<grid, 256, 0, ctx->stream>>>(A, B, dst, kb, M, N, K, ka, k_per);
+  else if (transA && !transB) gemm_simt_kernel<true, false><<<grid, 256, 0, ctx->stream>>>(A, B, dst, kb, M, N, K, ka, k_per);
+  else gemm_simt_kernel<true, true><<<grid, 256, 0, ctx->stream>>>(A, B, dst, kb, M, N, K, ka, k_per);
+  VKP_TRY(vkp_after_launch(ctx, "gemm_simt"));
+  if (splits > 1) {
+    simt_splitk_reduce<<<vkp_grid_for(ctx, (size_t)M * N, 256, 8), 256, 0, ctx->stream>>>(dst, C, bias, M, N, splits,
+                                                                                        accumulate);
+    VKP_TRY(vkp_after_launch(ctx, "gemm_simt_splitk_reduce"));
+  }
+  return VKP_OK;
 }
 
 }  // namespace

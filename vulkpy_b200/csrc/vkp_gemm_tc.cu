@@ -135,7 +135,9 @@ template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                float* __restrict__ C, const float* __restrict__ bias, uint32_t M, uint32_t N, uint32_t K,
-               int accumulate) {
+               int accumulate, uint32_t splits, uint32_t kb_per_split) {
+  // splits > 1 (split-K for problems with fewer output tiles than SMs): work item = (tile, split),
+  // C is then a [splits][M][N] partial buffer and bias / accumulate are applied by splitk_reduce.
   using cfg = Cfg<BN>;
   constexpr int STAGES = cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -151,8 +153,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
-  const uint32_t num_tiles = m_blocks * n_blocks;
+  const uint32_t num_tiles = m_blocks * n_blocks * splits;     // work items
   const uint32_t k_blocks = (K + BK - 1) / BK;
+  auto k_range = [&](uint32_t work, uint32_t& kb0, uint32_t& kb1) {
+    const uint32_t sp = work % splits;
+    kb0 = sp * kb_per_split;
+    kb1 = (kb0 + kb_per_split < k_blocks) ? kb0 + kb_per_split : k_blocks;
+  };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -183,7 +190,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   // GROUP_M consecutive m-blocks share their B tiles in L2
   constexpr uint32_t GROUP_M = 16;
-  auto tile_coords = [&](uint32_t tile, uint32_t& mb, uint32_t& nb) {
+  auto tile_coords = [&](uint32_t work, uint32_t& mb, uint32_t& nb) {
+    const uint32_t tile = work / splits;
     const uint32_t per_group = GROUP_M * n_blocks;
     const uint32_t g = tile / per_group;
     const uint32_t first_m = g * GROUP_M;
@@ -200,7 +208,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         uint32_t mb, nb;
         tile_coords(tile, mb, nb);
-        for (uint32_t kb = 0; kb < k_blocks; kb++) {
+        uint32_t kb0, kb1;
+        k_range(tile, kb0, kb1);
+        for (uint32_t kb = kb0; kb < kb1; kb++) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           uint8_t* st = smem + stage * cfg::STAGE_BYTES;
           const uint32_t fb = smem_u32(&full_bar[stage]);
@@ -221,7 +231,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (uint32_t kb = 0; kb < k_blocks; kb++) {
+        uint32_t kb0, kb1;
+        k_range(tile, kb0, kb1);
+        for (uint32_t kb = kb0; kb < kb1; kb++) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           mbar_wait(smem_u32(&conv_bar[stage]), phase);
           tcgen05_fence_after();
@@ -233,12 +245,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; k++) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);   // 32 bytes per k-step
-            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, ((kb - kb0) | k) != 0);
             umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
             umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
           }
           tcgen05_commit(smem_u32(&empty_bar[stage]));
-          if (kb == k_blocks - 1) tcgen05_commit(smem_u32(&tfull_bar[acc]));
+          if (kb == kb1 - 1) tcgen05_commit(smem_u32(&tfull_bar[acc]));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -249,7 +261,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ctid = threadIdx.x - 256;   // 0..127
     uint32_t stage = 0, phase = 0;
     for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      for (uint32_t kb = 0; kb < k_blocks; kb++) {
+      uint32_t kb0, kb1;
+      k_range(tile, kb0, kb1);
+      for (uint32_t kb = kb0; kb < kb1; kb++) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         uint8_t* st = smem + stage * cfg::STAGE_BYTES;
         split_tile(st, st + A_TILE_BYTES, A_TILE_BYTES, ctid, 128);
@@ -277,7 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld32(taddr + c, v);
         const uint32_t col0 = nb * BN + c;
         if (row < M && col0 < N) {
-          float* dst = C + (size_t)row * N + col0;
+          float* dst = C + (size_t)(tile % splits) * M * N + (size_t)row * N + col0;
           const int ncol = (N - col0) < 32u ? (int)(N - col0) : 32;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -310,6 +324,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg::TMEM_COLS)
                  : "memory");
+  }
+}
+
+// C = (accumulate ? C : 0) + bias + sum_s part[s]   (fixed order: deterministic)
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ C, const float* __restrict__ bias,
+                     uint32_t M, uint32_t N, uint32_t splits, int accumulate) {
+  const size_t mn = (size_t)M * N;
+  for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4; i < mn; i += (size_t)gridDim.x * blockDim.x * 4) {
+    float4 acc = *reinterpret_cast<const float4*>(part + i);
+    for (uint32_t s2 = 1; s2 < splits; s2++) {
+      const float4 p = *reinterpret_cast<const float4*>(part + s2 * mn + i);
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    if (bias) {
+      const float4 bv = *reinterpret_cast<const float4*>(bias + (i % N));
+      acc.x += bv.x; acc.y += bv.y; acc.z += bv.z; acc.w += bv.w;
+    }
+    if (accumulate) {
+      const float4 cv = *reinterpret_cast<const float4*>(C + i);
+      acc.x += cv.x; acc.y += cv.y; acc.z += cv.z; acc.w += cv.w;
+    }
+    *reinterpret_cast<float4*>(C + i) = acc;
   }
 }
 
@@ -370,9 +407,34 @@ int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, float* C, const flo
   VKP_TRY(make_map(&tmB, Bt, N, K, BN));
   VKP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
   const uint32_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const unsigned grid = tiles < (uint32_t)ctx->sms ? tiles : (unsigned)ctx->sms;
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, cfg::SMEM_BYTES, ctx->stream>>>(tmA, tmB, C, bias, M, N, K, accumulate);
-  return vkp_after_launch(ctx, "gemm_tc(tcgen05 3xTF32)");
+  const uint32_t k_blocks = (K + BK - 1) / BK;
+  // split-K when the output has fewer tiles than SMs and K is long: partials in workspace slot 0
+  uint32_t splits = 1;
+  if (tiles * 2 <= (uint32_t)ctx->sms && k_blocks >= 16) {
+    splits = (uint32_t)ctx->sms / tiles;
+    if (splits > k_blocks / 8) splits = k_blocks / 8;
+    if (splits > 16) splits = 16;
+    if (splits < 1) splits = 1;
+  }
+  uint32_t kb_per = (k_blocks + splits - 1) / splits;
+  splits = (k_blocks + kb_per - 1) / kb_per;
+  float* dst = C;
+  if (splits > 1) {
+    void* ws;
+    VKP_TRY(vkp_workspace(ctx, 0, (size_t)splits * M * N * sizeof(float), &ws));
+    dst = static_cast<float*>(ws);
+  }
+  const uint32_t work = tiles * splits;
+  const unsigned grid = work < (uint32_t)ctx->sms ? work : (unsigned)ctx->sms;
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, cfg::SMEM_BYTES, ctx->stream>>>(
+      tmA, tmB, dst, splits > 1 ? nullptr : bias, M, N, K, splits > 1 ? 0 : accumulate, splits, kb_per);
+  VKP_TRY(vkp_after_launch(ctx, "gemm_tc(tcgen05 3xTF32)"));
+  if (splits > 1) {
+    const unsigned rgrid = vkp_grid_for(ctx, ((size_t)M * N + 3) / 4, 256, 8);
+    splitk_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(dst, C, bias, M, N, splits, accumulate);
+    VKP_TRY(vkp_after_launch(ctx, "gemm_splitk_reduce"));
+  }
+  return VKP_OK;
 }
 
 }  // namespace

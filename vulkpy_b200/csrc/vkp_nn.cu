@@ -1,0 +1,145 @@
+// vkp_nn.cu -- fused kernels for the vulkpy.nn compositions.
+//
+// The reference builds these from chains of single-op shaders (Adam: 13 jobs and 5 temporaries
+// per tensor, nn/optimizers.py:235-253; Softmax.forward: 5 jobs, nn/layers.py:297-300; the
+// activation backward passes: 3 jobs each, nn/layers.py:207-210,262-267,320-323).  Each kernel
+// here performs the SAME float32 operations in the SAME order with one rounding per reference
+// operation (the library is compiled with -fmad=false), so results are bit-identical to the
+// op-by-op path; only the HBM round trips between the operations disappear.
+#include "vkp_common.cuh"
+#include "vkp_math.cuh"
+#include "vkp_tables.cuh"
+
+namespace {
+
+constexpr int NB = 256;
+
+// m = m*b1 + (1-b1)*g ; v = v*b2 + (1-b2)*g^2 ; diff = (m/(1-b1t)) * (-lr) / (sqrt(v/(1-b2t)) + eps)
+// scalars arrive already rounded to float32 exactly as they cross the reference's boundary
+// (_vkarray.cc:841-845).  g^2 is the correctly rounded square (what pow(g, 2.0) returns).
+__global__ void __launch_bounds__(NB)
+adam_kernel(const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, float* __restrict__ diff,
+            size_t n, float b1, float omb1, float b2, float omb2, float c1, float c2, float eps, float neg_lr) {
+  for (size_t i = blockIdx.x * (size_t)NB + threadIdx.x; i < n; i += (size_t)gridDim.x * NB) {
+    const float gi = g[i];
+    float mi = m[i] * b1;          // self.m *= beta1
+    mi = mi + omb1 * gi;           // self.m += (1 - beta1) * grad
+    float vi = v[i] * b2;          // self.v *= beta2
+    vi = vi + omb2 * (gi * gi);    // self.v += (1 - beta2) * grad ** 2
+    m[i] = mi;
+    v[i] = vi;
+    float mh = mi / c1;            // mhat = m / (1 - beta1t)
+    float vh = vi / c2;            // vhat = v / (1 - beta2t)
+    vh = __fsqrt_rn(vh);           // vhat.sqrt(inplace=True)
+    vh = vh + eps;                 // vhat += eps
+    mh = mh * neg_lr;              // mhat *= -lr
+    diff[i] = mh / vh;             // mhat /= vhat
+  }
+}
+
+// dx = (sign(y) max 0) * dy   (ReLU.backward, nn/layers.py:207-210)
+__global__ void __launch_bounds__(NB)
+relu_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)NB + threadIdx.x; i < n; i += (size_t)gridDim.x * NB)
+    dx[i] = fmaxf(vkpm::sign_f(y[i]), 0.0f) * dy[i];
+}
+
+// dx = ((1 - y) * y) * dy      (Sigmoid.backward / Softmax.backward, nn/layers.py:262-267,320-323)
+__global__ void __launch_bounds__(NB)
+ymul_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)NB + threadIdx.x; i < n; i += (size_t)gridDim.x * NB) {
+    const float yi = y[i];
+    dx[i] = ((1.0f - yi) * yi) * dy[i];
+  }
+}
+
+// Softmax.forward over axis 1 of [rows, cols] (nn/layers.py:297-300): X = x - max(x); X = exp(X);
+// X /= sum(X).  One warp per row; max and the sum run in the reference's serial order
+// k = 0..cols-1 per row when cols <= 32 (each lane holds one element, lane 0 folds them through
+// shuffles), longer rows use per-lane partials + a shuffle tree.
+__global__ void __launch_bounds__(NB)
+softmax_fwd_kernel(const __grid_constant__ vkpm::MathCoef coef, const float* __restrict__ x, float* __restrict__ y,
+                   uint32_t rows, uint32_t cols) {
+  const vkpt::LaneTables tab(coef);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps_per_grid = gridDim.x * (NB / 32);
+  const uint32_t nwarp_rows = (rows + warps_per_grid - 1) / warps_per_grid;
+  for (uint32_t it = 0; it < nwarp_rows; it++) {   // warp-uniform trip count (shuffles inside)
+    const uint32_t row = (blockIdx.x * (NB / 32) + (threadIdx.x >> 5)) + it * warps_per_grid;
+    const bool live_row = row < rows;
+    const float* xr = x + (size_t)(live_row ? row : 0) * cols;
+    float* yr = y + (size_t)(live_row ? row : 0) * cols;
+    // max
+    float mx = -INFINITY;
+    for (uint32_t k = lane; k < cols; k += 32) mx = fmaxf(mx, xr[k]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // exp(x - max), kept in registers for short rows, written to y otherwise
+    float sum = 0.f;
+    const uint32_t nk = (cols + 31) / 32;
+    for (uint32_t j = 0; j < nk; j++) {
+      const uint32_t k = j * 32 + lane;
+      const bool ok = k < cols;
+      bool sp = false;
+      const float d = ok ? (xr[k] - mx) : 0.f;
+      float e = vkpm::exp_core(d, tab, sp);
+      if (sp) e = vkpm::exp_f(d);
+      if (!ok) e = 0.f;
+      if (live_row && ok) yr[k] = e;
+      // serial fold of this group of 32 in index order (lane 0 accumulates)
+      for (uint32_t l = 0; l < 32; l++) {
+        const float el = __shfl_sync(0xffffffffu, e, l);
+        if (j * 32 + l < cols) sum = sum + el;
+      }
+    }
+    __syncwarp();
+    for (uint32_t k = lane; k < cols; k += 32)
+      if (live_row) yr[k] = yr[k] / sum;
+  }
+}
+
+}  // namespace
+
+#define NN_PROLOGUE(...)                                   \
+  VKP_CHECK(ctx, "vkp_nn: null context");                  \
+  VKP_TRY(vkp_make_current(ctx));                          \
+  std::lock_guard<std::mutex> g_(ctx->mu);                 \
+  void* bufs_[] = {__VA_ARGS__};                           \
+  VKP_TRY(vkp_prepare_buffers(ctx, bufs_, (int)(sizeof(bufs_) / sizeof(void*))))
+
+extern "C" int vkp_nn_adam(vkp_ctx* ctx, const float* grad, float* m, float* v, float* diff, size_t n,
+                           float beta1, float one_minus_beta1, float beta2, float one_minus_beta2,
+                           float one_minus_beta1t, float one_minus_beta2t, float eps, float neg_lr,
+                           vkp_job** job) {
+  NN_PROLOGUE((void*)grad, m, v, diff);
+  if (n) {
+    adam_kernel<<<vkp_grid_for(ctx, n, NB, 16), NB, 0, ctx->stream>>>(grad, m, v, diff, n, beta1, one_minus_beta1, beta2,
+                                                                      one_minus_beta2, one_minus_beta1t,
+                                                                      one_minus_beta2t, eps, neg_lr);
+    VKP_TRY(vkp_after_launch(ctx, "nn_adam"));
+  }
+  return vkp_finish_op(ctx, job);
+}
+
+extern "C" int vkp_nn_activation_backward(vkp_ctx* ctx, int kind, const float* y, const float* dy, float* dx,
+                                          size_t n, vkp_job** job) {
+  NN_PROLOGUE((void*)y, (void*)dy, dx);
+  VKP_CHECK(kind == 0 || kind == 1, "vkp_nn_activation_backward: kind must be 0 (relu) or 1 (y(1-y))");
+  if (n) {
+    const unsigned grid = vkp_grid_for(ctx, n, NB, 16);
+    if (kind == 0) relu_bwd_kernel<<<grid, NB, 0, ctx->stream>>>(y, dy, dx, n);
+    else ymul_bwd_kernel<<<grid, NB, 0, ctx->stream>>>(y, dy, dx, n);
+    VKP_TRY(vkp_after_launch(ctx, "nn_activation_backward"));
+  }
+  return vkp_finish_op(ctx, job);
+}
+
+extern "C" int vkp_nn_softmax_forward(vkp_ctx* ctx, const float* x, float* y, uint32_t rows, uint32_t cols,
+                                      vkp_job** job) {
+  NN_PROLOGUE((void*)x, y);
+  if (rows && cols) {
+    const unsigned grid = vkp_grid_for(ctx, rows, NB / 32, 16);
+    softmax_fwd_kernel<<<grid, NB, 0, ctx->stream>>>(vkpt::host_coef(), x, y, rows, cols);
+    VKP_TRY(vkp_after_launch(ctx, "nn_softmax_forward"));
+  }
+  return vkp_finish_op(ctx, job);
+}

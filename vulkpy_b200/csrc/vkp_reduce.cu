@@ -17,6 +17,8 @@
 // reference's serial k = 0..axis-1 order, the parity tolerance is stated in tests/.
 #include "vkp_common.cuh"
 
+#include <cstdlib>
+
 int vkp_broadcast_copy_3d(vkp_ctx* ctx, const float* src, float* dst, uint32_t prev, uint32_t axis,
                           uint32_t post);  // vkp_broadcast.cu
 
@@ -209,40 +211,44 @@ __global__ void reduce_strided(const float* __restrict__ in, float* __restrict__
 }
 
 template <int OP>
-int reduce_rows(vkp_ctx* ctx, const float* in, float* out, uint32_t nrows, uint64_t len) {
+int reduce_rows(vkp_ctx* ctx, const float* in, float* out, uint32_t nrows, uint64_t len, uint64_t ws_off = 0) {
   if (nrows == 0) return VKP_OK;
   if (len <= 1024) {
     int lpr = 1;
     while (lpr < 32 && (uint64_t)lpr * 4 < len) lpr <<= 1;
     const unsigned gpb = RB_BLOCK / lpr;
-    const unsigned grid = vkp_grid_for(ctx, nrows, gpb, 8);
+    const unsigned grid = (nrows + gpb - 1) / gpb;
     reduce_rows_group<OP><<<grid, RB_BLOCK, 0, ctx->stream>>>(in, out, nrows, (uint32_t)len, lpr);
     return vkp_after_launch(ctx, "reduce_rows_group");
   }
-  // long rows: split a row across CTAs when there are too few rows to fill the machine
-  const uint64_t target_ctas = (uint64_t)ctx->sms * 8;
+  // long rows: one CTA per <= 32 Ki-element segment (many small CTAs balance better than a
+  // persistent grid: profiles/r01_micro_stream_variants.txt); rows are split only when there are
+  // too few of them to fill the machine.  Partials of a split go to the workspace at `ws_off`
+  // and are folded by a recursive call that uses the space behind them.
+  const uint64_t target_ctas = (uint64_t)ctx->sms * 32;
   uint32_t nsplit = 1;
   if (nrows < target_ctas) {
     uint64_t want = (target_ctas + nrows - 1) / nrows;
-    const uint64_t max_split = (len + 8191) / 8192;  // at least 8192 elements per CTA
+    const uint64_t max_split = (len + 16383) / 16384;  // at least 16 Ki elements per CTA
     if (want > max_split) want = max_split;
-    if (want > 1024) want = 1024;  // the second pass then always takes the lane-group kernel
     nsplit = (uint32_t)(want < 1 ? 1 : want);
   }
   uint64_t seg = (len + nsplit - 1) / nsplit;
   seg = (seg + 3) & ~3ull;
   nsplit = (uint32_t)((len + seg - 1) / seg);
   const uint64_t jobs = (uint64_t)nrows * nsplit;
-  const unsigned grid = (unsigned)(jobs < target_ctas * 4 ? jobs : target_ctas * 4);
+  VKP_CHECK(jobs < (1ull << 31), "reduction too large");
+  const unsigned grid = (unsigned)jobs;
   if (nsplit == 1) {
     reduce_rows_block<OP><<<grid, RB_BLOCK, 0, ctx->stream>>>(in, out, nrows, len, 1, seg);
     return vkp_after_launch(ctx, "reduce_rows_block");
   }
   void* ws;
-  VKP_TRY(vkp_workspace(ctx, 0, jobs * sizeof(float), &ws));
-  reduce_rows_block<OP><<<grid, RB_BLOCK, 0, ctx->stream>>>(in, (float*)ws, nrows, len, nsplit, seg);
+  VKP_TRY(vkp_workspace(ctx, 0, (ws_off + jobs) * sizeof(float) * 2 + 4096, &ws));
+  float* part = static_cast<float*>(ws) + ws_off;
+  reduce_rows_block<OP><<<grid, RB_BLOCK, 0, ctx->stream>>>(in, part, nrows, len, nsplit, seg);
   VKP_TRY(vkp_after_launch(ctx, "reduce_rows_block"));
-  return reduce_rows<OP>(ctx, (const float*)ws, out, nrows, nsplit);
+  return reduce_rows<OP>(ctx, part, out, nrows, nsplit, ws_off + ((jobs + 63) & ~63ull));
 }
 
 template <int OP>
@@ -251,14 +257,16 @@ int reduce_axis(vkp_ctx* ctx, const float* in, float* out, uint32_t prev, uint32
   if (post == 1) return reduce_rows<OP>(ctx, in, out, prev, axis);
   const bool vec = (post % 4 == 0) && ((((uintptr_t)in) & 15) == 0) && ((((uintptr_t)out) & 15) == 0);
   const uint32_t cols = vec ? post / 4 : post;
+  // threads along `post`: up to VKP_COLS_BX (default 128) lanes wide so that a CTA row is a long
+  // contiguous run (2 KiB with float4), the rest of the 256 threads split the axis
+  static const uint32_t max_bx = getenv("VKP_COLS_BX") ? (uint32_t)atoi(getenv("VKP_COLS_BX")) : 64u;
   uint32_t bx = 1;
-  while (bx < 32 && bx < cols) bx <<= 1;
-  if (cols >= 64 && !vec) bx = 64;
+  while (bx < max_bx && bx < cols) bx <<= 1;
   const uint32_t by = 256 / bx;
   const uint32_t ctile = bx * (vec ? 4 : 1);
   const uint32_t ntile = (post + ctile - 1) / ctile;
   const uint64_t base_jobs = (uint64_t)prev * ntile;
-  const uint64_t target_ctas = (uint64_t)ctx->sms * 8;
+  const uint64_t target_ctas = (uint64_t)ctx->sms * 32;
   uint32_t nsplit = 1;
   if (base_jobs < target_ctas) {
     uint64_t want = (target_ctas + base_jobs - 1) / base_jobs;
@@ -270,7 +278,8 @@ int reduce_axis(vkp_ctx* ctx, const float* in, float* out, uint32_t prev, uint32
   nsplit = seg ? (axis + seg - 1) / seg : 1;
   if (nsplit < 1) nsplit = 1;
   const uint64_t jobs = base_jobs * nsplit;
-  const unsigned grid = (unsigned)(jobs < target_ctas * 4 ? jobs : target_ctas * 4);
+  VKP_CHECK(jobs < (1ull << 31), "reduction too large");
+  const unsigned grid = (unsigned)jobs;
   float* dst = out;
   if (nsplit > 1) {
     void* ws;
@@ -285,8 +294,7 @@ int reduce_axis(vkp_ctx* ctx, const float* in, float* out, uint32_t prev, uint32
   VKP_TRY(vkp_after_launch(ctx, "reduce_cols"));
   if (nsplit > 1) {
     // second pass over [prev, nsplit, post]; nsplit is small so it never splits again
-    const uint64_t jobs2 = base_jobs;
-    const unsigned grid2 = (unsigned)(jobs2 < target_ctas * 4 ? jobs2 : target_ctas * 4);
+    const unsigned grid2 = (unsigned)base_jobs;
     if (vec)
       reduce_cols<OP, 4><<<grid2, block, 0, ctx->stream>>>(dst, out, prev, nsplit, post, 1, nsplit);
     else

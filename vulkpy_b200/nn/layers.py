@@ -9,8 +9,16 @@ from ..vkarray import GPU, Array, DataShape, BatchAffineParams
 from .core import Module, Optimizer, Regularizer
 from .parameters import Parameter
 from .initializers import HeNormal
+from . import optimizers as _opt
 
 __all__ = ["Dense", "ReLU", "Sigmoid", "Softmax"]
+
+
+def _fused_backward(kind: int, y: Array, dy: Array) -> Array:
+    dx = Array(dy._gpu, shape=y.shape)
+    dx.job = dy._gpu.gpu.nn_activation_backward(kind, y.buffer, dy.buffer, dx.buffer)
+    dx._keep = [y, dy]
+    return dx
 
 Init = Callable[[GPU, Iterable[int]], Array]
 
@@ -75,6 +83,8 @@ class ReLU(Module):
         return x.max(0.0)
 
     def backward(self, dy: Array) -> Array:
+        if not _opt.UNFUSED:
+            return _fused_backward(0, self._y, dy)
         dx = self._y.sign()
         dx.max(0.0, inplace=True)
         dx *= dy
@@ -91,6 +101,8 @@ class Sigmoid(Module):
         return 1.0 / y
 
     def backward(self, dy: Array) -> Array:
+        if not _opt.UNFUSED:
+            return _fused_backward(1, self._y, dy)
         dx = 1.0 - self._y
         dx *= self._y
         dx *= dy
@@ -102,12 +114,19 @@ class Softmax(Module):
     of the Jacobian only, like the reference (layers.py:270-323)."""
 
     def forward(self, x: Array) -> Array:
+        if not _opt.UNFUSED and len(x.shape) == 2:
+            y = Array(x._gpu, shape=x.shape)
+            y.job = x._gpu.gpu.nn_softmax_forward(x.buffer, y.buffer, x.shape[0], x.shape[1])
+            y._keep = [x]
+            return y
         e = x - x.maximum(axis=1, rebroadcast=True)
         e.exp(inplace=True)
         e /= e.sum(axis=1, rebroadcast=True)
         return e
 
     def backward(self, dy: Array) -> Array:
+        if not _opt.UNFUSED:
+            return _fused_backward(1, self._y, dy)
         dx = 1.0 - self._y
         dx *= self._y
         dx *= dy

@@ -7,6 +7,7 @@ so that every intermediate is rounded to float32 exactly where the reference rou
 from __future__ import annotations
 
 import logging
+import os
 from typing import Iterable
 
 from ..vkarray import GPU, Array, zeros
@@ -15,6 +16,9 @@ from .core import Optimizer, OptimizerState
 __all__ = ["SGD", "SGDState", "AdaGrad", "AdaGradState", "Adam", "AdamState", "Optimizer", "OptimizerState"]
 
 logger = logging.getLogger("vulkpy")
+
+# VULKPY_NN_UNFUSED=1 keeps the reference's op-by-op compositions (tests compare both paths)
+UNFUSED = os.environ.get("VULKPY_NN_UNFUSED", "0") == "1"
 
 
 class SGDState(OptimizerState):
@@ -75,6 +79,17 @@ class AdamState(OptimizerState):
 
     def grad2diff(self, grad: Array) -> Array:
         o = self.opt
+        if not UNFUSED:
+            # one kernel with the same operations, order and float32 roundings as the chain below
+            self.beta1t *= o.beta1
+            self.beta2t *= o.beta2
+            diff = Array(grad._gpu, shape=grad.shape)
+            diff.job = grad._gpu.gpu.nn_adam(grad.buffer, self.m.buffer, self.v.buffer, diff.buffer,
+                                              o.beta1, 1 - o.beta1, o.beta2, 1 - o.beta2,
+                                              1 - self.beta1t, 1 - self.beta2t, o.eps, -o.lr)
+            diff._keep = [grad, self.m, self.v]
+            self.m.job = self.v.job = diff.job
+            return diff
         self.m *= o.beta1
         self.m += (1 - o.beta1) * grad
         self.v *= o.beta2
