@@ -40,6 +40,7 @@ struct FScalar {
   __device__ float operator()(float a) const { return REV ? B()(s, a) : B()(a, s); }
 };
 
+struct USquare { __device__ float operator()(float a) const { return a * a; } };  // pow(x, 2.0), correctly rounded incl. ties
 struct UAbs   { __device__ float operator()(float a) const { return fabsf(a); } };
 struct USign  { __device__ float operator()(float a) const { return vkpm::sign_f(a); } };
 struct USin   { __device__ float operator()(float a) const { return sinf(a); } };
@@ -356,7 +357,11 @@ int dispatch_scalar(vkp_ctx* ctx, int sub, float s, const void* a, void* out, si
     case VKB_DIV: return launch_scalar<FDiv>(ctx, "div_scalar", false, s, a, out, n);
     case VKB_MAX: return launch_scalar<FMax>(ctx, "max_scalar", false, s, a, out, n);
     case VKB_MIN: return launch_scalar<FMin>(ctx, "min_scalar", false, s, a, out, n);
-    case VKB_POW: return launch_ew_tab<1>(ctx, "pow_scalar", TPowScalar<false>{s}, a, nullptr, out, n);
+    case VKB_POW:
+      // x ** 2.0 (MSELoss, Ridge, Adam, AdaGrad: nn/losses.py:294-296, nn/optimizers.py:131,239) is the
+      // exactly rounded square, also on ties and for negative x
+      if (s == 2.0f) return launch_ew<1>(ctx, "pow_scalar(2)", USquare(), a, nullptr, nullptr, out, n);
+      return launch_ew_tab<1>(ctx, "pow_scalar", TPowScalar<false>{s}, a, nullptr, out, n);
     case VKB_RSUB: return launch_scalar<FSub>(ctx, "rsub_scalar", true, s, a, out, n);
     case VKB_RDIV: return launch_scalar<FDiv>(ctx, "rdiv_scalar", true, s, a, out, n);
     case VKB_RPOW: return launch_ew_tab<1>(ctx, "rpow_scalar", TPowScalar<true>{s}, a, nullptr, out, n);

@@ -114,24 +114,35 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-// split a landed fp32 tile: hi = x & ~0x1fff (in place), lo = tf32(x - hi) at the same offset
+// Split a landed fp32 tile into TF32 hi / lo parts at the same (swizzled) offsets.
+//   REWRITE_HI = true : hi = RN_tf32(x) written back in place, lo = RN_tf32(x - hi)
+//                       (|x - hi - lo| <= 2^-22 |x|, independent of how the tensor core treats the
+//                       low 13 mantissa bits of an fp32 operand)
+//   REWRITE_HI = false: the hi tile stays the raw fp32 data -- the tensor core ignores the low 13
+//                       bits (truncation, verified by tests/test_gpu_gemm.py) -- and
+//                       lo = RN_tf32(x - trunc_tf32(x)); one shared-memory store less per 16 bytes
+//                       (the kernel is shared-memory-pipe bound: profiles/r01_ncu_gemm_tc.csv).
+template <bool REWRITE_HI>
 __device__ __forceinline__ void split_tile(uint8_t* hi, uint8_t* lo, int bytes, int tid, int nthreads) {
   for (int off = tid * 16; off < bytes; off += nthreads * 16) {
     uint4 x = *reinterpret_cast<uint4*>(hi + off);
     uint4 h, l;
-    // round to nearest TF32 (add half an ulp of the 10-bit mantissa, clear 13 bits): |x-hi| <= 2^-11|x|
-    h.x = (x.x + 0x1000u) & 0xffffe000u; h.y = (x.y + 0x1000u) & 0xffffe000u;
-    h.z = (x.z + 0x1000u) & 0xffffe000u; h.w = (x.w + 0x1000u) & 0xffffe000u;
+    if (REWRITE_HI) {
+      h.x = (x.x + 0x1000u) & 0xffffe000u; h.y = (x.y + 0x1000u) & 0xffffe000u;
+      h.z = (x.z + 0x1000u) & 0xffffe000u; h.w = (x.w + 0x1000u) & 0xffffe000u;
+    } else {
+      h.x = x.x & 0xffffe000u; h.y = x.y & 0xffffe000u; h.z = x.z & 0xffffe000u; h.w = x.w & 0xffffe000u;
+    }
     l.x = (__float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x)) + 0x1000u) & 0xffffe000u;
     l.y = (__float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y)) + 0x1000u) & 0xffffe000u;
     l.z = (__float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z)) + 0x1000u) & 0xffffe000u;
     l.w = (__float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w)) + 0x1000u) & 0xffffe000u;
-    *reinterpret_cast<uint4*>(hi + off) = h;
+    if (REWRITE_HI) *reinterpret_cast<uint4*>(hi + off) = h;
     *reinterpret_cast<uint4*>(lo + off) = l;
   }
 }
 
-template <int BN>
+template <int BN, bool REWRITE_HI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                float* __restrict__ C, const float* __restrict__ bias, uint32_t M, uint32_t N, uint32_t K,
@@ -266,8 +277,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (uint32_t kb = kb0; kb < kb1; kb++) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         uint8_t* st = smem + stage * cfg::STAGE_BYTES;
-        split_tile(st, st + A_TILE_BYTES, A_TILE_BYTES, ctid, 128);
-        split_tile(st + 2 * A_TILE_BYTES, st + 2 * A_TILE_BYTES + cfg::B_TILE_BYTES, cfg::B_TILE_BYTES, ctid, 128);
+        split_tile<REWRITE_HI>(st, st + A_TILE_BYTES, A_TILE_BYTES, ctid, 128);
+        split_tile<REWRITE_HI>(st + 2 * A_TILE_BYTES, st + 2 * A_TILE_BYTES + cfg::B_TILE_BYTES, cfg::B_TILE_BYTES, ctid, 128);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> tensor-core reads
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&conv_bar[stage]));
@@ -405,7 +416,9 @@ int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, float* C, const flo
   CUtensorMap tmA, tmB;
   VKP_TRY(make_map(&tmA, A, M, K, BM));
   VKP_TRY(make_map(&tmB, Bt, N, K, BN));
-  VKP_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+  static const bool rewrite_hi = getenv("VKP_TC_REWRITE_HI") != nullptr;
+  auto kernel = rewrite_hi ? gemm_tc_kernel<BN, true> : gemm_tc_kernel<BN, false>;
+  VKP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
   const uint32_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const uint32_t k_blocks = (K + BK - 1) / BK;
   // split-K when the output has fewer tiles than SMs and K is long: partials in workspace slot 0
@@ -426,7 +439,7 @@ int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, float* C, const flo
   }
   const uint32_t work = tiles * splits;
   const unsigned grid = work < (uint32_t)ctx->sms ? work : (unsigned)ctx->sms;
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, cfg::SMEM_BYTES, ctx->stream>>>(
+  kernel<<<grid, NUM_THREADS, cfg::SMEM_BYTES, ctx->stream>>>(
       tmA, tmB, dst, splits > 1 ? nullptr : bias, M, N, K, splits > 1 ? 0 : accumulate, splits, kb_per);
   VKP_TRY(vkp_after_launch(ctx, "gemm_tc(tcgen05 3xTF32)"));
   if (splits > 1) {
