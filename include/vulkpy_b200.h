@@ -55,12 +55,26 @@ VKP_API int vkp_ctx_launch_count(vkp_ctx* ctx, uint64_t* kernels);/* kernels lau
 VKP_API int vkp_ctx_mem_info(vkp_ctx* ctx, size_t* pooled_bytes, size_t* live_bytes);
 VKP_API int vkp_ctx_trim(vkp_ctx* ctx);                          /* give cached blocks back     */
 
-/* ---- buffers: GPU::createBuffer<T>/toBuffer<T> (_vkarray.cc:512-525), Buffer<T> (:38-130) */
+/* ---- buffers: GPU::createBuffer<T>/toBuffer<T> (_vkarray.cc:512-525), Buffer<T> (:38-130)
+ * Every device pointer an entry point of this library takes is the BASE pointer vkp_alloc
+ * returned (the reference binds whole buffers too: BufferInfo, _vkarray.cc:88-96); the pool
+ * tracks in-flight work per block by that pointer. */
 VKP_API int vkp_alloc(vkp_ctx* ctx, size_t bytes, void** ptr);
 VKP_API int vkp_free(vkp_ctx* ctx, void* ptr);
 /* stream-ordered host->buffer / buffer->host copies (Buffer::set, _vkarray.cc:98-108) */
 VKP_API int vkp_upload(vkp_ctx* ctx, void* dst, const void* src_host, size_t bytes);
 VKP_API int vkp_download(vkp_ctx* ctx, void* dst_host, const void* src, size_t bytes);
+/* Copy-engine transfers on side streams, for callers that pipeline steps: they overlap the
+ * compute stream and each other (PCIe is full duplex).  Host memory must be page-locked
+ * (vkp_host_alloc).  Ordering is per buffer: the upload waits for enqueued work that still uses
+ * `dst`, operations bound to `dst` wait for the upload; the download sees everything enqueued
+ * before it, later operations bound to `src` wait for it.  `*job` completes with the transfer
+ * (the source of an upload may be rewritten / the destination of a download read after that).
+ * vkp_alloc_for_upload prefers a cached block no enqueued work can still touch.  The reference
+ * has no counterpart: Buffer::set (_vkarray.cc:98-108) is a blocking memcpy into mapped memory. */
+VKP_API int vkp_alloc_for_upload(vkp_ctx* ctx, size_t bytes, void** ptr);
+VKP_API int vkp_upload_async(vkp_ctx* ctx, void* dst, const void* src_pinned, size_t bytes, vkp_job** job);
+VKP_API int vkp_download_async(vkp_ctx* ctx, void* dst_pinned, const void* src, size_t bytes, vkp_job** job);
 /* Call before the host touches `ptr` through its NumPy view.  Makes sure no earlier
  * user of a recycled block is still in flight and (prefetch!=0) migrates the pages to
  * host memory in one bulk transfer instead of page faults. */

@@ -1,5 +1,5 @@
 """Roofline sweep over every SURVEY section-8 row on one B200 (device-resident inputs, CUDA events
-on the launch stream, median of REPS after warm-up).  Writes JSON to stdout / --out.
+on the launch stream around INNER back-to-back calls, median of REPS after warm-up).  Writes JSON to stdout / --out.
 
   C2 elementwise family (incl. in-place, scalar, unary, clamp, broadcast)   bytes per BASELINE.md 4
   C3 reductions: sum/maximum/mean over axis 0 / 1 / None and rebroadcast on 16384^2
@@ -16,7 +16,9 @@ from vulkpy_b200._backend import Timer
 ap = argparse.ArgumentParser()
 ap.add_argument("--out", default=None)
 ap.add_argument("--reps", type=int, default=7)
+ap.add_argument("--inner", type=int, default=4, help="calls enqueued back to back between one event pair (hides the host enqueue latency of the first)")
 ap.add_argument("--small", action="store_true", help="quarter-size arrays (debug)")
+ap.add_argument("--only", default=None, help="comma-separated substrings; time only the rows whose name contains one")
 args = ap.parse_args()
 
 PEAK = 6555.2
@@ -42,15 +44,19 @@ def timed(fn, reps=args.reps, warm=2):
         t0, t1 = Timer(dev), Timer(dev)
         l0 = dev.launch_count()
         t0.record()
-        out = fn()
+        for _ in range(args.inner):
+            out = fn()
         t1.record()
-        ts.append(t0.elapsed_ms(t1))
-        launches = dev.launch_count() - l0
+        ts.append(t0.elapsed_ms(t1) / args.inner)
+        launches = (dev.launch_count() - l0) // args.inner
         del out
     return statistics.median(ts), min(ts), launches
 
 
 def row(name, fn, nbytes=None, flops=None, note=None):
+    if args.only and not any(k in name for k in args.only.split(",")):
+        res["rows"][name] = {"skipped": True, "tflops": 0.0}
+        return
     ms, best, launches = timed(fn)
     r = {"ms": round(ms, 4), "best_ms": round(best, 4), "launches": launches}
     if nbytes is not None:

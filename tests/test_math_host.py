@@ -23,6 +23,10 @@ void f_log(const float* x, float* y, long n){ vkpm::HostTables t; for(long i=0;i
 void f_log2(const float* x, float* y, long n){ vkpm::HostTables t; for(long i=0;i<n;i++) y[i]=vkpm::log2_fast(x[i],t); }
 void f_pow(const float* x, const float* y, float* z, long n){ vkpm::HostTables t; for(long i=0;i<n;i++) z[i]=vkpm::pow_fast(x[i],y[i],t); }
 void f_sincos(const float* x, float* s, float* c, long n){ for(long i=0;i<n;i++) vkpm::sincos_small(x[i], s[i], c[i]); }
+void f_asinh(const float* x, float* y, long n){ for(long i=0;i<n;i++) y[i]=vkpm::asinh_f(x[i]); }
+void f_bm_log(const float* x, float* y, long n){ for(long i=0;i<n;i++) y[i]=vkpm::bm_log(x[i]); }
+void f_bm_pair(const float* u0, const float* u1, float* o, long n, float mean, float sd){
+  for(long i=0;i<n;i++) vkpm::box_muller_pair(u0[i], u1[i], mean, sd, o[2*i], o[2*i+1]); }
 }
 """
 
@@ -182,3 +186,43 @@ def test_sincos_small(hm):
     assert np.abs(s - np.sin(x.astype(np.float64))).max() < 1.2e-7
     assert np.abs(c - np.cos(x.astype(np.float64))).max() < 1.2e-7
     assert ulps(s, np.sin(x.astype(np.float64))).max() < 2.0 and ulps(c, np.cos(x.astype(np.float64))).max() < 2.0
+
+
+def test_bm_log_every_input(hm):
+    """1 - u takes only the values k 2^-23, k = 1..2^23: check the Box-Muller log on all of them."""
+    k = np.arange(1, (1 << 23) + 1, dtype=np.float64)
+    x = (k * 2.0 ** -23).astype(np.float32)
+    got = call1(hm, "f_bm_log", x)
+    ref = np.log(x.astype(np.float64))
+    assert got[-1] == 0.0
+    assert ulps(got[:-1], ref[:-1]).max() < 0.95
+    assert np.all(got <= 0)
+
+
+def test_box_muller_pair(hm):
+    rng = np.random.default_rng(8)
+    n = 1_000_000
+    u0 = ((rng.integers(0, 1 << 23, n)).astype(np.float64) * 2.0 ** -23).astype(np.float32)
+    u1 = ((rng.integers(0, 1 << 23, n)).astype(np.float64) * 2.0 ** -23).astype(np.float32)
+    u0[:3] = [0.0, 1 - 2.0 ** -23, 2.0 ** -23]
+    o = np.empty(2 * n, np.float32)
+    hm.f_bm_pair(C.c_void_p(u0.ctypes.data), C.c_void_p(u1.ctypes.data), C.c_void_p(o.ctypes.data), C.c_long(n),
+                 C.c_float(0.5), C.c_float(2.0))
+    r = np.sqrt(-2 * np.log(1 - u0.astype(np.float64))) * 2.0
+    ang = (np.float32(6.28318530718) * u1).astype(np.float64)
+    assert o[0] == 0.5 and o[1] == 0.5                                   # u0 = 0: r = 0 exactly
+    assert np.abs(o[0::2] - (0.5 + r * np.sin(ang))).max() < 2e-6
+    assert np.abs(o[1::2] - (0.5 + r * np.cos(ang))).max() < 2e-6
+
+
+def test_asinh(hm):
+    rng = np.random.default_rng(9)
+    x = np.concatenate([rng.uniform(-4, 4, 1_000_000), np.exp(rng.uniform(-90, 88, 1_000_000)) * rng.choice([-1, 1], 1_000_000),
+                        [0.0, -0.0, 1e-45, -1e-40, 1e18, 9.9e17, -3e38, 0.5, 1.0]]).astype(np.float32)
+    got = call1(hm, "f_asinh", x)
+    ref = np.arcsinh(x.astype(np.float64))
+    nz = x != 0
+    assert ulps(got[nz], ref[nz]).max() < 2.5
+    assert np.all(np.signbit(got) == np.signbit(x))
+    sp = call1(hm, "f_asinh", [np.inf, -np.inf, np.nan])
+    assert sp[0] == np.inf and sp[1] == -np.inf and np.isnan(sp[2])

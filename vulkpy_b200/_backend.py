@@ -48,6 +48,9 @@ PROTOTYPES = {
     "vkp_ctx_trim": (C.c_int, [_vp]),
     "vkp_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
     "vkp_free": (C.c_int, [_vp, _vp]),
+    "vkp_alloc_for_upload": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
+    "vkp_upload_async": (C.c_int, [_vp, _vp, _vp, _sz, C.POINTER(_vp)]),
+    "vkp_download_async": (C.c_int, [_vp, _vp, _vp, _sz, C.POINTER(_vp)]),
     "vkp_upload": (C.c_int, [_vp, _vp, _vp, _sz]),
     "vkp_download": (C.c_int, [_vp, _vp, _vp, _sz]),
     "vkp_host_acquire": (C.c_int, [_vp, _vp, _sz, C.c_int]),
@@ -184,11 +187,11 @@ class _BufferBase:
     _dtype = np.dtype(np.float32)
     __slots__ = ("_dev", "ptr", "_n", "__weakref__")
 
-    def __init__(self, dev: "Device", n: int):
+    def __init__(self, dev: "Device", n: int, for_upload: bool = False):
         self._dev = dev
         self._n = int(n)
         p = _vp()
-        _check(lib.vkp_alloc(dev._ctx, self._n * 4, C.byref(p)))
+        _check((lib.vkp_alloc_for_upload if for_upload else lib.vkp_alloc)(dev._ctx, self._n * 4, C.byref(p)))
         self.ptr = p.value
 
     def size(self) -> int:
@@ -216,6 +219,20 @@ class _BufferBase:
         """Stream-ordered copy of a contiguous host array into the buffer."""
         assert host.nbytes == self._n * 4 and host.flags.c_contiguous
         _check(lib.vkp_upload(self._dev._ctx, self.ptr, host.ctypes.data, host.nbytes))
+
+    def upload_async(self, pinned: np.ndarray) -> Job:
+        """Copy-engine upload from a ``pinned_empty`` array; overlaps compute and downloads."""
+        assert pinned.nbytes == self._n * 4 and pinned.flags.c_contiguous
+        job = _vp()
+        _check(lib.vkp_upload_async(self._dev._ctx, self.ptr, pinned.ctypes.data, pinned.nbytes, C.byref(job)))
+        return Job(job.value)
+
+    def download_async(self, pinned: np.ndarray) -> Job:
+        """Copy-engine download into a ``pinned_empty`` array; overlaps compute and uploads."""
+        assert pinned.nbytes == self._n * 4 and pinned.flags.c_contiguous
+        job = _vp()
+        _check(lib.vkp_download_async(self._dev._ctx, pinned.ctypes.data, self.ptr, pinned.nbytes, C.byref(job)))
+        return Job(job.value)
 
     def __del__(self):
         p, self.ptr = self.ptr, None

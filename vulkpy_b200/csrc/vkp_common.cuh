@@ -44,6 +44,11 @@ struct vkp_block {
   uint64_t guard_seq = 0;   // work submitted up to this sequence number may still touch the block
   bool host_dirty = false;  // pages may live in host memory -> prefetch before the next kernel
   bool in_use = false;
+  uint64_t last_seq = 0;    // sequence number of the last compute-stream operation bound to the block
+  // copy-engine transfers in flight on the side streams (vkp_upload_async / vkp_download_async):
+  // the next compute operation bound to the block waits for them (vkp_prepare_buffers)
+  cudaEvent_t h2d_ev = nullptr;
+  cudaEvent_t d2h_ev = nullptr;
 };
 
 struct vkp_comm_state;  // vkp_comm.cu
@@ -52,6 +57,13 @@ struct vkp_ctx {
   int device = 0;
   int sms = 148;
   cudaStream_t stream = nullptr;
+  // copy-engine streams: host->device and device->host transfers that overlap the compute stream
+  // and each other (PCIe is full duplex); created on first use
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  // cudaMalloc bounce buffers for page-locked transfers, one per stream (0 h2d, 1 d2h, 2 compute).
+  // Copies that touch managed memory directly do not overlap across directions and run ~8 % slower
+  // (scripts/micro/copy_duplex.cu); DMA into plain device memory + a copy kernel does neither.
+  void* stage[3] = {nullptr, nullptr, nullptr};
   std::mutex mu;
   uint64_t seq = 0;        // number of operations enqueued so far
   uint64_t done_seq = 0;   // all operations with sequence <= done_seq are known complete
@@ -69,10 +81,13 @@ struct vkp_ctx {
   vkp_comm_state* comm = nullptr;
 };
 
+enum { VKP_JOB_COMPUTE = 0, VKP_JOB_UPLOAD = 1, VKP_JOB_DOWNLOAD = 2 };
+
 struct vkp_job {
   vkp_ctx* ctx;
   cudaEvent_t ev;
-  uint64_t seq;
+  uint64_t seq;   // compute-stream operations <= seq are complete once `ev` has fired (0 for uploads)
+  int kind = VKP_JOB_COMPUTE;
 };
 
 struct vkp_timer {

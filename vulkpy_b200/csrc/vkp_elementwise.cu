@@ -52,7 +52,7 @@ struct UAtan  { __device__ float operator()(float a) const { return atanf(a); } 
 struct USinh  { __device__ float operator()(float a) const { return sinhf(a); } };
 struct UCosh  { __device__ float operator()(float a) const { return coshf(a); } };
 struct UTanh  { __device__ float operator()(float a) const { return tanhf(a); } };
-struct UAsinh { __device__ float operator()(float a) const { return asinhf(a); } };
+struct UAsinh { __device__ float operator()(float a) const { return vkpm::asinh_f(a); } };
 struct UAcosh { __device__ float operator()(float a) const { return acoshf(a); } };
 struct UAtanh { __device__ float operator()(float a) const { return atanhf(a); } };
 struct UExp   { __device__ float operator()(float a) const { return vkpm::exp_f(a); } };
@@ -263,30 +263,15 @@ int launch_ew_tab(vkp_ctx* ctx, const char* name, F f, const void* in0, const vo
 // One thread per pair.  Unlike the reference dispatch (floor(n/2) invocations rounded up to a
 // workgroup, random.py:106-121) the last element of an odd-length output is always written.
 __global__ void __launch_bounds__(256)
-box_muller_kernel(const __grid_constant__ vkpm::MathCoef coef, const float* a, float* b, size_t n, float mean,
-                  float stddev) {
-  const LaneTables tab(coef);
+box_muller_kernel(const float* a, float* b, size_t n, float mean, float stddev) {
   const size_t npair = (n + 1) >> 1;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  // warp-uniform trip count: the table lookups inside log_core are shuffles
-  const size_t first = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) & ~(size_t)31;
-  for (size_t i0 = first; i0 < npair; i0 += stride) {
-    const size_t i = i0 + (threadIdx.x & 31);
-    const bool live = i < npair;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npair; i += (size_t)gridDim.x * blockDim.x) {
     const size_t j = 2 * i, k = j + 1;
-    const float2 u = live ? *reinterpret_cast<const float2*>(a + j) : make_float2(0.5f, 0.5f);  // a has an even length
-    bool sp = false;
-    const float om = 1.0f - u.x;
-    float lg = vkpm::log_core(om, tab, sp);
-    if (sp) lg = vkpm::log_f(om);
-    const float r = __fsqrt_rn(-2.0f * lg) * stddev;
-    float s, c;
-    vkpm::sincos_small(6.28318530718f * u.y, s, c);
-    const float o0 = mean + r * s, o1 = mean + r * c;
-    if (live) {
-      if (k < n) *reinterpret_cast<float2*>(b + j) = make_float2(o0, o1);
-      else b[j] = o0;
-    }
+    const float2 u = *reinterpret_cast<const float2*>(a + j);  // a has an even number of elements
+    float o0, o1;
+    vkpm::box_muller_pair(u.x, u.y, mean, stddev, o0, o1);
+    if (k < n) *reinterpret_cast<float2*>(b + j) = make_float2(o0, o1);
+    else b[j] = o0;
   }
 }
 
@@ -460,8 +445,8 @@ int vkp_launch_elementwise(vkp_ctx* ctx, int fam, int sub, void* const* bufs, in
       NEED(2, vkp_vectorscalar2_params);
       if (p->size == 0) return VKP_OK;
       const unsigned grid = vkp_grid_for(ctx, (p->size + 1) / 2, 256, 8);
-      box_muller_kernel<<<grid, 256, 0, ctx->stream>>>(vkpt::host_coef(), (const float*)bufs[0], (float*)bufs[1],
-                                                        p->size, p->scalar[0], p->scalar[1]);
+      box_muller_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)bufs[0], (float*)bufs[1], p->size,
+                                                        p->scalar[0], p->scalar[1]);
       return vkp_after_launch(ctx, "prng_box_muller");
     }
     case VKF_IBOX_MULLER: {  // A (rw, even n)
@@ -469,8 +454,8 @@ int vkp_launch_elementwise(vkp_ctx* ctx, int fam, int sub, void* const* bufs, in
       if (p->size == 0) return VKP_OK;
       VKP_CHECK(p->size % 2 == 0, "prng_ibox_muller needs an even element count (random.py:109-115)");
       const unsigned grid = vkp_grid_for(ctx, p->size / 2, 256, 8);
-      box_muller_kernel<<<grid, 256, 0, ctx->stream>>>(vkpt::host_coef(), (const float*)bufs[0], (float*)bufs[0],
-                                                        p->size, p->scalar[0], p->scalar[1]);
+      box_muller_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)bufs[0], (float*)bufs[0], p->size,
+                                                        p->scalar[0], p->scalar[1]);
       return vkp_after_launch(ctx, "prng_ibox_muller");
     }
     case VKF_RANDRANGE: {  // A ([0,1) floats), B (u32 out)

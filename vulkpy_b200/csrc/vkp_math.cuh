@@ -443,6 +443,98 @@ VKP_HD void sincos_small(float x, float& s, float& c) {
   c = ((k + 1) & 2) ? -c0 : c0;
 }
 
+// Reciprocal square root seed with ~2^-22 relative error (MUFU.RSQ on the device).
+VKP_HD float rsqrt_seed(float x) {
+#if defined(__CUDA_ARCH__)
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#else
+  return 1.0f / std::sqrt(x);
+#endif
+}
+
+// log(x) for a positive, finite, NORMAL float32 x, all in float32: x = 2^e m with m in
+// [2/3, 4/3), log(x) = e ln2 + f + f^2 Q(f), f = m - 1; Q fitted by scripts/fit/fit_bm_log.py.
+// About 0.9 ulp.  No checks for zero / negative / subnormal / inf: callers know their range.
+VKP_HD float log_pos_normal(float x) {
+  const uint32_t b = f2bits(x);
+  const int32_t e = (int32_t)(b - 0x3f2aaaabu) >> 23;
+  const float f = bits2f(b - ((uint32_t)e << 23)) - 1.0f;
+  float q = -0.135309964f;
+  q = ffma(q, f, 0.142100722f);
+  q = ffma(q, f, -0.120142907f);
+  q = ffma(q, f, 0.139542714f);
+  q = ffma(q, f, -0.166959479f);
+  q = ffma(q, f, 0.200140804f);
+  q = ffma(q, f, -0.249992505f);
+  q = ffma(q, f, 0.333331376f);
+  q = ffma(q, f, -0.50000006f);
+  return ffma((float)e, 0.693147180559945f, ffma(f, f * q, f));
+}
+
+// log(x) for x = k 2^-23, k = 1 .. 2^23 -- the only values 1 - u can take for a uniform
+// u = (bits >> 9) 2^-23 (prng_xoshiro128pp_float.comp:44).  Worst error over all 2^23 inputs:
+// 0.92 ulp (tests/test_math_host.py checks every one of them).
+VKP_HD float bm_log(float x) { return log_pos_normal(x); }
+
+// asinh(x) = sign(x) log1p(|x| + x^2 / (1 + sqrt(1 + x^2)))  (asinh.comp:22 leaves it to the driver).
+// The log1p is log(u) + (w - (u - 1)) / u with u = 1 + w, which keeps full relative accuracy for
+// tiny |x|.  About 40 float32 instructions, no branches below |x| = 1e18; error < 2.5 ulp.
+VKP_HD float asinh_f(float x) {
+  const float ax = bits2f(f2bits(x) & 0x7fffffffu);
+  if (!(ax < 1e18f)) {                                  // x^2 would overflow; inf and nan land here too
+    if (!(ax <= 3.4028234e38f)) return x;
+    const float r = log_pos_normal(ax) + 0.693147180559945f;
+    return bits2f(f2bits(r) | (f2bits(x) & 0x80000000u));
+  }
+  const float z = ax * ax;
+  const float t = 1.0f + z;
+  const float y = rsqrt_seed(t);
+  const float s0 = t * y, h = 0.5f * y;
+  const float s = ffma(ffma(-s0, s0, t), h, s0);       // sqrt(1 + x^2)
+  const float w = ax + z * rcp_seed(1.0f + s);
+  const float u = 1.0f + w;
+  const float c = w - (u - 1.0f);
+  const float r = log_pos_normal(u) + c * rcp_seed(u);
+  return bits2f(f2bits(r) | (f2bits(x) & 0x80000000u));
+}
+
+// sqrt(x) for 0 <= x <= 32 (-2 log(2^-23) = 31.9): reciprocal-square-root seed and one
+// Newton step, no range checks.  x = 0 gives 0 (the seed is clamped so 0 * y stays 0).
+VKP_HD float bm_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  y = fminf(y, 1e18f);
+  const float s = x * y, h = 0.5f * y;
+  return ffma(ffma(-s, s, x), h, s);
+#else
+  return std::sqrt(x);
+#endif
+}
+
+// One Box-Muller pair exactly in the shader's operation order (prng_box_muller.comp:26-31):
+//   r = sqrt(-2 * log(1 - u0)) * stddev;  angle = 6.28318530718f * u1;
+//   o0 = mean + r * sin(angle);  o1 = mean + r * cos(angle)
+// `om` is 1 - u0 (exact in float32 for every u0 the generator produces).  The reference leaves
+// log / sqrt / sin / cos to the Vulkan driver; here log <= 0.92 ulp, sqrt <= 1 ulp, sin / cos
+// <= 1.6 ulp, every multiply and add rounded separately as GLSL does without `precise` fusing.
+VKP_HD void box_muller_core(float om, float u1, float mean, float stddev, float& o0, float& o1) {
+  const float r = bm_sqrt(fabsf(-2.0f * bm_log(om))) * stddev;
+  float s, c;
+  sincos_small(6.28318530718f * u1, s, c);
+  o0 = mean + r * s;
+  o1 = mean + r * c;
+}
+
+VKP_HD void box_muller_pair(float u0, float u1, float mean, float stddev, float& o0, float& o1) {
+  // uniforms outside [0, 1) can only come from a caller-made buffer; keep log's domain
+  float om = 1.0f - u0;
+  om = om < 1.1920929e-7f ? 1.1920929e-7f : (om > 1.0f ? 1.0f : om);
+  box_muller_core(om, u1, mean, stddev, o0, o1);
+}
+
 VKP_HD float sign_f(float x) {
   return (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f);      // GLSL sign(): sign.comp:22
 }

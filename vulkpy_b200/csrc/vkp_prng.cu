@@ -203,26 +203,22 @@ xoshiro_stream_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ st
 // Fused uniform -> Box-Muller (random.py:60-124 + prng_box_muller.comp:19-32): a thread owns the
 // lane pair (l0, l0+1), whose draws are the adjacent outputs (2i, 2i+1); the uniforms never leave
 // registers.  n_draw = n rounded up to even (the reference draws n+1 uniforms for odd n).
-// The log uses the warp-shuffle tables, so the loops run a warp-uniform number of iterations and
-// finished threads idle on dummy values.
 __global__ void __launch_bounds__(128)
-xoshiro_normal_kernel(const __grid_constant__ vkpm::MathCoef coef, const uint4* __restrict__ state_in,
-                      uint4* __restrict__ state_out, float* __restrict__ out, const uint4* __restrict__ jump,
-                      uint32_t size, uint64_t n_draw, uint64_t n_out, uint32_t log2L, uint32_t nseg, float mean,
-                      float stddev) {
-  const vkpt::LaneTables tab(coef);
+xoshiro_normal_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ state_out, float* __restrict__ out,
+                      const uint4* __restrict__ jump, uint32_t size, uint64_t n_draw, uint64_t n_out,
+                      uint32_t log2L, uint32_t nseg, float mean, float stddev) {
   const uint32_t groups = size / 2;
   const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-  const bool valid = t < (uint64_t)groups * nseg;
-  const uint32_t p = valid ? (uint32_t)(t / groups) : 0u;
-  const uint32_t l0 = valid ? (uint32_t)(t % groups) * 2 : 0u;
+  if (t >= (uint64_t)groups * nseg) return;
+  const uint32_t p = (uint32_t)(t / groups);
+  const uint32_t l0 = (uint32_t)(t % groups) * 2;
   const uint64_t full = n_draw / size;
   const uint32_t rem = (uint32_t)(n_draw % size);   // even, like size and l0
   const uint64_t start = (uint64_t)p << log2L;
   const uint64_t seg_end = start + (1ull << log2L);
 
   uint4 s0 = state_in[l0], s1 = state_in[l0 + 1];
-  if (valid && p == 0 && full == 0 && l0 >= rem) {
+  if (p == 0 && full == 0 && l0 >= rem) {
     state_out[l0] = s0;
     state_out[l0 + 1] = s1;
   }
@@ -233,41 +229,46 @@ xoshiro_normal_kernel(const __grid_constant__ vkpm::MathCoef coef, const uint4* 
       s1 = matvec_dev(m, s1);
     }
   }
-
-  auto emit = [&](bool live, uint64_t j) {   // all 32 lanes call this together
-    float u0 = 0.5f, u1 = 0.5f;
-    if (live) {
-      u0 = u2f01(next_dev(s0));
-      u1 = u2f01(next_dev(s1));
-    }
-    bool sp = false;
-    const float om = 1.0f - u0;
-    float lg = vkpm::log_core(om, tab, sp);
-    if (sp) lg = vkpm::log_f(om);
-    const float rad = __fsqrt_rn(-2.0f * lg) * stddev;
-    float sn, cs;
-    vkpm::sincos_small(6.28318530718f * u1, sn, cs);
-    const float o0 = mean + rad * sn, o1 = mean + rad * cs;
-    if (live) {
-      if (j + 1 < n_out) *reinterpret_cast<float2*>(out + j) = make_float2(o0, o1);
-      else if (j < n_out) out[j] = o0;
-    }
-  };
-
+  // 1 - u = 2 - f for f = 1.bits in [1, 2): both exact, so one subtract replaces two
+#define VKP_BM_PAIR(o0, o1)                                                                          \
+  {                                                                                                  \
+    const float om = 2.0f - __uint_as_float((next_dev(s0) >> 9) | 0x3f800000u);                      \
+    const float u1 = u2f01(next_dev(s1));                                                            \
+    vkpm::box_muller_core(om, u1, mean, stddev, o0, o1);                                             \
+  }
   const uint64_t e1 = seg_end < full ? seg_end : full;
-  const uint32_t mine = (valid && e1 > start) ? (uint32_t)(e1 - start) : 0u;
-  const uint32_t trips = __reduce_max_sync(0xffffffffu, mine);
-  for (uint32_t it = 0; it < trips; it++) emit(it < mine, (start + it) * size + l0);
-
-  const bool tail = valid && rem != 0 && full >= start && full < seg_end && l0 < rem;
-  if (__any_sync(0xffffffffu, tail)) emit(tail, full * size + l0);
-
-  if (valid) {
-    const uint64_t cnt = full + ((l0 < rem) ? 1 : 0);
-    if (cnt > start && cnt <= seg_end) {
-      state_out[l0] = s0;
-      state_out[l0 + 1] = s1;
+  uint64_t iters = e1 > start ? e1 - start : 0;
+  float* o = out + start * size + l0;
+  // for an odd request the very last pair stores one value only; it is some thread's final emit
+  const bool half_last = (n_out & 1) && rem == 0 && iters > 0 && e1 == full && l0 == size - 2;
+  if (half_last) iters--;
+  while (iters > 0) {
+    const uint32_t batch = iters > 0x40000000ull ? 0x40000000u : (uint32_t)iters;
+    for (uint32_t i = 0; i < batch; i++) {
+      float o0, o1;
+      VKP_BM_PAIR(o0, o1);
+      *reinterpret_cast<float2*>(o) = make_float2(o0, o1);
+      o += size;
     }
+    iters -= batch;
+  }
+  if (half_last) {
+    float o0, o1;
+    VKP_BM_PAIR(o0, o1);
+    o[0] = o0;
+  }
+  if (rem != 0 && full >= start && full < seg_end && l0 < rem) {   // tail chunk
+    const uint64_t j = full * size + l0;
+    float o0, o1;
+    VKP_BM_PAIR(o0, o1);
+    if (j + 1 < n_out) *reinterpret_cast<float2*>(out + j) = make_float2(o0, o1);
+    else out[j] = o0;
+  }
+#undef VKP_BM_PAIR
+  const uint64_t cnt = full + ((l0 < rem) ? 1 : 0);
+  if (cnt > start && cnt <= seg_end) {
+    state_out[l0] = s0;
+    state_out[l0 + 1] = s1;
   }
 }
 
@@ -403,8 +404,8 @@ static int rng_generate(vkp_rng* rng, void* out, uint64_t n_out, float mean, flo
   xoshiro_stream_kernel<LPT, (MODE == MODE_NORMAL ? MODE_F32 : MODE)><<<grid, 128, 0, ctx->stream>>>(     \
       sin_, sout, (uint32_t*)out, rng->jump, size, n_draw, log2L, nseg)
     if (MODE == MODE_NORMAL) {
-      xoshiro_normal_kernel<<<grid, 128, 0, ctx->stream>>>(vkpt::host_coef(), sin_, sout, (float*)out, rng->jump,
-                                                           size, n_draw, n_out, log2L, nseg, mean, stddev);
+      xoshiro_normal_kernel<<<grid, 128, 0, ctx->stream>>>(sin_, sout, (float*)out, rng->jump, size, n_draw, n_out,
+                                                           log2L, nseg, mean, stddev);
     }
     else if (lpt == 4) { LAUNCH(4); }
     else if (lpt == 2) { LAUNCH(2); }

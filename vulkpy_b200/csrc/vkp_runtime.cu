@@ -77,6 +77,8 @@ extern "C" int vkp_ctx_create(int device, float priority, vkp_ctx** out) {
 static int sync_locked(vkp_ctx* ctx) {
   uint64_t s = ctx->seq;
   VKP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->h2d_stream) VKP_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
+  if (ctx->d2h_stream) VKP_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
   if (s > ctx->done_seq) ctx->done_seq = s;
   return VKP_OK;
 }
@@ -92,6 +94,8 @@ static int trim_locked(vkp_ctx* ctx) {
   VKP_TRY(sync_locked(ctx));
   for (auto& kv : ctx->free_lists) {
     for (vkp_block* b : kv.second) {
+      if (b->h2d_ev) ctx->event_pool.push_back(b->h2d_ev);   // all streams are idle after the sync
+      if (b->d2h_ev) ctx->event_pool.push_back(b->d2h_ev);
       ctx->blocks.erase(b->ptr);
       cudaFree(b->ptr);
       ctx->pooled_bytes -= b->bytes;
@@ -164,15 +168,23 @@ static size_t size_class(size_t bytes) {
   return (bytes + two_mib - 1) / two_mib * two_mib;
 }
 
-extern "C" int vkp_alloc(vkp_ctx* ctx, size_t bytes, void** ptr) {
+// quiet != 0: prefer a cached block that no enqueued compute work can still touch, so that a
+// copy-engine upload into it has nothing to wait for (the default is LIFO: hottest block first)
+static int alloc_impl(vkp_ctx* ctx, size_t bytes, void** ptr, int quiet) {
   VKP_CHECK(ctx && ptr, "vkp_alloc: null argument");
   VKP_TRY(vkp_make_current(ctx));
   std::lock_guard<std::mutex> g(ctx->mu);
   const size_t cls = size_class(bytes);
   auto it = ctx->free_lists.find(cls);
   if (it != ctx->free_lists.end() && !it->second.empty()) {
-    vkp_block* b = it->second.back();
-    it->second.pop_back();
+    std::vector<vkp_block*>& fl = it->second;
+    size_t pick = fl.size() - 1;
+    if (quiet) {
+      for (size_t i = 0; i < fl.size(); i++)
+        if (fl[i]->guard_seq <= ctx->done_seq && !fl[i]->d2h_ev) { pick = i; break; }
+    }
+    vkp_block* b = fl[pick];
+    fl.erase(fl.begin() + pick);
     b->in_use = true;
     ctx->live_bytes += b->bytes;
     *ptr = b->ptr;
@@ -201,6 +213,9 @@ extern "C" int vkp_alloc(vkp_ctx* ctx, size_t bytes, void** ptr) {
   return VKP_OK;
 }
 
+extern "C" int vkp_alloc(vkp_ctx* ctx, size_t bytes, void** ptr) { return alloc_impl(ctx, bytes, ptr, 0); }
+extern "C" int vkp_alloc_for_upload(vkp_ctx* ctx, size_t bytes, void** ptr) { return alloc_impl(ctx, bytes, ptr, 1); }
+
 extern "C" int vkp_free(vkp_ctx* ctx, void* ptr) {
   if (!ptr) return VKP_OK;
   VKP_CHECK(ctx, "vkp_free: null context");
@@ -209,7 +224,9 @@ extern "C" int vkp_free(vkp_ctx* ctx, void* ptr) {
   VKP_CHECK(it != ctx->blocks.end() && it->second->in_use, "vkp_free: %p is not a live buffer", ptr);
   vkp_block* b = it->second;
   b->in_use = false;
-  b->guard_seq = ctx->seq;  // kernels enqueued so far may still read or write it
+  // the last operation bound to the block may still read or write it (every entry point passes its
+  // buffers through vkp_prepare_buffers, and buffers are always bound by their base pointer)
+  b->guard_seq = b->last_seq;
   ctx->live_bytes -= b->bytes;
   ctx->free_lists[b->bytes].push_back(b);
   return VKP_OK;
@@ -225,6 +242,18 @@ int vkp_prepare_buffers(vkp_ctx* ctx, void* const* bufs, int nbuf) {
       VKP_CUDA(cudaMemPrefetchAsync(b->ptr, b->bytes, ctx->device, ctx->stream));
       b->host_dirty = false;
     }
+    // copy-engine transfers on the side streams: this and every later compute operation run after them
+    if (b->h2d_ev) {
+      VKP_CUDA(cudaStreamWaitEvent(ctx->stream, b->h2d_ev, 0));
+      ctx->event_pool.push_back(b->h2d_ev);
+      b->h2d_ev = nullptr;
+    }
+    if (b->d2h_ev) {
+      VKP_CUDA(cudaStreamWaitEvent(ctx->stream, b->d2h_ev, 0));
+      ctx->event_pool.push_back(b->d2h_ev);
+      b->d2h_ev = nullptr;
+    }
+    b->last_seq = ctx->seq + 1;
   }
   return VKP_OK;
 }
@@ -245,7 +274,7 @@ int vkp_finish_op(vkp_ctx* ctx, vkp_job** job) {
     cudaEvent_t ev;
     VKP_TRY(take_event(ctx, &ev));
     VKP_CUDA(cudaEventRecord(ev, ctx->stream));
-    vkp_job* j = new vkp_job{ctx, ev, ctx->seq};
+    vkp_job* j = new vkp_job{ctx, ev, ctx->seq, VKP_JOB_COMPUTE};
     *job = j;
   }
   return VKP_OK;
@@ -279,6 +308,52 @@ int vkp_workspace(vkp_ctx* ctx, int slot, size_t bytes, void** out) {
 }
 
 // ---- host <-> buffer ------------------------------------------------------------------
+static const size_t STAGE_BYTES = 128u << 20;   // one chunk = ~2.4 ms of PCIe 5 x16
+
+static __global__ void __launch_bounds__(256)
+stage_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16, size_t nwords) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+  for (size_t i = n16 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nwords; i += stride) d[i] = s[i];
+}
+
+static bool is_page_locked(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) return attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  return false;
+}
+
+static int stage_launch(vkp_ctx* ctx, cudaStream_t st, void* dst, const void* src, size_t bytes) {
+  const size_t nwords = bytes / 4, n16 = bytes / 16;
+  const unsigned grid = vkp_grid_for(ctx, n16 ? n16 : 1, 256 * 4, 4);
+  stage_copy_kernel<<<grid, 256, 0, st>>>((uint4*)dst, (const uint4*)src, n16, nwords);
+  return vkp_after_launch(ctx, "stage_copy");
+}
+
+// page-locked host memory <-> buffer through the bounce buffer of stream slot `slot`, chunk by chunk
+// (everything is in order on `st`, so one bounce buffer per stream is enough)
+static int staged_copy(vkp_ctx* ctx, cudaStream_t st, int slot, void* dst, const void* src, size_t bytes, bool h2d) {
+  VKP_CHECK(bytes % 4 == 0, "staged copy: %zu bytes is not a whole number of elements", bytes);
+  if (!ctx->stage[slot]) VKP_CUDA(cudaMalloc(&ctx->stage[slot], STAGE_BYTES));
+  char* bounce = (char*)ctx->stage[slot];
+  for (size_t off = 0; off < bytes; off += STAGE_BYTES) {
+    const size_t n = bytes - off < STAGE_BYTES ? bytes - off : STAGE_BYTES;
+    if (h2d) {
+      VKP_CUDA(cudaMemcpyAsync(bounce, (const char*)src + off, n, cudaMemcpyHostToDevice, st));
+      VKP_TRY(stage_launch(ctx, st, (char*)dst + off, bounce, n));
+    } else {
+      VKP_TRY(stage_launch(ctx, st, bounce, (const char*)src + off, n));
+      VKP_CUDA(cudaMemcpyAsync((char*)dst + off, bounce, n, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  return VKP_OK;
+}
+
+static const size_t STAGE_MIN_BYTES = 4u << 20;   // below this a direct copy is as fast
+
 extern "C" int vkp_upload(vkp_ctx* ctx, void* dst, const void* src_host, size_t bytes) {
   VKP_CHECK(ctx && (bytes == 0 || (dst && src_host)), "vkp_upload: null argument");
   if (bytes == 0) return VKP_OK;
@@ -287,7 +362,11 @@ extern "C" int vkp_upload(vkp_ctx* ctx, void* dst, const void* src_host, size_t 
   void* bufs[1] = {dst};
   VKP_TRY(vkp_prepare_buffers(ctx, bufs, 1));
   // stream-ordered: earlier kernels that still use a recycled block finish first
-  VKP_CUDA(cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyDefault, ctx->stream));
+  const bool locked = is_page_locked(src_host);
+  if (locked && bytes >= STAGE_MIN_BYTES && bytes % 4 == 0)
+    VKP_TRY(staged_copy(ctx, ctx->stream, 2, dst, src_host, bytes, true));
+  else
+    VKP_CUDA(cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyDefault, ctx->stream));
   ctx->seq++;
   // Contract: the source may be reused as soon as this returns (the reference's Buffer::set is a
   // plain memcpy).  Pageable sources are already staged by the runtime; page-locked ones are
@@ -304,9 +383,91 @@ extern "C" int vkp_download(vkp_ctx* ctx, void* dst_host, const void* src, size_
   if (bytes == 0) return VKP_OK;
   VKP_TRY(vkp_make_current(ctx));
   std::lock_guard<std::mutex> g(ctx->mu);
-  VKP_CUDA(cudaMemcpyAsync(dst_host, src, bytes, cudaMemcpyDefault, ctx->stream));
+  void* bufs[1] = {const_cast<void*>(src)};
+  VKP_TRY(vkp_prepare_buffers(ctx, bufs, 1));
+  if (bytes >= STAGE_MIN_BYTES && bytes % 4 == 0 && is_page_locked(dst_host))
+    VKP_TRY(staged_copy(ctx, ctx->stream, 2, dst_host, src, bytes, false));
+  else
+    VKP_CUDA(cudaMemcpyAsync(dst_host, src, bytes, cudaMemcpyDefault, ctx->stream));
   ctx->seq++;
   return sync_locked(ctx);
+}
+
+// ---- copy-engine transfers that overlap compute (and each other) ---------------------------
+static int ensure_copy_streams(vkp_ctx* ctx) {
+  if (!ctx->h2d_stream) VKP_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+  if (!ctx->d2h_stream) VKP_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+  return VKP_OK;
+}
+
+// `side` runs after everything enqueued on the compute stream so far
+static int order_after_compute(vkp_ctx* ctx, cudaStream_t side) {
+  cudaEvent_t ev;
+  VKP_TRY(take_event(ctx, &ev));
+  VKP_CUDA(cudaEventRecord(ev, ctx->stream));
+  VKP_CUDA(cudaStreamWaitEvent(side, ev, 0));
+  ctx->event_pool.push_back(ev);   // the wait has captured this recording; re-recording later is legal
+  return VKP_OK;
+}
+
+extern "C" int vkp_upload_async(vkp_ctx* ctx, void* dst, const void* src_pinned, size_t bytes, vkp_job** job) {
+  VKP_CHECK(ctx && dst && src_pinned && job, "vkp_upload_async: null argument");
+  VKP_TRY(vkp_make_current(ctx));
+  VKP_CHECK(is_page_locked(src_pinned), "vkp_upload_async: the source must be page-locked (vkp_host_alloc)");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  auto it = ctx->blocks.find(dst);
+  VKP_CHECK(it != ctx->blocks.end() && it->second->in_use, "vkp_upload_async: %p is not a live buffer", dst);
+  vkp_block* b = it->second;
+  VKP_CHECK(bytes <= b->bytes && bytes % 4 == 0, "vkp_upload_async: %zu bytes do not fit the buffer", bytes);
+  VKP_TRY(ensure_copy_streams(ctx));
+  const uint64_t busy = b->guard_seq > b->last_seq ? b->guard_seq : b->last_seq;
+  if (busy > ctx->done_seq) VKP_TRY(order_after_compute(ctx, ctx->h2d_stream));
+  if (b->d2h_ev) {   // a download still reads the block
+    VKP_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, b->d2h_ev, 0));
+    ctx->event_pool.push_back(b->d2h_ev);
+    b->d2h_ev = nullptr;
+  }
+  if (b->host_dirty) {
+    VKP_CUDA(cudaMemPrefetchAsync(b->ptr, b->bytes, ctx->device, ctx->h2d_stream));
+    b->host_dirty = false;
+  }
+  if (bytes >= STAGE_MIN_BYTES)
+    VKP_TRY(staged_copy(ctx, ctx->h2d_stream, 0, dst, src_pinned, bytes, true));
+  else if (bytes)
+    VKP_CUDA(cudaMemcpyAsync(dst, src_pinned, bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
+  if (!b->h2d_ev) VKP_TRY(take_event(ctx, &b->h2d_ev));
+  VKP_CUDA(cudaEventRecord(b->h2d_ev, ctx->h2d_stream));
+  b->guard_seq = 0;
+  cudaEvent_t jev;
+  VKP_TRY(take_event(ctx, &jev));
+  VKP_CUDA(cudaEventRecord(jev, ctx->h2d_stream));
+  *job = new vkp_job{ctx, jev, 0, VKP_JOB_UPLOAD};
+  return VKP_OK;
+}
+
+extern "C" int vkp_download_async(vkp_ctx* ctx, void* dst_pinned, const void* src, size_t bytes, vkp_job** job) {
+  VKP_CHECK(ctx && dst_pinned && src && job, "vkp_download_async: null argument");
+  VKP_TRY(vkp_make_current(ctx));
+  VKP_CHECK(is_page_locked(dst_pinned), "vkp_download_async: the destination must be page-locked (vkp_host_alloc)");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  auto it = ctx->blocks.find(const_cast<void*>(src));
+  VKP_CHECK(it != ctx->blocks.end() && it->second->in_use, "vkp_download_async: %p is not a live buffer", src);
+  vkp_block* b = it->second;
+  VKP_CHECK(bytes <= b->bytes && bytes % 4 == 0, "vkp_download_async: %zu bytes exceed the buffer", bytes);
+  VKP_TRY(ensure_copy_streams(ctx));
+  VKP_TRY(order_after_compute(ctx, ctx->d2h_stream));
+  if (b->h2d_ev) VKP_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, b->h2d_ev, 0));   // stays pending for compute
+  if (bytes >= STAGE_MIN_BYTES)
+    VKP_TRY(staged_copy(ctx, ctx->d2h_stream, 1, dst_pinned, src, bytes, false));
+  else if (bytes)
+    VKP_CUDA(cudaMemcpyAsync(dst_pinned, src, bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  if (!b->d2h_ev) VKP_TRY(take_event(ctx, &b->d2h_ev));
+  VKP_CUDA(cudaEventRecord(b->d2h_ev, ctx->d2h_stream));
+  cudaEvent_t jev;
+  VKP_TRY(take_event(ctx, &jev));
+  VKP_CUDA(cudaEventRecord(jev, ctx->d2h_stream));
+  *job = new vkp_job{ctx, jev, ctx->seq, VKP_JOB_DOWNLOAD};
+  return VKP_OK;
 }
 
 extern "C" int vkp_host_acquire(vkp_ctx* ctx, void* ptr, size_t bytes, int mode) {
@@ -317,6 +478,16 @@ extern "C" int vkp_host_acquire(vkp_ctx* ctx, void* ptr, size_t bytes, int mode)
   VKP_CHECK(it != ctx->blocks.end(), "vkp_host_acquire: %p is not a buffer of this context", ptr);
   vkp_block* b = it->second;
   const bool prefetch = (mode & 1) != 0, writing = (mode & 2) != 0;
+  if (b->h2d_ev) {   // copy-engine upload in flight: the host view must see it
+    VKP_CUDA(cudaEventSynchronize(b->h2d_ev));
+    ctx->event_pool.push_back(b->h2d_ev);
+    b->h2d_ev = nullptr;
+  }
+  if (b->d2h_ev && (writing || prefetch)) {
+    VKP_CUDA(cudaEventSynchronize(b->d2h_ev));
+    ctx->event_pool.push_back(b->d2h_ev);
+    b->d2h_ev = nullptr;
+  }
   bool need_sync = b->guard_seq > ctx->done_seq;       // earlier tenant of a recycled block
   if (writing && ctx->seq > ctx->done_seq) need_sync = true;  // readers of this array in flight
   if (prefetch && !b->host_dirty && bytes > 0) {
@@ -346,7 +517,7 @@ extern "C" int vkp_host_free(void* ptr) {
 extern "C" int vkp_job_wait(vkp_job* job, uint64_t timeout_ns) {
   VKP_CHECK(job, "vkp_job_wait: null job");
   vkp_ctx* ctx = job->ctx;
-  if (ctx->done_seq >= job->seq) return VKP_OK;
+  if (job->kind == VKP_JOB_COMPUTE && ctx->done_seq >= job->seq) return VKP_OK;
   VKP_TRY(vkp_make_current(ctx));
   if (timeout_ns == UINT64_MAX) {
     cudaError_t e = cudaEventSynchronize(job->ev);
@@ -376,7 +547,7 @@ extern "C" int vkp_job_wait(vkp_job* job, uint64_t timeout_ns) {
 
 extern "C" int vkp_job_done(vkp_job* job, int* done) {
   VKP_CHECK(job && done, "vkp_job_done: null argument");
-  if (job->ctx->done_seq >= job->seq) { *done = 1; return VKP_OK; }
+  if (job->kind == VKP_JOB_COMPUTE && job->ctx->done_seq >= job->seq) { *done = 1; return VKP_OK; }
   cudaError_t e = cudaEventQuery(job->ev);
   if (e == cudaSuccess) { *done = 1; return VKP_OK; }
   if (e == cudaErrorNotReady) { *done = 0; return VKP_OK; }

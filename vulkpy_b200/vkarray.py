@@ -195,17 +195,44 @@ class _GPUArray(Resource):
             return v.astype(dtype)
         return v.copy() if copy else v
 
-    def to_host(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+    def to_host(self, out: Optional[np.ndarray] = None, wait: bool = True) -> np.ndarray:
         """Copy the contents into host memory with one stream-ordered device-to-host transfer
         (additive helper: unlike ``np.asarray(array)`` no managed page migrates, so the array
-        stays resident in HBM; pass a ``pinned_empty`` buffer as ``out`` for full PCIe rate)."""
+        stays resident in HBM; pass a ``pinned_empty`` buffer as ``out`` for full PCIe rate).
+
+        ``wait=False`` (``out`` must be a ``pinned_empty`` array) runs the transfer on the
+        device-to-host copy engine and returns at once; ``self.wait()`` completes it.  Uploads
+        of the next step (``from_host``) and kernels overlap it."""
         if out is None:
+            assert wait, "an asynchronous download needs a pinned `out`"
             out = np.empty(self.shape, dtype=self._np_dtype)
         assert out.nbytes == self.buffer.nbytes and out.flags.c_contiguous
+        if not wait:
+            self.job = self.buffer.download_async(out.reshape(-1))
+            self._keep = [out]
+            return out
         _b._check(_b.lib.vkp_download(self._gpu.gpu._ctx, out.ctypes.data, self.buffer.ptr, out.nbytes))
         self.job = None
         self._keep = []
         return out
+
+    @classmethod
+    def from_host(cls, gpu: "GPU", pinned: np.ndarray):
+        """Array filled from a ``pinned_empty`` host array by the host-to-device copy engine.
+
+        Additive helper for pipelined steps: returns at once, the transfer overlaps kernels and
+        downloads already enqueued, operations on the result are ordered after it.  Unlike
+        ``Array(gpu, data=...)`` the source is read asynchronously: do not rewrite ``pinned``
+        before ``wait()`` on the result (or on anything computed from it) has returned."""
+        self = cls.__new__(cls)
+        _GPUArray.__init__(self, gpu)
+        host = np.asarray(pinned)
+        assert host.dtype == cls._np_dtype and host.flags.c_contiguous
+        self.shape = host.shape
+        self.buffer = (_b.Shape if cls._np_dtype == np.uint32 else _b.Buffer)(gpu.gpu, host.size, for_upload=True)
+        self.job = self.buffer.upload_async(host.reshape(-1))
+        self._keep = [host]
+        return self
 
     def _set_shape(self, shape):
         shape = tuple(int(s) for s in (shape if np.ndim(shape) else (shape,)))
