@@ -381,7 +381,7 @@ def main():
             "config": {"workload": f"C2: {len(OPS)} elementwise/broadcast/transcendental ops on "
                                    f"{rows}x{cols} float32 per GPU ({BYTES_PER_ELEM} algorithmic B/elem)",
                        "ops": [o for o, _ in OPS], "l2": "inputs (1 GiB each) are larger than the 126 MB L2",
-                       "memory": "cudaMallocManaged pool, resident in HBM"},
+                       "memory": "cudaMalloc pool (buffers move to managed memory only when the host views them)"},
             "frac_of_peak": round(value / world / peak, 4),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "matmul_8192": matmul,

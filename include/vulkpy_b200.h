@@ -75,7 +75,13 @@ VKP_API int vkp_download(vkp_ctx* ctx, void* dst_host, const void* src, size_t b
 VKP_API int vkp_alloc_for_upload(vkp_ctx* ctx, size_t bytes, void** ptr);
 VKP_API int vkp_upload_async(vkp_ctx* ctx, void* dst, const void* src_pinned, size_t bytes, vkp_job** job);
 VKP_API int vkp_download_async(vkp_ctx* ctx, void* dst_pinned, const void* src, size_t bytes, vkp_job** job);
-/* Call before the host touches `ptr` through its NumPy view.  Makes sure no earlier
+/* Buffers are born in plain device memory (cudaMalloc).  The reference maps every buffer
+ * host-visible and NumPy views it zero-copy (_vkarray.cc:61-72, :797-833); here the first request
+ * for such a view moves the contents into a managed block whose pointer is valid on host and
+ * device: `*host_visible` replaces `ptr` for every later call (the old pointer is released).
+ * A buffer that is already host-visible returns itself. */
+VKP_API int vkp_host_view(vkp_ctx* ctx, void* ptr, void** host_visible);
+/* Call before the host touches a host-visible `ptr` through its NumPy view.  Makes sure no earlier
  * user of a recycled block is still in flight and (prefetch!=0) migrates the pages to
  * host memory in one bulk transfer instead of page faults. */
 VKP_API int vkp_host_acquire(vkp_ctx* ctx, void* ptr, size_t bytes, int prefetch);

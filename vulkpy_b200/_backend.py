@@ -51,6 +51,7 @@ PROTOTYPES = {
     "vkp_alloc_for_upload": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
     "vkp_upload_async": (C.c_int, [_vp, _vp, _vp, _sz, C.POINTER(_vp)]),
     "vkp_download_async": (C.c_int, [_vp, _vp, _vp, _sz, C.POINTER(_vp)]),
+    "vkp_host_view": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "vkp_upload": (C.c_int, [_vp, _vp, _vp, _sz]),
     "vkp_download": (C.c_int, [_vp, _vp, _vp, _sz]),
     "vkp_host_acquire": (C.c_int, [_vp, _vp, _sz, C.c_int]),
@@ -207,11 +208,20 @@ class _BufferBase:
     def nbytes(self) -> int:
         return self._n * 4
 
+    def host_view(self):
+        """Make the buffer host-visible (first call moves it from device memory into a managed
+        block; ``ptr`` changes once and then stays put for the life of the buffer)."""
+        p = _vp()
+        _check(lib.vkp_host_view(self._dev._ctx, self.ptr, C.byref(p)))
+        self.ptr = p.value
+
     @property
     def __array_interface__(self):
+        self.host_view()
         return {"shape": (self._n,), "typestr": self._dtype.str, "data": (self.ptr, False), "version": 3}
 
     def host_acquire(self, prefetch: bool = False, write: bool = False):
+        self.host_view()
         _check(lib.vkp_host_acquire(self._dev._ctx, self.ptr, self._n * 4,
                                     (1 if prefetch else 0) | (2 if write else 0)))
 

@@ -42,7 +42,10 @@ struct vkp_block {
   void* ptr = nullptr;
   size_t bytes = 0;         // rounded size class
   uint64_t guard_seq = 0;   // work submitted up to this sequence number may still touch the block
-  bool host_dirty = false;  // pages may live in host memory -> prefetch before the next kernel
+  // Plain device memory (cudaMalloc) until the host asks for a view of the buffer; then the
+  // contents move into a managed block, whose pointer is valid on host and device (vkp_host_view).
+  bool managed = false;
+  bool host_dirty = false;  // managed pages may live in host memory -> prefetch before the next kernel
   bool in_use = false;
   uint64_t last_seq = 0;    // sequence number of the last compute-stream operation bound to the block
   // copy-engine transfers in flight on the side streams (vkp_upload_async / vkp_download_async):
@@ -71,7 +74,7 @@ struct vkp_ctx {
   bool debug_sync = false;
   int refcount = 1;
   std::unordered_map<void*, vkp_block*> blocks;
-  std::unordered_map<size_t, std::vector<vkp_block*>> free_lists;
+  std::unordered_map<size_t, std::vector<vkp_block*>> free_lists[2];   // [0] device, [1] managed
   size_t pooled_bytes = 0, live_bytes = 0;
   std::vector<cudaEvent_t> event_pool;
   // device scratch: slot 0 = partials of two-pass reductions, slot 1 = reduced values awaiting

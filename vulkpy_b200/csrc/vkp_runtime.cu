@@ -92,7 +92,8 @@ extern "C" int vkp_ctx_sync(vkp_ctx* ctx) {
 
 static int trim_locked(vkp_ctx* ctx) {
   VKP_TRY(sync_locked(ctx));
-  for (auto& kv : ctx->free_lists) {
+  for (int k = 0; k < 2; k++)
+  for (auto& kv : ctx->free_lists[k]) {
     for (vkp_block* b : kv.second) {
       if (b->h2d_ev) ctx->event_pool.push_back(b->h2d_ev);   // all streams are idle after the sync
       if (b->d2h_ev) ctx->event_pool.push_back(b->d2h_ev);
@@ -169,14 +170,13 @@ static size_t size_class(size_t bytes) {
 }
 
 // quiet != 0: prefer a cached block that no enqueued compute work can still touch, so that a
-// copy-engine upload into it has nothing to wait for (the default is LIFO: hottest block first)
-static int alloc_impl(vkp_ctx* ctx, size_t bytes, void** ptr, int quiet) {
-  VKP_CHECK(ctx && ptr, "vkp_alloc: null argument");
-  VKP_TRY(vkp_make_current(ctx));
-  std::lock_guard<std::mutex> g(ctx->mu);
+// copy-engine upload into it has nothing to wait for (the default is LIFO: hottest block first).
+// managed != 0: host-visible block (cudaMallocManaged, prefetched into HBM); otherwise cudaMalloc.
+static int alloc_locked(vkp_ctx* ctx, size_t bytes, void** ptr, int quiet, int managed) {
   const size_t cls = size_class(bytes);
-  auto it = ctx->free_lists.find(cls);
-  if (it != ctx->free_lists.end() && !it->second.empty()) {
+  auto& lists = ctx->free_lists[managed ? 1 : 0];
+  auto it = lists.find(cls);
+  if (it != lists.end() && !it->second.empty()) {
     std::vector<vkp_block*>& fl = it->second;
     size_t pick = fl.size() - 1;
     if (quiet) {
@@ -191,26 +191,38 @@ static int alloc_impl(vkp_ctx* ctx, size_t bytes, void** ptr, int quiet) {
     return VKP_OK;
   }
   void* p = nullptr;
-  cudaError_t e = cudaMallocManaged(&p, cls, cudaMemAttachGlobal);
+  auto raw_alloc = [&]() { return managed ? cudaMallocManaged(&p, cls, cudaMemAttachGlobal) : cudaMalloc(&p, cls); };
+  cudaError_t e = raw_alloc();
   if (e != cudaSuccess) {
     cudaGetLastError();
     // release cached blocks and retry once
     VKP_TRY(trim_locked(ctx));
-    e = cudaMallocManaged(&p, cls, cudaMemAttachGlobal);
-    if (e != cudaSuccess)
-      return vkp_set_error("cudaMallocManaged(%zu bytes) failed: %s", cls, cudaGetErrorString(e));
+    e = raw_alloc();
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return vkp_set_error("%s(%zu bytes) failed: %s", managed ? "cudaMallocManaged" : "cudaMalloc", cls,
+                           cudaGetErrorString(e));
+    }
   }
-  // populate the pages in HBM now; kernels then run at full rate without GPU page faults
-  VKP_CUDA(cudaMemPrefetchAsync(p, cls, ctx->device, ctx->stream));
+  // populate managed pages in HBM now; kernels then run at full rate without GPU page faults
+  if (managed) VKP_CUDA(cudaMemPrefetchAsync(p, cls, ctx->device, ctx->stream));
   vkp_block* b = new vkp_block();
   b->ptr = p;
   b->bytes = cls;
+  b->managed = managed != 0;
   b->in_use = true;
   ctx->blocks[p] = b;
   ctx->pooled_bytes += cls;
   ctx->live_bytes += cls;
   *ptr = p;
   return VKP_OK;
+}
+
+static int alloc_impl(vkp_ctx* ctx, size_t bytes, void** ptr, int quiet) {
+  VKP_CHECK(ctx && ptr, "vkp_alloc: null argument");
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  return alloc_locked(ctx, bytes, ptr, quiet, 0);
 }
 
 extern "C" int vkp_alloc(vkp_ctx* ctx, size_t bytes, void** ptr) { return alloc_impl(ctx, bytes, ptr, 0); }
@@ -228,7 +240,7 @@ extern "C" int vkp_free(vkp_ctx* ctx, void* ptr) {
   // buffers through vkp_prepare_buffers, and buffers are always bound by their base pointer)
   b->guard_seq = b->last_seq;
   ctx->live_bytes -= b->bytes;
-  ctx->free_lists[b->bytes].push_back(b);
+  ctx->free_lists[b->managed ? 1 : 0][b->bytes].push_back(b);
   return VKP_OK;
 }
 
@@ -238,7 +250,7 @@ int vkp_prepare_buffers(vkp_ctx* ctx, void* const* bufs, int nbuf) {
     auto it = ctx->blocks.find(bufs[i]);
     if (it == ctx->blocks.end()) continue;
     vkp_block* b = it->second;
-    if (b->host_dirty) {
+    if (b->host_dirty) {   // only managed blocks are ever host-dirty
       VKP_CUDA(cudaMemPrefetchAsync(b->ptr, b->bytes, ctx->device, ctx->stream));
       b->host_dirty = false;
     }
@@ -354,6 +366,13 @@ static int staged_copy(vkp_ctx* ctx, cudaStream_t st, int slot, void* dst, const
 
 static const size_t STAGE_MIN_BYTES = 4u << 20;   // below this a direct copy is as fast
 
+// page-locked transfers bounce only when the device side is a managed block
+static bool wants_bounce(vkp_ctx* ctx, const void* dev_ptr, size_t bytes) {
+  if (bytes < STAGE_MIN_BYTES || bytes % 4 != 0) return false;
+  auto it = ctx->blocks.find(const_cast<void*>(dev_ptr));
+  return it != ctx->blocks.end() && it->second->managed;
+}
+
 extern "C" int vkp_upload(vkp_ctx* ctx, void* dst, const void* src_host, size_t bytes) {
   VKP_CHECK(ctx && (bytes == 0 || (dst && src_host)), "vkp_upload: null argument");
   if (bytes == 0) return VKP_OK;
@@ -363,7 +382,7 @@ extern "C" int vkp_upload(vkp_ctx* ctx, void* dst, const void* src_host, size_t 
   VKP_TRY(vkp_prepare_buffers(ctx, bufs, 1));
   // stream-ordered: earlier kernels that still use a recycled block finish first
   const bool locked = is_page_locked(src_host);
-  if (locked && bytes >= STAGE_MIN_BYTES && bytes % 4 == 0)
+  if (locked && wants_bounce(ctx, dst, bytes))
     VKP_TRY(staged_copy(ctx, ctx->stream, 2, dst, src_host, bytes, true));
   else
     VKP_CUDA(cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyDefault, ctx->stream));
@@ -385,7 +404,7 @@ extern "C" int vkp_download(vkp_ctx* ctx, void* dst_host, const void* src, size_
   std::lock_guard<std::mutex> g(ctx->mu);
   void* bufs[1] = {const_cast<void*>(src)};
   VKP_TRY(vkp_prepare_buffers(ctx, bufs, 1));
-  if (bytes >= STAGE_MIN_BYTES && bytes % 4 == 0 && is_page_locked(dst_host))
+  if (wants_bounce(ctx, src, bytes) && is_page_locked(dst_host))
     VKP_TRY(staged_copy(ctx, ctx->stream, 2, dst_host, src, bytes, false));
   else
     VKP_CUDA(cudaMemcpyAsync(dst_host, src, bytes, cudaMemcpyDefault, ctx->stream));
@@ -431,7 +450,7 @@ extern "C" int vkp_upload_async(vkp_ctx* ctx, void* dst, const void* src_pinned,
     VKP_CUDA(cudaMemPrefetchAsync(b->ptr, b->bytes, ctx->device, ctx->h2d_stream));
     b->host_dirty = false;
   }
-  if (bytes >= STAGE_MIN_BYTES)
+  if (wants_bounce(ctx, dst, bytes))
     VKP_TRY(staged_copy(ctx, ctx->h2d_stream, 0, dst, src_pinned, bytes, true));
   else if (bytes)
     VKP_CUDA(cudaMemcpyAsync(dst, src_pinned, bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
@@ -457,7 +476,7 @@ extern "C" int vkp_download_async(vkp_ctx* ctx, void* dst_pinned, const void* sr
   VKP_TRY(ensure_copy_streams(ctx));
   VKP_TRY(order_after_compute(ctx, ctx->d2h_stream));
   if (b->h2d_ev) VKP_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, b->h2d_ev, 0));   // stays pending for compute
-  if (bytes >= STAGE_MIN_BYTES)
+  if (wants_bounce(ctx, src, bytes))
     VKP_TRY(staged_copy(ctx, ctx->d2h_stream, 1, dst_pinned, src, bytes, false));
   else if (bytes)
     VKP_CUDA(cudaMemcpyAsync(dst_pinned, src, bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
@@ -470,6 +489,41 @@ extern "C" int vkp_download_async(vkp_ctx* ctx, void* dst_pinned, const void* sr
   return VKP_OK;
 }
 
+// Buffers are born in plain device memory.  The first time the host wants to look at one through
+// its pointer (NumPy view), the contents move into a managed block and the buffer lives there from
+// then on: `*out` replaces `ptr`, which is released.  Keeps managed memory -- a scarce, system-wide
+// resource on multi-GPU boxes (scripts/micro/managed_limit.py: ~64 GiB over all processes) -- for the
+// few arrays the host actually views, and lets everything else DMA and run from cudaMalloc memory.
+extern "C" int vkp_host_view(vkp_ctx* ctx, void* ptr, void** out) {
+  VKP_CHECK(ctx && ptr && out, "vkp_host_view: null argument");
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  auto it = ctx->blocks.find(ptr);
+  VKP_CHECK(it != ctx->blocks.end() && it->second->in_use, "vkp_host_view: %p is not a live buffer", ptr);
+  vkp_block* b = it->second;
+  if (b->managed) {
+    *out = ptr;
+    return VKP_OK;
+  }
+  void* np = nullptr;
+  int rc = alloc_locked(ctx, b->bytes, &np, 0, 1);
+  if (rc != VKP_OK)
+    return vkp_set_error("host view of a %zu-byte buffer: no managed memory left (%s); use vkp_download / "
+                         "Array.to_host() for bulk reads", b->bytes, vkp_last_error());
+  vkp_block* nb = ctx->blocks[np];
+  void* bufs[2] = {ptr, np};
+  VKP_TRY(vkp_prepare_buffers(ctx, bufs, 2));   // also orders the copy after copy-engine transfers
+  VKP_TRY(stage_launch(ctx, ctx->stream, np, ptr, b->bytes));
+  ctx->seq++;
+  nb->guard_seq = ctx->seq;                     // vkp_host_acquire waits for the move
+  b->in_use = false;
+  b->guard_seq = b->last_seq;
+  ctx->live_bytes -= b->bytes;
+  ctx->free_lists[0][b->bytes].push_back(b);
+  *out = np;
+  return VKP_OK;
+}
+
 extern "C" int vkp_host_acquire(vkp_ctx* ctx, void* ptr, size_t bytes, int mode) {
   VKP_CHECK(ctx && ptr, "vkp_host_acquire: null argument");
   VKP_TRY(vkp_make_current(ctx));
@@ -477,6 +531,7 @@ extern "C" int vkp_host_acquire(vkp_ctx* ctx, void* ptr, size_t bytes, int mode)
   auto it = ctx->blocks.find(ptr);
   VKP_CHECK(it != ctx->blocks.end(), "vkp_host_acquire: %p is not a buffer of this context", ptr);
   vkp_block* b = it->second;
+  VKP_CHECK(b->managed, "vkp_host_acquire: %p is device memory; call vkp_host_view first", ptr);
   const bool prefetch = (mode & 1) != 0, writing = (mode & 2) != 0;
   if (b->h2d_ev) {   // copy-engine upload in flight: the host view must see it
     VKP_CUDA(cudaEventSynchronize(b->h2d_ev));
