@@ -40,6 +40,32 @@ OPS = [
     ("sin(b)", 8), ("exp(b)", 8), ("a**b", 12), ("a**2.7", 8), ("clamp_ss", 8), ("clamp_vv", 16),
 ]
 BYTES_PER_ELEM = sum(b for _, b in OPS)
+# op -> kernel-name fragment in the committed ncu capture of this step (profiles/*ncu_elementwise*.csv)
+NCU_KERNEL = {"a+b": "ew_kernel<2, FAdd>", "a*b": "ew_kernel<2, FMul>", "c+=b": "ew_kernel<2, FAdd>",
+              "a*2.5": "ew_kernel<1, FScalar<FMul", "a+row": "bcast_vec_kernel<BAdd", "a*col": "bcast_vec_kernel<BMul",
+              "sin(b)": "USin", "exp(b)": "TExp", "a**b": "TPow>", "a**2.7": "TPowScalar", "clamp_ss": "CClampSS",
+              "clamp_vv": "CClampVV"}
+
+
+def ncu_traffic(op, n_elems):
+    """DRAM bytes per launch of the op's kernel (dram__bytes_read.sum + dram__bytes_write.sum of the
+    committed `ncu --set full` capture, which ran this same step on 2^28 elements), or None."""
+    import csv, glob
+    root = os.path.dirname(os.path.abspath(__file__))
+    files = sorted(glob.glob(os.path.join(root, "profiles", "*ncu_elementwise*.csv")))
+    if not files or n_elems != 1 << 28:
+        return None, None
+    try:
+        rows = list(csv.reader(open(files[-1])))
+        h = rows[0]
+        kn, rd, wr = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+        unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[rows[1][rd]]
+        for r in rows[2:]:
+            if NCU_KERNEL[op] in r[kn]:
+                return int((float(r[rd]) + float(r[wr])) * unit), os.path.relpath(files[-1], root)
+    except Exception:
+        pass
+    return None, None
 
 
 def op_list(a, b, row, col):
@@ -192,6 +218,24 @@ def reference_main(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------- GPU arm
+def bind_near_gpu(local_rank):
+    """Multi-rank runs: keep this rank's threads (and so its page-locked staging memory, which is
+    placed on the allocating thread's NUMA node) on the CPUs next to its GPU's PCIe root."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        cpus = set()
+        for part in open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -220,6 +264,8 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    if world > 1:
+        bind_near_gpu(local_rank)
     import vulkpy_b200 as vk
     gpu = vk.GPU(local_rank)
     dev = gpu.gpu
@@ -292,8 +338,10 @@ def main():
     op_gbs = {name: bpe * n / (op_ms[name] * 1e-3) / 1e9 for name, bpe in OPS}
     dominant = max(op_ms, key=op_ms.get)
     peak, peak_src = measured_peak()
+    traffic, traffic_src = ncu_traffic(dominant, n)
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": round(op_gbs[dominant], 1), "peak": peak,
-                "unit": "GB/s", "frac": round(op_gbs[dominant] / peak, 4), "traffic": None,
+                "unit": "GB/s", "frac": round(op_gbs[dominant] / peak, 4), "traffic": traffic,
+                "traffic_source": traffic_src, "algorithmic_bytes": dict(OPS)[dominant] * n,
                 "peak_source": peak_src, "share_of_step": round(op_ms[dominant] / sum(op_ms.values()), 4),
                 "per_op_gbs": {k: round(v, 1) for k, v in op_gbs.items()},
                 "per_op_frac": {k: round(v / peak, 4) for k, v in op_gbs.items()}}

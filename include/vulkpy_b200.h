@@ -150,6 +150,17 @@ VKP_API int vkp_nn_activation_backward(vkp_ctx* ctx, int kind, const float* y, c
 VKP_API int vkp_nn_softmax_forward(vkp_ctx* ctx, const float* x, float* y, uint32_t rows, uint32_t cols,
                                    vkp_job** job);
 
+/* ---- argmax / argmin / permutation.  The reference lists them as missing
+ * (README.md:73 "argmax, argmin", :77 "shuffle") and its training example does them on the host
+ * (example/02-nn.py:82 `rng.shuffle(idx)`, :96 `np.argmax(pred_y, axis=1)`); semantics are NumPy's:
+ * first occurrence wins, NaN counts as the extreme.  `in` is [prev, axis, post] as in the axis
+ * reductions (vkarray.py:1398-1432), `out` [prev, post] uint32.  op: 0 = argmax, 1 = argmin.
+ * vkp_argsort_u32: out = indices 0..n-1 stably sorted by keys (np.argsort(keys, kind="stable"));
+ * with keys from vkp_rng_uint32 that is a random permutation. */
+VKP_API int vkp_argreduce(vkp_ctx* ctx, int op, const float* in, uint32_t* out, uint32_t prev, uint32_t axis,
+                          uint32_t post, vkp_job** job);
+VKP_API int vkp_argsort_u32(vkp_ctx* ctx, const uint32_t* keys, uint32_t* out, uint32_t n, vkp_job** job);
+
 /* ---- jobs: Job::wait (_vkarray.cc:446-456, :876-879) ------------------------------ */
 VKP_API int vkp_job_wait(vkp_job* job, uint64_t timeout_ns);   /* timeout_ns==UINT64_MAX: forever; 2 = timeout */
 VKP_API int vkp_job_done(vkp_job* job, int* done);

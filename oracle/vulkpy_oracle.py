@@ -385,3 +385,22 @@ def batch_affine(w, bias, x):
     for i in range(x.shape[1]):
         acc = (acc + (x[:, i:i + 1] * w[:, i][None, :]).astype(F32)).astype(F32)
     return (acc + bias[None, :]).astype(F32)
+
+
+# ---- argmax / argmin / permutation (additive; the reference does them with NumPy on the host:
+# example/02-nn.py:82 `rng.shuffle(idx)`, :96 `np.argmax(pred_y, axis=1)`) -------------------------
+def argmax(a, axis=None):
+    a = np.asarray(a, dtype=np.float32)
+    r = np.argmax(a, axis=axis)
+    return np.asarray(r, dtype=np.uint32).reshape((1,) if axis is None or a.ndim == 1 else r.shape)
+
+
+def argmin(a, axis=None):
+    a = np.asarray(a, dtype=np.float32)
+    r = np.argmin(a, axis=axis)
+    return np.asarray(r, dtype=np.uint32).reshape((1,) if axis is None or a.ndim == 1 else r.shape)
+
+
+def permutation_from_keys(keys):
+    """Indices 0..n-1 stably sorted by uint32 keys (keys = the generator's next n randint draws)."""
+    return np.argsort(np.asarray(keys, dtype=np.uint32), kind="stable").astype(np.uint32)

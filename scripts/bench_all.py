@@ -117,6 +117,9 @@ for op in ("sum", "maximum", "mean"):
     row(f"{op}(axis=None)", (lambda o: (lambda: getattr(a, o)()))(op), B4 + 4)
 row("sum(axis=1,rebroadcast)", lambda: a.sum(axis=1, rebroadcast=True), 2 * B4)
 row("maximum(axis=0,rebroadcast)", lambda: a.maximum(axis=0, rebroadcast=True), 2 * B4)
+row("argmax(axis=1)", lambda: a.argmax(axis=1), B4 + 4 * R)
+row("argmax(axis=0)", lambda: a.argmax(axis=0), B4 + 4 * R)
+row("argmin(axis=None)", lambda: a.argmin(), B4 + 4)
 a3 = a
 a3.reshape((R // 64, 64, R))
 row("sum(axis=1) of (R/64,64,R)", lambda: a3.sum(axis=1), B4 + 4 * N // 64)
@@ -155,6 +158,8 @@ for size in (64, 1 << 20):
     row(f"randint 2^30 (size={size})", (lambda gg: (lambda: gg.randint(buffer=ubuf)))(g), 4 * P)
     row(f"normal 2^30 (size={size})", (lambda gg: (lambda: gg.normal(buffer=buf)))(g), 4 * P)
 del buf, ubuf
+g = vk.random.Xoshiro128pp(gpu, size=1 << 20, seed=7)
+row("permutation(2^24)", lambda: g.permutation(1 << 24), 4 * (1 << 24) * 2, note="bytes = keys written + indices written; the radix sort moves more")
 
 # ---- C5 MLP step ---------------------------------------------------------------------------------------
 Bsz, D, H, C = (2048 if args.small else 8192), 1024, 1024, 16

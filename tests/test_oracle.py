@@ -198,3 +198,12 @@ def test_cross_entropy_known_answer():
     # test/test_nn.py:216-223: -log(0.5) = 0.6931472
     np.testing.assert_allclose(orc.cross_entropy([[0.5, 0.5]], [[1.0, 0.0]]).sum(), 0.6931472, rtol=1e-6)
     np.testing.assert_allclose(orc.cross_entropy_backward([[0.5, 0.5]], [[1.0, 0.0]]), [[-2.0, 0.0]], rtol=1e-6)
+
+
+def test_arg_and_permutation_oracle():
+    x = np.array([[1, 5, 5], [np.nan, 2, -1]], np.float32)
+    np.testing.assert_array_equal(orc.argmax(x, 1), [1, 0])
+    np.testing.assert_array_equal(orc.argmin(x, 1), [0, 0])
+    np.testing.assert_array_equal(orc.argmax(x), [3])
+    assert orc.argmax(x, 0).dtype == np.uint32
+    np.testing.assert_array_equal(orc.permutation_from_keys([5, 1, 5, 0]), [3, 1, 0, 2])

@@ -52,6 +52,8 @@ PROTOTYPES = {
     "vkp_upload_async": (C.c_int, [_vp, _vp, _vp, _sz, C.POINTER(_vp)]),
     "vkp_download_async": (C.c_int, [_vp, _vp, _vp, _sz, C.POINTER(_vp)]),
     "vkp_host_view": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "vkp_argreduce": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
+    "vkp_argsort_u32": (C.c_int, [_vp, _vp, _vp, C.c_uint32, C.POINTER(_vp)]),
     "vkp_upload": (C.c_int, [_vp, _vp, _vp, _sz]),
     "vkp_download": (C.c_int, [_vp, _vp, _vp, _sz]),
     "vkp_host_acquire": (C.c_int, [_vp, _vp, _sz, C.c_int]),
@@ -326,6 +328,16 @@ class Device:
         job = _vp()
         _check(lib.vkp_gemm(self._ctx, int(transA), int(transB), M, N, K, A.ptr, B.ptr, Cbuf.ptr,
                             bias.ptr if bias is not None else None, flags, C.byref(job)))
+        return Job(job.value)
+
+    def argreduce(self, op: int, src: Buffer, dst: "Shape", prev: int, axis: int, post: int) -> Job:
+        job = _vp()
+        _check(lib.vkp_argreduce(self._ctx, op, src.ptr, dst.ptr, prev, axis, post, C.byref(job)))
+        return Job(job.value)
+
+    def argsort_u32(self, keys: "Shape", dst: "Shape") -> Job:
+        job = _vp()
+        _check(lib.vkp_argsort_u32(self._ctx, keys.ptr, dst.ptr, keys.size(), C.byref(job)))
         return Job(job.value)
 
     def nn_adam(self, grad: Buffer, m: Buffer, v: Buffer, diff: Buffer, *scalars: float) -> Job:

@@ -88,6 +88,19 @@ class PRNG(Resource):
         out._keep = [u]
         return out
 
+    def permutation(self, n: int) -> vk.U32Array:
+        """Random permutation of ``0 .. n-1``: the indices stably sorted by ``n`` keys from
+        ``randint`` (``np.argsort(keys, kind="stable")``).  Additive: the reference lists shuffle
+        as missing (README.md:77) and example/02-nn.py:82 shuffles an index array on the host."""
+        n = int(n)
+        if n < 0:
+            raise ValueError(f"`n` must be non negative, but {n}")
+        keys = self.randint(shape=(n,))
+        out = vk.U32Array(self._gpu, shape=(n,))
+        out.job = self._gpu.gpu.argsort_u32(keys.buffer, out.buffer)
+        out._keep = [keys]
+        return out
+
     def wait(self):
         pass
 

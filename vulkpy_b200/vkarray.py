@@ -509,6 +509,38 @@ class Array(_GPUArray):
             ret *= (ret.buffer.size() / n_before)
         return ret
 
+    # -- argmax / argmin: listed as missing by the reference (README.md:73; example/02-nn.py:96 uses
+    #    np.argmax on the host); NumPy semantics, uint32 indices ------------------------------------
+    def _argreduce(self, op: int, axis: Optional[int]) -> U32Array:
+        if self.buffer.size() == 0:
+            raise ValueError("attempt to get argmax of an empty sequence")
+        if axis is None:
+            prev, n, post, shape = 1, self.buffer.size(), 1, (1,)
+        else:
+            (a,) = self._norm_axis(axis)
+            prev = int(np.prod(self.shape[:a], dtype=np.int64))
+            post = int(np.prod(self.shape[a + 1:], dtype=np.int64))
+            n, shape = int(self.shape[a]), tuple(self.shape[:a]) + tuple(self.shape[a + 1:])
+        ret = U32Array(self._gpu, shape=shape if len(shape) else (1,))
+        ret.job = self._gpu.gpu.argreduce(op, self.buffer, ret.buffer, prev, n, post)
+        ret._keep = [self]
+        return ret
+
+    def argmax(self, axis: Optional[int] = None) -> U32Array:
+        """Index of the first maximum (NaN counts as maximum) over everything (flat index, shape
+        ``(1,)``) or along ``axis`` -- ``np.argmax`` as ``uint32``."""
+        return self._argreduce(0, axis)
+
+    def argmin(self, axis: Optional[int] = None) -> U32Array:
+        """Index of the first minimum (NaN counts as minimum); see :meth:`argmax`."""
+        return self._argreduce(1, axis)
+
+    def shuffle(self, rng) -> "Array":
+        """Rows (leading axis) in a random order drawn from ``rng`` (a
+        ``vulkpy.random.Xoshiro128pp``): ``self.gather(rng.permutation(len), axis=0)``.  The
+        reference lists shuffle as missing (README.md:77; example/02-nn.py:82 shuffles on the host)."""
+        return self.gather(rng.permutation(int(self.shape[0])), axis=0)
+
     # -- broadcast / gather (reference: vkarray.py:1434-1521) ----------------------------------------
     def broadcast_to(self, shape: Iterable[int]) -> "Array":
         """Materialise the array broadcast to ``shape``; ``ValueError`` if not broadcastable."""
