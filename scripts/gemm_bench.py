@@ -13,7 +13,7 @@ for m in (2048, 4096, 8192):
     a = rng.random(shape=(m, m)); a -= 0.5
     b = rng.random(shape=(m, m)); b -= 0.5
     for name, flags in (("tc", 2), ("simt", 1)):
-        if name == "simt" and m > 4096:
+        if name == "simt" and (m > 4096 or os.environ.get("GEMM_BENCH_NO_SIMT")):
             continue
         c = vk.Array(gpu, shape=(m, m))
         for _ in range(2):
