@@ -193,7 +193,18 @@ VKP_API int vkp_comm_init(vkp_ctx* ctx, int nranks, int rank, const void* id);
 VKP_API int vkp_comm_destroy(vkp_ctx* ctx);
 /* op: 0 sum, 1 prod, 2 max, 3 min (the four reductions of vkarray.py:1278-1396) */
 VKP_API int vkp_comm_allreduce(vkp_ctx* ctx, const float* send, float* recv, size_t count, int op, vkp_job** job);
+/* n <= 16 tensors all-reduced in place as one grouped NCCL launch, then x *= scale on all of them in
+ * one kernel (the data-parallel gradient bucket: sum, then 1/world so reduce="mean" losses of
+ * nn/losses.py:41-46 keep their meaning) */
+VKP_API int vkp_comm_allreduce_multi(vkp_ctx* ctx, float* const* bufs, const size_t* counts, int n, int op,
+                                     float scale, vkp_job** job);
 VKP_API int vkp_comm_allgather(vkp_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank, vkp_job** job);
+/* Row-sharded matmul (vkarray.py:585-605 on a sharded pair): C[M,N] = A[M,K] @ B[K,N] with A, C the
+ * local row blocks and B_shard the local [K/nranks, N] row block of B.  The peers' shards are pulled
+ * over NVLink (CUDA IPC peer memory, copy engines) while ONE tcgen05 GEMM already runs on the local
+ * K range and enters each further range as its flag is raised; collective, same shapes on every rank. */
+VKP_API int vkp_comm_matmul_allgather(vkp_ctx* ctx, uint32_t M, uint32_t N, uint32_t K, const float* A,
+                                      const float* B_shard, float* C, vkp_job** job);
 
 #ifdef __cplusplus
 }

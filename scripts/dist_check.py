@@ -34,6 +34,19 @@ A_f, B_f = rs.uniform(-1, 1, (R, K)).astype(F), rs.uniform(-1, 1, (K, 80)).astyp
 C = g.shard(A_f) @ g.shard(B_f)
 np.testing.assert_allclose(C.to_numpy(), A_f.astype(np.float64) @ B_f, atol=1e-4)
 
+# fused pull + GEMM path (vkp_comm_matmul_allgather): local rows >= 128, K/world a multiple of 32
+Mg, Kg, Ng = 256 * world, 64 * world, 384
+A_f, B_f = rs.uniform(-1, 1, (Mg, Kg)).astype(F), rs.uniform(-1, 1, (Kg, Ng)).astype(F)
+for rep in range(3):      # three calls: both staging copies and the epoch flags get reused
+    C = g.shard(A_f) @ g.shard(B_f)
+    want = A_f.astype(np.float64) @ B_f
+    mag = np.abs(A_f).astype(np.float64) @ np.abs(B_f)
+    err = float((np.abs(C.to_numpy() - want) / mag).max())
+    assert err < 6e-6, err
+    B_f = B_f + F(0.25)    # new contents every call: a stale staging copy would show
+out["fused_matmul_used"] = not g.t._fused_broken
+out["fused_matmul_err"] = err
+
 # ---- sharded PRNG == single-GPU stream -------------------------------------------------------------
 shape = (16 * world, 256)
 ref = np.asarray(vk.random.Xoshiro128pp(gpu, seed=11).random(shape=shape))
@@ -94,7 +107,35 @@ del x, y
 M = 8192
 A = g.random(rng, (M, M), "random"); Bm = g.random(rng, (M, M), "random")
 ms = timed(lambda: A @ Bm, reps=5)
-out["matmul 8192^3 row-sharded + allgather(B)"] = {"ms": round(ms, 3), "agg_tflops": round(2 * M ** 3 / ms / 1e9, 1)}
+out["matmul 8192^3 row-sharded, peers' B pulled inside one GEMM"] = {"ms": round(ms, 3), "agg_tflops": round(2 * M ** 3 / ms / 1e9, 1)}
+g.t._fused_broken = True          # the NCCL all-gather + GEMM path, for comparison
+ms = timed(lambda: A @ Bm, reps=5)
+out["matmul 8192^3 row-sharded, ncclAllGather(B) then GEMM"] = {"ms": round(ms, 3), "agg_tflops": round(2 * M ** 3 / ms / 1e9, 1)}
+g.t._fused_broken = False
+del A, Bm
+
+# weak-scaling matmul: 8192 rows of A per GPU (M = 8192 * world), B 8192 x 8192 sharded by rows
+A = g.random(rng, (M * world, M), "random"); Bm = g.random(rng, (M, M), "random")
+ms = timed(lambda: A @ Bm, reps=3)
+out["matmul (8192*world) x 8192 x 8192 weak scaling, fused"] = {"ms": round(ms, 3), "agg_tflops": round(2 * world * M ** 3 / ms / 1e9, 1)}
+del A, Bm
+
+# data-parallel MLP step (config 5): Dense(1024,1024)-ReLU-Dense(1024,16)-Softmax, Adam, 8192 rows per GPU
+def make_mlp():
+    opt = lambda: nn.Adam(gpu, lr=1e-3)
+    return nn.Sequence([nn.Dense(gpu, 1024, 1024, w_opt=opt(), b_opt=opt(), w_init=nn.HeNormal(gpu, 1024, seed=1)), nn.ReLU(),
+                        nn.Dense(gpu, 1024, 16, w_opt=opt(), b_opt=opt(), w_init=nn.HeNormal(gpu, 1024, seed=2)), nn.Softmax()],
+                       nn.CrossEntropyLoss())
+Bl = 8192
+xb = vk.random.Xoshiro128pp(gpu, size=1 << 16, seed=100 + rank).normal(shape=(Bl, 1024))
+yb = vk.random.Xoshiro128pp(gpu, size=1 << 16, seed=200 + rank).randrange(shape=(Bl,), low=0, high=16).to_onehot(16)
+mlp = make_mlp()
+dpm = dist.DataParallel(mlp, g)
+ms = timed(lambda: dpm.train(xb, yb)[1], reps=10)
+out["DP MLP step (8192 rows/GPU)"] = {"ms": round(ms, 4), "agg_rows_per_s": round(Bl * world / ms * 1e3, 1)}
+single_mlp = make_mlp()
+ms1 = timed(lambda: single_mlp.train(xb, yb)[1], reps=10)
+out["MLP step without exchange"] = {"ms": round(ms1, 4)}
 if rank == 0:
     print(json.dumps(out))
 g.t.close()

@@ -26,6 +26,8 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -50,6 +52,8 @@ int load_nccl() {
   SYM(CommDestroy, "ncclCommDestroy");
   SYM(AllReduce, "ncclAllReduce");
   SYM(AllGather, "ncclAllGather");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
   SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
   g_nccl.lib = h;
@@ -64,9 +68,35 @@ int load_nccl() {
 
 }  // namespace
 
+// vkp_gemm_tc.cu
+int vkp_tc_split_lo(vkp_ctx* ctx, cudaStream_t stream, const float* in, float* lo, size_t elems);
+int vkp_tc_split_lo_2d(vkp_ctx* ctx, cudaStream_t stream, const float* in, float* lo, uint32_t rows, uint32_t cols,
+                       size_t ld);
+int vkp_tc_transpose_split(vkp_ctx* ctx, cudaStream_t stream, const float* in, uint32_t rows, uint32_t cols,
+                           float* hi, float* lo, size_t ldo);
+int vkp_gemm_tc_chunked(vkp_ctx* ctx, uint32_t M, uint32_t N, uint32_t K, const float* A, const float* Alo,
+                        const float* Bt, const float* Btlo, float* C, vkp_tc_chunks ch);
+int vkp_gemm_tc_supported(int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
+                          const float* B, float* C, int forced);
+
+#define VKP_MAX_RANKS 64
+#define VKP_MAX_BUCKET 16
+
 struct vkp_comm_state {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
+  // ---- row-sharded matmul over peer memory (vkp_comm_matmul_allgather) ----
+  cudaStream_t pull_stream = nullptr;     // copy-engine pulls of the peers' shards + their lo split + flags
+  cudaEvent_t ready_ev = nullptr;         // this rank's shard is staged and every rank passed the barrier
+  cudaEvent_t pull_done_ev = nullptr;     // last pull of the previous call has finished
+  float* barrier_word = nullptr;          // 1-element all-reduce = stream-ordered barrier
+  uint32_t* flags = nullptr;              // [VKP_MAX_RANKS] K-range c is valid once flags[c] == epoch
+  uint32_t epoch = 0;
+  // symmetric staging: two [N, K] K-major copies of B (alternating per call), exported with CUDA IPC
+  void* symm = nullptr;
+  size_t symm_bytes = 0;                  // bytes of ONE copy
+  void* peer[VKP_MAX_RANKS] = {};         // peer[r] = rank r's symm mapped here (peer[rank] = symm)
+  uint64_t calls = 0;
 };
 
 static_assert(VKP_COMM_ID_BYTES == sizeof(ncclUniqueId), "unique id size");
@@ -105,7 +135,17 @@ extern "C" int vkp_comm_destroy(vkp_ctx* ctx) {
   if (!ctx->comm) return VKP_OK;
   VKP_TRY(vkp_make_current(ctx));
   cudaStreamSynchronize(ctx->stream);
-  g_nccl.CommDestroy(ctx->comm->comm);
+  vkp_comm_state* st = ctx->comm;
+  if (st->pull_stream) cudaStreamSynchronize(st->pull_stream);
+  for (int r = 0; r < st->nranks; r++)
+    if (r != st->rank && st->peer[r]) cudaIpcCloseMemHandle(st->peer[r]);
+  g_nccl.CommDestroy(st->comm);          // collective: every rank has stopped reading this rank's memory
+  if (st->symm) cudaFree(st->symm);
+  if (st->flags) cudaFree(st->flags);
+  if (st->barrier_word) cudaFree(st->barrier_word);
+  if (st->ready_ev) cudaEventDestroy(st->ready_ev);
+  if (st->pull_done_ev) cudaEventDestroy(st->pull_done_ev);
+  if (st->pull_stream) cudaStreamDestroy(st->pull_stream);
   delete ctx->comm;
   ctx->comm = nullptr;
   return VKP_OK;
@@ -123,6 +163,57 @@ extern "C" int vkp_comm_allreduce(vkp_ctx* ctx, const float* send, float* recv, 
   return vkp_finish_op(ctx, job);
 }
 
+// One bucket for a set of small tensors (the data-parallel gradient exchange): the
+// all-reduces are grouped into a single NCCL launch and one kernel applies the 1/world scale to all
+// of them, instead of a launch pair per parameter.
+namespace {
+struct ScaleMany {
+  float* ptr[VKP_MAX_BUCKET];
+  unsigned long long count[VKP_MAX_BUCKET];
+  int n;
+};
+__global__ void __launch_bounds__(256) scale_many_kernel(ScaleMany p, float scale) {
+  for (int t = 0; t < p.n; t++) {
+    float* x = p.ptr[t];
+    const size_t n = p.count[t];
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+      x[i] = x[i] * scale;
+  }
+}
+}  // namespace
+
+extern "C" int vkp_comm_allreduce_multi(vkp_ctx* ctx, float* const* bufs, const size_t* counts, int n, int op,
+                                        float scale, vkp_job** job) {
+  VKP_CHECK(ctx && ctx->comm, "vkp_comm_allreduce_multi: communicator not initialised");
+  VKP_CHECK(bufs && counts && n >= 1 && n <= VKP_MAX_BUCKET, "vkp_comm_allreduce_multi: 1..%d tensors", VKP_MAX_BUCKET);
+  VKP_CHECK(op >= 0 && op <= 3, "vkp_comm_allreduce_multi: bad op %d", op);
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  VKP_TRY(vkp_prepare_buffers(ctx, (void* const*)bufs, n));
+  ScaleMany sm;
+  sm.n = n;
+  size_t most = 0;
+  VKP_NCCL(g_nccl.GroupStart());
+  for (int t = 0; t < n; t++) {
+    sm.ptr[t] = bufs[t];
+    sm.count[t] = counts[t];
+    if (counts[t] > most) most = counts[t];
+    if (counts[t]) {
+      ncclResult_t r = g_nccl.AllReduce(bufs[t], bufs[t], counts[t], ncclFloat32, op, ctx->comm->comm, ctx->stream);
+      if (r != 0) {
+        g_nccl.GroupEnd();
+        return vkp_set_error("ncclAllReduce (grouped) failed: %s", g_nccl.GetErrorString(r));
+      }
+    }
+  }
+  VKP_NCCL(g_nccl.GroupEnd());
+  if (scale != 1.0f && most) {
+    scale_many_kernel<<<vkp_grid_for(ctx, most, 256, 4), 256, 0, ctx->stream>>>(sm, scale);
+    VKP_TRY(vkp_after_launch(ctx, "scale_many"));
+  }
+  return vkp_finish_op(ctx, job);
+}
+
 extern "C" int vkp_comm_allgather(vkp_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank,
                                   vkp_job** job) {
   VKP_CHECK(ctx && ctx->comm, "vkp_comm_allgather: communicator not initialised");
@@ -132,5 +223,140 @@ extern "C" int vkp_comm_allgather(vkp_ctx* ctx, const void* send, void* recv, si
   VKP_TRY(vkp_prepare_buffers(ctx, bufs, 2));
   if (bytes_per_rank)
     VKP_NCCL(g_nccl.AllGather(send, recv, bytes_per_rank, ncclInt8, ctx->comm->comm, ctx->stream));
+  return vkp_finish_op(ctx, job);
+}
+
+// ======================================================================================================
+// Row-sharded matmul  C_r[M_r, N] = A_r[M_r, K] @ B[K, N],  B sharded by rows: rank s owns B_s[K/w, N]
+// ("all-gather of B chunked by K-block and overlapped with the GEMM").
+//
+// No all-gather call and no gathered copy of B in its original layout:
+//   1. every rank transposes + TF32-splits ITS shard once into the K-range it owns of a symmetric
+//      [N, K] staging matrix (K-major, what the tensor-core kernel wants) that is mapped into every
+//      peer with CUDA IPC; a one-word all-reduce is the barrier "all shards are staged";
+//   2. ONE persistent tcgen05 GEMM starts at once on the local K-range; its TMA producer walks the
+//      other ranges in ring order (rank+1, rank+2, ...) and before entering a range waits on a flag
+//      word in device memory;
+//   3. meanwhile a second stream pulls the peers' ranges over NVLink with the copy engines (no SM
+//      does communication), splits off their lo parts and raises the flags.  At step j every rank
+//      reads from a different owner, so all NVSwitch ports are busy.
+// The accumulators never leave TMEM between ranges, C is written once.  The staging matrix is
+// double-buffered by call parity, which makes the single barrier sufficient: a rank can overwrite
+// copy n%2 in call n only after it passed barrier n-1, i.e. after every peer finished GEMM n-2 and
+// with it all reads of that copy.
+// ======================================================================================================
+namespace {
+
+__global__ void set_flag_kernel(uint32_t* flag, uint32_t epoch) {
+  __threadfence_system();
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+
+int symm_reserve(vkp_ctx* ctx, vkp_comm_state* st, size_t bytes_one) {
+  if (bytes_one <= st->symm_bytes) return VKP_OK;
+  // collective growth (all ranks see the same shapes): quiesce, drop the old mappings, re-export
+  VKP_CUDA(cudaStreamSynchronize(ctx->stream));
+  VKP_CUDA(cudaStreamSynchronize(st->pull_stream));
+  VKP_NCCL(g_nccl.AllReduce(st->barrier_word, st->barrier_word, 1, ncclFloat32, ncclSum, st->comm, ctx->stream));
+  VKP_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int r = 0; r < st->nranks; r++) {
+    if (r != st->rank && st->peer[r]) VKP_CUDA(cudaIpcCloseMemHandle(st->peer[r]));
+    st->peer[r] = nullptr;
+  }
+  VKP_NCCL(g_nccl.AllReduce(st->barrier_word, st->barrier_word, 1, ncclFloat32, ncclSum, st->comm, ctx->stream));
+  VKP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (st->symm) VKP_CUDA(cudaFree(st->symm));
+  st->symm = nullptr;
+  st->symm_bytes = 0;
+  const size_t one = (bytes_one + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+  VKP_CUDA(cudaMalloc(&st->symm, 2 * one));
+  cudaIpcMemHandle_t mine;
+  VKP_CUDA(cudaIpcGetMemHandle(&mine, st->symm));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  unsigned char* dev_handles = nullptr;
+  VKP_CUDA(cudaMalloc(&dev_handles, 64 * (size_t)st->nranks));
+  VKP_CUDA(cudaMemcpyAsync(dev_handles + 64 * st->rank, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+  VKP_NCCL(g_nccl.AllGather(dev_handles + 64 * st->rank, dev_handles, 64, ncclInt8, st->comm, ctx->stream));
+  std::vector<cudaIpcMemHandle_t> all(st->nranks);
+  VKP_CUDA(cudaMemcpyAsync(all.data(), dev_handles, 64 * (size_t)st->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+  VKP_CUDA(cudaStreamSynchronize(ctx->stream));
+  VKP_CUDA(cudaFree(dev_handles));
+  for (int r = 0; r < st->nranks; r++) {
+    if (r == st->rank) { st->peer[r] = st->symm; continue; }
+    cudaError_t e = cudaIpcOpenMemHandle(&st->peer[r], all[r], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      st->peer[r] = nullptr;
+      return vkp_set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+    }
+  }
+  st->symm_bytes = one;
+  return VKP_OK;
+}
+
+}  // namespace
+
+extern "C" int vkp_comm_matmul_allgather(vkp_ctx* ctx, uint32_t M, uint32_t N, uint32_t K, const float* A,
+                                         const float* B_shard, float* C, vkp_job** job) {
+  VKP_CHECK(ctx && ctx->comm, "vkp_comm_matmul_allgather: communicator not initialised");
+  VKP_CHECK(A && B_shard && C, "vkp_comm_matmul_allgather: null argument");
+  vkp_comm_state* st = ctx->comm;
+  const uint32_t w = (uint32_t)st->nranks, rank = (uint32_t)st->rank;
+  VKP_CHECK(w <= VKP_MAX_RANKS, "vkp_comm_matmul_allgather: more than %d ranks", VKP_MAX_RANKS);
+  VKP_CHECK(K % w == 0 && (K / w) % 32 == 0, "vkp_comm_matmul_allgather: K = %u must split into %u ranges of whole 32-wide k-blocks", K, w);
+  VKP_CHECK(vkp_gemm_tc_supported(0, 1, M, N, K, A, B_shard, C, 1),
+            "vkp_comm_matmul_allgather: shape (%u,%u,%u) is not supported by the tensor-core kernel", M, N, K);
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  void* bufs[3] = {(void*)A, (void*)B_shard, (void*)C};
+  VKP_TRY(vkp_prepare_buffers(ctx, bufs, 3));
+  if (!st->pull_stream) {
+    int lo_p = 0, hi_p = 0;
+    VKP_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+    VKP_CUDA(cudaStreamCreateWithPriority(&st->pull_stream, cudaStreamNonBlocking, hi_p));
+    VKP_CUDA(cudaEventCreateWithFlags(&st->ready_ev, cudaEventDisableTiming));
+    VKP_CUDA(cudaEventCreateWithFlags(&st->pull_done_ev, cudaEventDisableTiming));
+    VKP_CUDA(cudaMalloc(&st->barrier_word, 256));
+    VKP_CUDA(cudaMemsetAsync(st->barrier_word, 0, 256, ctx->stream));
+    VKP_CUDA(cudaMalloc(&st->flags, sizeof(uint32_t) * VKP_MAX_RANKS));
+    VKP_CUDA(cudaMemsetAsync(st->flags, 0, sizeof(uint32_t) * VKP_MAX_RANKS, ctx->stream));
+  }
+  const size_t nk = (size_t)N * K, mk = (size_t)M * K;
+  VKP_TRY(symm_reserve(ctx, st, nk * sizeof(float)));
+  void* ws;
+  VKP_TRY(vkp_workspace(ctx, 1, (nk + mk) * sizeof(float), &ws));
+  float* bt_lo = static_cast<float*>(ws);
+  float* a_lo = bt_lo + nk;
+  const uint32_t kc = K / w;
+  const size_t copy_off = (st->calls & 1) ? st->symm_bytes : 0;
+  float* bt_hi = reinterpret_cast<float*>(static_cast<char*>(st->symm) + copy_off);
+  st->calls++;
+  st->epoch++;
+
+  // 1. stage the local operands (compute stream): A_lo, and B_shard^T (hi into the exported matrix)
+  VKP_TRY(vkp_tc_split_lo(ctx, ctx->stream, A, a_lo, mk));
+  VKP_TRY(vkp_tc_transpose_split(ctx, ctx->stream, B_shard, kc, N, bt_hi + (size_t)rank * kc, bt_lo + (size_t)rank * kc, K));
+  // barrier: every rank's shard is staged (and every rank is done with the copy used two calls ago)
+  VKP_NCCL(g_nccl.AllReduce(st->barrier_word, st->barrier_word, 1, ncclFloat32, ncclSum, st->comm, ctx->stream));
+  VKP_CUDA(cudaEventRecord(st->ready_ev, ctx->stream));
+
+  // 2. pulls over NVLink on the copy engines, ring order, then the lo split and the flag of that range
+  VKP_CUDA(cudaStreamWaitEvent(st->pull_stream, st->ready_ev, 0));
+  for (uint32_t j = 1; j < w; j++) {
+    const uint32_t s = (rank + j) % w;
+    const float* src = reinterpret_cast<const float*>(static_cast<const char*>(st->peer[s]) + copy_off) + (size_t)s * kc;
+    float* dst = bt_hi + (size_t)s * kc;
+    VKP_CUDA(cudaMemcpy2DAsync(dst, (size_t)K * 4, src, (size_t)K * 4, (size_t)kc * 4, N, cudaMemcpyDeviceToDevice,
+                               st->pull_stream));
+    VKP_TRY(vkp_tc_split_lo_2d(ctx, st->pull_stream, dst, bt_lo + (size_t)s * kc, N, kc, K));
+    set_flag_kernel<<<1, 1, 0, st->pull_stream>>>(st->flags + s, st->epoch);
+    VKP_TRY(vkp_after_launch(ctx, "set_flag"));
+  }
+  VKP_CUDA(cudaEventRecord(st->pull_done_ev, st->pull_stream));
+
+  // 3. one GEMM over all ranges, starting with the local one
+  vkp_tc_chunks ch{st->flags, st->epoch, 0, rank, w};
+  VKP_TRY(vkp_gemm_tc_chunked(ctx, M, N, K, A, a_lo, bt_hi, bt_lo, C, ch));
+  // later work on the compute stream may reuse the workspace: order it after the pull stream too
+  VKP_CUDA(cudaStreamWaitEvent(ctx->stream, st->pull_done_ev, 0));
   return vkp_finish_op(ctx, job);
 }

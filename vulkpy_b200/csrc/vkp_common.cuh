@@ -93,6 +93,15 @@ struct vkp_job {
   int kind = VKP_JOB_COMPUTE;
 };
 
+// K ranges of a GEMM that become valid while the kernel runs (vkp_gemm_tc.cu, vkp_comm.cu)
+struct vkp_tc_chunks {
+  const uint32_t* flags;   // [n_chunks] device words; range c may be read once flags[c] == epoch
+  uint32_t epoch;
+  uint32_t kb_per_chunk;   // filled in by the launcher
+  uint32_t first;          // range that is valid from the start (no flag), walked first
+  uint32_t n_chunks;       // <= 1: plain GEMM
+};
+
 struct vkp_timer {
   vkp_ctx* ctx;
   cudaEvent_t ev;

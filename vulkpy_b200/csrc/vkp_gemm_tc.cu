@@ -86,6 +86,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 
+// Wait until *flag == epoch (written by the stream that brings the K range in, after the data).
+// Bounded: ~2 s of polling, then trap -- a lost flag must fail the call, not hang the GPU.
+__device__ __forceinline__ void chunk_wait(const uint32_t* flag, uint32_t epoch) {
+  uint32_t v;
+  for (uint32_t spin = 0;; spin++) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v == epoch) break;
+    __nanosleep(200);
+    if (spin > (1u << 23)) __trap();
+  }
+  asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy acquire -> TMA (async proxy) reads
+}
+
 // K-major, swizzled rows of BK fp32 (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B), 8-row groups
 // 8*row bytes apart (SBO), version 1 (sm_100)
 template <int BK>
@@ -158,7 +171,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
                float* __restrict__ C, const float* __restrict__ bias, uint32_t M, uint32_t N, uint32_t K,
-               int accumulate, uint32_t splits, uint32_t kb_per_split) {
+               int accumulate, uint32_t splits, uint32_t kb_per_split, vkp_tc_chunks ch) {
+  // ch.n_chunks > 1 (row-sharded matmul, vkp_comm.cu): K is cut into n_chunks ranges that become
+  // valid one after the other while this kernel runs (peers' shards of B arriving over NVLink);
+  // the producer walks them starting at ch.first (the local shard) and, before the first load of
+  // another range, waits until ch.flags[range] == ch.epoch.
   // splits > 1 (split-K for problems with fewer output tiles than SMs): work item = (tile, split),
   // C is then a [splits][M][N] partial buffer and bias / accumulate are applied by splitk_reduce.
   using cfg = Cfg<BN, BK>;
@@ -240,7 +257,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tile_coords(tile, mb, nb);
         uint32_t kb0, kb1;
         k_range(tile, kb0, kb1);
-        for (uint32_t kb = kb0; kb < kb1; kb++) {
+        for (uint32_t it = kb0; it < kb1; it++) {
+          uint32_t kb = it;
+          if (ch.n_chunks > 1) {
+            const uint32_t ci = it / ch.kb_per_chunk;
+            uint32_t c = ch.first + ci;
+            if (c >= ch.n_chunks) c -= ch.n_chunks;
+            kb = c * ch.kb_per_chunk + (it - ci * ch.kb_per_chunk);
+            if (ci != 0 && it == ci * ch.kb_per_chunk) chunk_wait(ch.flags + c, ch.epoch);
+          }
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           uint8_t* st = smem + stage * cfg::STAGE_BYTES;
           const uint32_t fb = smem_u32(&full_bar[stage]);
@@ -392,8 +417,10 @@ __device__ __forceinline__ float tf32_lo(float x) {
 }
 
 // out[c, r] = in[r, c]   (in: rows x cols); with lo != nullptr also lo[c, r] = tf32_lo(in[r, c])
+// (ldo = leading dimension of out / lo, >= rows: lets a K-range of a wider [N, K] matrix be filled)
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                        float* __restrict__ lo, uint32_t rows, uint32_t cols) {
+                                                        float* __restrict__ lo, uint32_t rows, uint32_t cols,
+                                                        size_t ldo) {
   __shared__ float tile[32][33];
   const uint32_t bx = blockIdx.x * 32, by = blockIdx.y * 32;
   const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -406,9 +433,22 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
     const uint32_t c = bx + j, r = by + tx;
     if (c < cols && r < rows) {
       const float x = tile[tx][j];
-      out[(size_t)c * rows + r] = x;
-      if (lo) lo[(size_t)c * rows + r] = tf32_lo(x);
+      out[(size_t)c * ldo + r] = x;
+      if (lo) lo[(size_t)c * ldo + r] = tf32_lo(x);
     }
+  }
+}
+
+// lo[r, c] = tf32_lo(in[r, c]) for a [rows, cols] window of matrices with leading dimension ld
+// (cols % 4 == 0, 16-byte aligned rows)
+__global__ void __launch_bounds__(256) split_lo_2d_kernel(const float* __restrict__ in, float* __restrict__ lo,
+                                                          uint32_t rows, uint32_t cols, size_t ld) {
+  const uint32_t c4 = cols / 4;
+  const size_t n4 = (size_t)rows * c4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / c4, c = (i - r * c4) * 4;
+    const float4 x = *reinterpret_cast<const float4*>(in + r * ld + c);
+    *reinterpret_cast<float4*>(lo + r * ld + c) = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
   }
 }
 
@@ -454,7 +494,8 @@ int make_map(CUtensorMap* map, const float* ptr, uint32_t rows, uint32_t K, uint
 // Alo / Btlo: pre-split low parts (MODE_PRESPLIT) or nullptr (converter warps split in shared memory)
 template <int BN, int BK>
 int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, const float* Alo, const float* Btlo, float* C,
-              const float* bias, uint32_t M, uint32_t N, uint32_t K, int accumulate) {
+              const float* bias, uint32_t M, uint32_t N, uint32_t K, int accumulate,
+              vkp_tc_chunks ch = vkp_tc_chunks{nullptr, 0, 0, 0, 1}) {
   using cfg = Cfg<BN, BK>;
   const bool presplit = Alo != nullptr;
   CUtensorMap tmA, tmB, tmAlo, tmBlo;
@@ -470,7 +511,8 @@ int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, const float* Alo, c
   const uint32_t k_blocks = (K + BK - 1) / BK;
   // split-K when the output has fewer tiles than SMs and K is long: partials in workspace slot 0
   uint32_t splits = 1;
-  if (tiles * 2 <= (uint32_t)ctx->sms && k_blocks >= 16) {
+  if (ch.n_chunks > 1) ch.kb_per_chunk = (K / ch.n_chunks) / BK;   // caller guarantees divisibility
+  if (ch.n_chunks <= 1 && tiles * 2 <= (uint32_t)ctx->sms && k_blocks >= 16) {
     splits = (uint32_t)ctx->sms / tiles;
     if (splits > k_blocks / 8) splits = k_blocks / 8;
     if (splits > 16) splits = 16;
@@ -487,7 +529,7 @@ int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, const float* Alo, c
   const uint32_t work = tiles * splits;
   const unsigned grid = work < (uint32_t)ctx->sms ? work : (unsigned)ctx->sms;
   kernel<<<grid, NUM_THREADS, cfg::SMEM_BYTES, ctx->stream>>>(
-      tmA, tmB, tmAlo, tmBlo, dst, splits > 1 ? nullptr : bias, M, N, K, splits > 1 ? 0 : accumulate, splits, kb_per);
+      tmA, tmB, tmAlo, tmBlo, dst, splits > 1 ? nullptr : bias, M, N, K, splits > 1 ? 0 : accumulate, splits, kb_per, ch);
   VKP_TRY(vkp_after_launch(ctx, "gemm_tc(tcgen05 3xTF32)"));
   if (splits > 1) {
     const unsigned rgrid = vkp_grid_for(ctx, ((size_t)M * N + 3) / 4, 256, 8);
@@ -549,7 +591,7 @@ int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, ui
     }
     if (transA) {   // A stored [K, M] -> [M, K]
       dim3 g((M + 31) / 32, (K + 31) / 32);
-      transpose_kernel<<<g, 256, 0, ctx->stream>>>(A, w, alo, K, M);
+      transpose_kernel<<<g, 256, 0, ctx->stream>>>(A, w, alo, K, M, K);
       VKP_TRY(vkp_after_launch(ctx, "transpose(A)"));
       Ak = w;
       w += a_elems;
@@ -560,7 +602,7 @@ int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, ui
     }
     if (!transB) {  // B stored [K, N] -> [N, K]
       dim3 g((N + 31) / 32, (K + 31) / 32);
-      transpose_kernel<<<g, 256, 0, ctx->stream>>>(B, w, blo, K, N);
+      transpose_kernel<<<g, 256, 0, ctx->stream>>>(B, w, blo, K, N, K);
       VKP_TRY(vkp_after_launch(ctx, "transpose(B)"));
       Bk = w;
     } else if (presplit) {
@@ -580,4 +622,33 @@ int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, ui
     return launch_tc<256, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate);
   }
   return launch_tc<128, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate);
+}
+
+// ---- pieces of the row-sharded matmul (vkp_comm.cu): operands pre-split, K arriving in ranges ----
+int vkp_tc_split_lo(vkp_ctx* ctx, cudaStream_t stream, const float* in, float* lo, size_t elems) {
+  split_lo_kernel<<<vkp_grid_for(ctx, elems / 4, 256, 8), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(lo), elems / 4);
+  return vkp_after_launch(ctx, "split_lo");
+}
+
+int vkp_tc_split_lo_2d(vkp_ctx* ctx, cudaStream_t stream, const float* in, float* lo, uint32_t rows, uint32_t cols,
+                       size_t ld) {
+  split_lo_2d_kernel<<<vkp_grid_for(ctx, (size_t)rows * cols / 4, 256, 4), 256, 0, stream>>>(in, lo, rows, cols, ld);
+  return vkp_after_launch(ctx, "split_lo_2d");
+}
+
+// in: [rows, cols] row-major  ->  hi[c * ldo + r] = in[r, c], lo[...] = its TF32 low part
+int vkp_tc_transpose_split(vkp_ctx* ctx, cudaStream_t stream, const float* in, uint32_t rows, uint32_t cols,
+                           float* hi, float* lo, size_t ldo) {
+  dim3 g((cols + 31) / 32, (rows + 31) / 32);
+  transpose_kernel<<<g, 256, 0, stream>>>(in, hi, lo, rows, cols, ldo);
+  return vkp_after_launch(ctx, "transpose_split");
+}
+
+int vkp_gemm_tc_chunked(vkp_ctx* ctx, uint32_t M, uint32_t N, uint32_t K, const float* A, const float* Alo,
+                        const float* Bt, const float* Btlo, float* C, vkp_tc_chunks ch) {
+  VKP_CHECK(ch.n_chunks >= 1 && K % ch.n_chunks == 0 && (K / ch.n_chunks) % 32 == 0,
+            "vkp_gemm_tc_chunked: K = %u does not split into %u ranges of whole k-blocks", K, ch.n_chunks);
+  if (N % 256 == 0 || N >= 1024) return launch_tc<256, 16>(ctx, A, Bt, Alo, Btlo, C, nullptr, M, N, K, 0, ch);
+  return launch_tc<128, 32>(ctx, A, Bt, Alo, Btlo, C, nullptr, M, N, K, 0, ch);
 }

@@ -71,6 +71,23 @@ class NcclTransport:
         arr.job = b.Job(job.value)
         return arr
 
+    def allreduce_many(self, arrs, op: str, scale: float = 1.0):
+        """In-place all-reduce of up to 16 local arrays as ONE grouped NCCL launch, then
+        ``x *= scale`` on all of them in one kernel (``vkp_comm_allreduce_multi``)."""
+        b = self._b
+        for i in range(0, len(arrs), 16):
+            part = arrs[i:i + 16]
+            n = len(part)
+            ptrs = (C.c_void_p * n)(*[a.buffer.ptr for a in part])
+            counts = (C.c_size_t * n)(*[a.buffer.size() for a in part])
+            job = C.c_void_p()
+            b._check(b.lib.vkp_comm_allreduce_multi(self.gpu.gpu._ctx, ptrs, counts, n, _OPS[op],
+                                                    float(np.float32(scale)), C.byref(job)))
+            j = b.Job(job.value)
+            for a in part:
+                a.job = j
+        return arrs
+
     def allgather(self, arr, out):
         """``out`` (world * len(arr) elements) receives every rank's ``arr`` in rank order."""
         b = self._b
@@ -80,6 +97,34 @@ class NcclTransport:
         out.job = b.Job(job.value)
         out._keep = [arr]
         return out
+
+    def matmul_allgather(self, a, b_shard, n_cols: int):
+        """``a`` [M, K] local rows, ``b_shard`` [K/world, N] local rows of B -> local rows of A @ B.
+        One tcgen05 GEMM that starts on the local K range while the copy engines pull the peers'
+        shards over NVLink (``vkp_comm_matmul_allgather``).  Returns ``None`` when the shape does
+        not fit that kernel (the caller then all-gathers B and multiplies)."""
+        b = self._b
+        M, K = a.shape
+        kc = K // self.world
+        if (self._fused_broken or K % self.world or kc % 32 or b_shard.shape[0] != kc or M < 128 or n_cols < 128
+                or M % 4 or n_cols % 4):
+            return None
+        import vulkpy_b200 as vk
+        out = vk.Array(self.gpu, shape=(M, n_cols))
+        job = C.c_void_p()
+        try:
+            b._check(b.lib.vkp_comm_matmul_allgather(self.gpu.gpu._ctx, M, n_cols, K, a.buffer.ptr,
+                                                     b_shard.buffer.ptr, out.buffer.ptr, C.byref(job)))
+        except RuntimeError as e:      # e.g. CUDA IPC not permitted in this container: collective fallback
+            if "cudaIpc" not in str(e):
+                raise
+            self._fused_broken = True
+            return None
+        out.job = b.Job(job.value)
+        out._keep = [a, b_shard]
+        return out
+
+    _fused_broken = False
 
     def new_array(self, shape):
         import vulkpy_b200 as vk
@@ -284,6 +329,11 @@ class ShardedArray:
         if _is_sharded(other):
             if other.shape[0] != self.shape[-1]:
                 raise ValueError(f"Incompatible shapes: {self.shape} vs {other.shape}")
+            fused = getattr(self.group.t, "matmul_allgather", None)
+            if fused is not None and len(self.local.shape) == 2 and len(other.shape) == 2:
+                out = fused(self.local, other.local, int(other.shape[1]))
+                if out is not None:
+                    return self._like(out)
             other = other.allgather()
         return self._like(self.local @ other)
 
@@ -341,12 +391,15 @@ class DataParallel:
         net._zero_grad()
         net._backward()
         inv = 1.0 / g.world
-        for p in self.parameters():
-            g.t.allreduce(p.grad, "sum")
-            p.grad *= inv
+        bucket = [p.grad for p in self.parameters()] + [loss]
+        many = getattr(g.t, "allreduce_many", None)
+        if many is not None:            # one grouped exchange + one scale kernel for the whole bucket
+            many(bucket, "sum", inv)
+        else:
+            for t in bucket:
+                g.t.allreduce(t, "sum")
+                t *= inv
         net._update()
-        g.t.allreduce(loss, "sum")
-        loss *= inv
         return pred, loss
 
     def predict(self, x, y=None):
