@@ -205,6 +205,8 @@ VKP_API int vkp_comm_allgather(vkp_ctx* ctx, const void* send, void* recv, size_
  * K range and enters each further range as its flag is raised; collective, same shapes on every rank. */
 VKP_API int vkp_comm_matmul_allgather(vkp_ctx* ctx, uint32_t M, uint32_t N, uint32_t K, const float* A,
                                       const float* B_shard, float* C, vkp_job** job);
+/* diagnostics: device milliseconds the last vkp_comm_matmul_allgather spent pulling (synchronises) */
+VKP_API int vkp_comm_last_pull_ms(vkp_ctx* ctx, float* ms);
 
 #ifdef __cplusplus
 }
