@@ -142,6 +142,16 @@ VKP_API int vkp_nn_adam(vkp_ctx* ctx, const float* grad, float* m, float* v, flo
                         float beta1, float one_minus_beta1, float beta2, float one_minus_beta2,
                         float one_minus_beta1t, float one_minus_beta2t, float eps, float neg_lr,
                         vkp_job** job);
+/* The optimizer step of up to 16 parameters in one launch: per element vkp_nn_adam followed by
+ * Parameter.update's `value += diff` (nn/parameters.py:88-95).  scalars = [n_tensors][8]:
+ * beta1, 1-beta1, beta2, 1-beta2, 1-beta1^t, 1-beta2^t, eps, -lr as float32. */
+VKP_API int vkp_nn_adam_apply_many(vkp_ctx* ctx, int n_tensors, const float* const* grad, float* const* m,
+                                   float* const* v, float* const* value, const size_t* count,
+                                   const float* scalars, vkp_job** job);
+/* `a[:] = scalar` on up to 16 arrays in one launch (Parameter.zero_grad of a whole model,
+ * nn/parameters.py:81-86, nn/models.py:46-53) */
+VKP_API int vkp_fill_many_u32(vkp_ctx* ctx, int n_tensors, void* const* ptr, const size_t* count, uint32_t bits,
+                              vkp_job** job);
 /* kind 0: ReLU.backward dx = max(sign(y),0)*dy (nn/layers.py:207-210);
  * kind 1: Sigmoid/Softmax.backward dx = ((1-y)*y)*dy (nn/layers.py:262-267,320-323) */
 VKP_API int vkp_nn_activation_backward(vkp_ctx* ctx, int kind, const float* y, const float* dy, float* dx,

@@ -83,6 +83,9 @@ PROTOTYPES = {
     "vkp_timer_record": (C.c_int, [_vp]),
     "vkp_timer_elapsed_ms": (C.c_int, [_vp, _vp, C.POINTER(C.c_float)]),
     "vkp_timer_destroy": (C.c_int, [_vp]),
+    "vkp_nn_adam_apply_many": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                                         C.POINTER(_sz), C.POINTER(C.c_float), C.POINTER(_vp)]),
+    "vkp_fill_many_u32": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_sz), C.c_uint32, C.POINTER(_vp)]),
     "vkp_comm_unique_id": (C.c_int, [_vp]),
     "vkp_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "vkp_comm_destroy": (C.c_int, [_vp]),
@@ -346,6 +349,24 @@ class Device:
     def nn_adam(self, grad: Buffer, m: Buffer, v: Buffer, diff: Buffer, *scalars: float) -> Job:
         job = _vp()
         _check(lib.vkp_nn_adam(self._ctx, grad.ptr, m.ptr, v.ptr, diff.ptr, grad.size(), *scalars, C.byref(job)))
+        return Job(job.value)
+
+    def nn_adam_apply_many(self, grads, ms, vs, values, scalars) -> Job:
+        """One launch for the Adam step + ``value += diff`` of up to 16 parameters."""
+        n = len(grads)
+        arr = lambda bufs: (_vp * n)(*[b.ptr for b in bufs])
+        counts = (_sz * n)(*[b.size() for b in grads])
+        sc = (C.c_float * (8 * n))(*[x for row in scalars for x in row])
+        job = _vp()
+        _check(lib.vkp_nn_adam_apply_many(self._ctx, n, arr(grads), arr(ms), arr(vs), arr(values), counts, sc, C.byref(job)))
+        return Job(job.value)
+
+    def fill_many(self, bufs, bits: int) -> Job:
+        n = len(bufs)
+        ptrs = (_vp * n)(*[b.ptr for b in bufs])
+        counts = (_sz * n)(*[b.size() for b in bufs])
+        job = _vp()
+        _check(lib.vkp_fill_many_u32(self._ctx, n, ptrs, counts, bits & 0xFFFFFFFF, C.byref(job)))
         return Job(job.value)
 
     def nn_activation_backward(self, kind: int, y: Buffer, dy: Buffer, dx: Buffer) -> Job:

@@ -13,6 +13,7 @@
 namespace {
 
 constexpr int NB = 256;
+#define VKP_NN_MAX_TENSORS 16
 
 // m = m*b1 + (1-b1)*g ; v = v*b2 + (1-b2)*g^2 ; diff = (m/(1-b1t)) * (-lr) / (sqrt(v/(1-b2t)) + eps)
 // scalars arrive already rounded to float32 exactly as they cross the reference's boundary
@@ -35,6 +36,54 @@ adam_kernel(const float* __restrict__ g, float* __restrict__ m, float* __restric
     mh = mh * neg_lr;              // mhat *= -lr
     diff[i] = mh / vh;             // mhat /= vhat
   }
+}
+
+// The optimizer step of a whole model in one launch (blockIdx.y = tensor): per element exactly
+// adam_kernel followed by Parameter.update's `value += diff` (nn/parameters.py:88-95), diff rounded
+// to float32 before the add as the op-by-op path does.
+struct AdamMany {
+  const float* g[VKP_NN_MAX_TENSORS];
+  float* m[VKP_NN_MAX_TENSORS];
+  float* v[VKP_NN_MAX_TENSORS];
+  float* value[VKP_NN_MAX_TENSORS];
+  unsigned long long n[VKP_NN_MAX_TENSORS];
+  float s[VKP_NN_MAX_TENSORS][8];   // b1, 1-b1, b2, 1-b2, 1-b1^t, 1-b2^t, eps, -lr
+};
+__global__ void __launch_bounds__(NB) adam_apply_many_kernel(const __grid_constant__ AdamMany a) {
+  const int t = blockIdx.y;
+  const float* __restrict__ g = a.g[t];
+  float* __restrict__ m = a.m[t];
+  float* __restrict__ v = a.v[t];
+  float* __restrict__ val = a.value[t];
+  const size_t n = a.n[t];
+  const float b1 = a.s[t][0], omb1 = a.s[t][1], b2 = a.s[t][2], omb2 = a.s[t][3];
+  const float c1 = a.s[t][4], c2 = a.s[t][5], eps = a.s[t][6], neg_lr = a.s[t][7];
+  for (size_t i = blockIdx.x * (size_t)NB + threadIdx.x; i < n; i += (size_t)gridDim.x * NB) {
+    const float gi = g[i];
+    float mi = m[i] * b1;
+    mi = mi + omb1 * gi;
+    float vi = v[i] * b2;
+    vi = vi + omb2 * (gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    float mh = mi / c1;
+    float vh = vi / c2;
+    vh = __fsqrt_rn(vh);
+    vh = vh + eps;
+    mh = mh * neg_lr;
+    const float diff = mh / vh;
+    val[i] = val[i] + diff;        // self.value += diff
+  }
+}
+
+struct FillMany {
+  uint32_t* p[VKP_NN_MAX_TENSORS];
+  unsigned long long n[VKP_NN_MAX_TENSORS];
+};
+__global__ void __launch_bounds__(NB) fill_many_kernel(const __grid_constant__ FillMany a, uint32_t bits) {
+  uint32_t* __restrict__ p = a.p[blockIdx.y];
+  const size_t n = a.n[blockIdx.y];
+  for (size_t i = blockIdx.x * (size_t)NB + threadIdx.x; i < n; i += (size_t)gridDim.x * NB) p[i] = bits;
 }
 
 // dx = (sign(y) max 0) * dy   (ReLU.backward, nn/layers.py:207-210)
@@ -116,6 +165,53 @@ extern "C" int vkp_nn_adam(vkp_ctx* ctx, const float* grad, float* m, float* v, 
                                                                       one_minus_beta2, one_minus_beta1t,
                                                                       one_minus_beta2t, eps, neg_lr);
     VKP_TRY(vkp_after_launch(ctx, "nn_adam"));
+  }
+  return vkp_finish_op(ctx, job);
+}
+
+extern "C" int vkp_nn_adam_apply_many(vkp_ctx* ctx, int n_tensors, const float* const* grad, float* const* m,
+                                      float* const* v, float* const* value, const size_t* count,
+                                      const float* scalars /* [n_tensors][8] */, vkp_job** job) {
+  VKP_CHECK(ctx && grad && m && v && value && count && scalars, "vkp_nn_adam_apply_many: null argument");
+  VKP_CHECK(n_tensors >= 1 && n_tensors <= VKP_NN_MAX_TENSORS, "vkp_nn_adam_apply_many: 1..%d tensors", VKP_NN_MAX_TENSORS);
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g_(ctx->mu);
+  void* bufs[4 * VKP_NN_MAX_TENSORS];
+  AdamMany a;
+  size_t most = 0;
+  for (int t = 0; t < n_tensors; t++) {
+    bufs[4 * t] = (void*)grad[t]; bufs[4 * t + 1] = m[t]; bufs[4 * t + 2] = v[t]; bufs[4 * t + 3] = value[t];
+    a.g[t] = grad[t]; a.m[t] = m[t]; a.v[t] = v[t]; a.value[t] = value[t]; a.n[t] = count[t];
+    for (int k = 0; k < 8; k++) a.s[t][k] = scalars[8 * t + k];
+    if (count[t] > most) most = count[t];
+  }
+  VKP_TRY(vkp_prepare_buffers(ctx, bufs, 4 * n_tensors));
+  if (most) {
+    dim3 grid(vkp_grid_for(ctx, most, NB, 16), n_tensors);
+    adam_apply_many_kernel<<<grid, NB, 0, ctx->stream>>>(a);
+    VKP_TRY(vkp_after_launch(ctx, "nn_adam_apply_many"));
+  }
+  return vkp_finish_op(ctx, job);
+}
+
+extern "C" int vkp_fill_many_u32(vkp_ctx* ctx, int n_tensors, void* const* ptr, const size_t* count, uint32_t bits,
+                                 vkp_job** job) {
+  VKP_CHECK(ctx && ptr && count, "vkp_fill_many_u32: null argument");
+  VKP_CHECK(n_tensors >= 1 && n_tensors <= VKP_NN_MAX_TENSORS, "vkp_fill_many_u32: 1..%d tensors", VKP_NN_MAX_TENSORS);
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g_(ctx->mu);
+  FillMany a;
+  size_t most = 0;
+  for (int t = 0; t < n_tensors; t++) {
+    a.p[t] = static_cast<uint32_t*>(ptr[t]);
+    a.n[t] = count[t];
+    if (count[t] > most) most = count[t];
+  }
+  VKP_TRY(vkp_prepare_buffers(ctx, ptr, n_tensors));
+  if (most) {
+    dim3 grid(vkp_grid_for(ctx, most, NB * 4, 8), n_tensors);
+    fill_many_kernel<<<grid, NB, 0, ctx->stream>>>(a, bits);
+    VKP_TRY(vkp_after_launch(ctx, "fill_many"));
   }
   return vkp_finish_op(ctx, job);
 }

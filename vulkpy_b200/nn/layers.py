@@ -21,6 +21,7 @@ def _fused_backward(kind: int, y: Array, dy: Array) -> Array:
     return dx
 
 Init = Callable[[GPU, Iterable[int]], Array]
+_GEMM_ACCUMULATE = 4   # VKP_GEMM_ACCUMULATE (include/vulkpy_b200.h)
 
 
 class Dense(Module):
@@ -57,15 +58,30 @@ class Dense(Module):
         The reference forms dW by materialising ``dy[:, :, None] * x[:, None, :]``
         (batch x out x in) and summing over the batch (layers.py:126-141); the same
         contraction is one GEMM here."""
+        self._backward_params(dy)
+        return dy @ self.w.value
+
+    def _backward_params(self, dy: Array):
+        """Parameter gradients only (what ``Sequence`` needs from its first layer)."""
         self.b.add_grad(dy.sum(axis=0))
         x = self._x
         dev = dy._gpu.gpu
+        g = self.w.grad
+        if g is not None and not _opt.UNFUSED:
+            # `grad += dy^T x` in the GEMM epilogue: the accumulated float32 product is added to
+            # the old value with one rounding, exactly what add_grad's `+=` does to a temporary
+            g.job = dev.gemm(True, False, self.output_dim, self.input_dim, dy.shape[0],
+                             dy.buffer, x.buffer, g.buffer, None, _GEMM_ACCUMULATE)
+            g._keep = [dy, x]
+            return
         dW = Array(dy._gpu, shape=(self.output_dim, self.input_dim))
         dW.job = dev.gemm(True, False, self.output_dim, self.input_dim, dy.shape[0],
                           dy.buffer, x.buffer, dW.buffer)
         dW._keep = [dy, x]
         self.w.add_grad(dW)
-        return dy @ self.w.value
+
+    def _parameters(self):
+        return [self.w, self.b]
 
     def zero_grad(self):
         self.w.zero_grad()

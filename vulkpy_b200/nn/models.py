@@ -7,6 +7,8 @@ from typing import Iterable, Optional, Tuple, Union
 
 from ..vkarray import Array
 from .core import Module, Loss
+from . import optimizers as _opt
+from .optimizers import AdamState
 
 __all__ = ["Sequence"]
 
@@ -25,17 +27,72 @@ class Sequence:
         return x
 
     def _backward(self):
+        """Layers in reverse.  The reference also asks the FIRST layer for the gradient of the
+        network input and drops it (models.py:46-53); a layer that can produce its parameter
+        gradients alone (``_backward_params``) is spared that contraction."""
         dx = self.loss.grad()
+        first = self.L[0] if self.L else None
         for layer in reversed(self.L):
-            dx = layer.backward(dx)
+            if layer is first and not _opt.UNFUSED and hasattr(layer, "_backward_params"):
+                layer._backward_params(dx)
+            else:
+                dx = layer.backward(dx)
+
+    def _known_parameters(self):
+        """(parameters of the layers that expose them, the other layers)."""
+        params, rest = [], []
+        for layer in self.L:
+            ps = getattr(layer, "_parameters", None)
+            if ps is None:
+                rest.append(layer)
+            else:
+                params.extend(p for p in ps() if p.grad is not None)
+        return params, rest
 
     def _zero_grad(self):
-        for layer in self.L:
+        if _opt.UNFUSED:
+            for layer in self.L:
+                layer.zero_grad()
+            return
+        params, rest = self._known_parameters()
+        for layer in rest:
             layer.zero_grad()
+        # all gradients in one device fill (the reference zeroes each through its host view)
+        for i in range(0, len(params), 16):
+            part = [p.grad for p in params[i:i + 16]]
+            job = part[0]._gpu.gpu.fill_many([g.buffer for g in part], 0)
+            for g in part:
+                g.job = job
+                g._keep = []
 
     def _update(self):
-        for layer in self.L:
+        if _opt.UNFUSED:
+            for layer in self.L:
+                layer.update()
+            return
+        params, rest = self._known_parameters()
+        for layer in rest:
             layer.update()
+        adam = [p for p in params if type(p.opt_state) is AdamState]
+        for p in params:
+            if type(p.opt_state) is not AdamState:
+                p.update()
+        # Adam step and `value += diff` of every parameter in one launch, same float32 operations
+        # in the same order as AdamState.grad2diff + Parameter.update (nn/optimizers.py:235-253)
+        for i in range(0, len(adam), 16):
+            part = adam[i:i + 16]
+            rows = []
+            for p in part:
+                st, o = p.opt_state, p.opt_state.opt
+                st.beta1t *= o.beta1
+                st.beta2t *= o.beta2
+                rows.append((o.beta1, 1 - o.beta1, o.beta2, 1 - o.beta2, 1 - st.beta1t, 1 - st.beta2t, o.eps, -o.lr))
+            dev = part[0].value._gpu.gpu
+            job = dev.nn_adam_apply_many([p.grad.buffer for p in part], [p.opt_state.m.buffer for p in part],
+                                         [p.opt_state.v.buffer for p in part], [p.value.buffer for p in part], rows)
+            for p in part:
+                p.value.job = p.opt_state.m.job = p.opt_state.v.job = job
+                p.value._keep = [p.grad]
 
     def train(self, x: Array, y: Array) -> Tuple[Array, Array]:
         pred = self._forward(x)

@@ -18,6 +18,8 @@ from __future__ import annotations
 
 from typing import Iterable, Optional
 
+import math
+
 import numpy as np
 
 from . import _backend as _b
@@ -55,7 +57,7 @@ class PRNG(Resource):
         """Box-Muller over ``random()`` output: in place for even n, via an (n+1)-element
         temporary for odd n (reference: random.py:60-124)."""
         out = _target(vk.Array, self._gpu, shape, buffer)
-        n = int(np.prod(out.shape, dtype=np.int64))
+        n = math.prod(out.shape)
         p = _b.VectorScalar2Params(n, float(mean), float(stddev))
         d = _b.DataShape(n // 2, 1, 1)
         if n % 2 == 0:
@@ -118,7 +120,7 @@ class Xoshiro128pp(PRNG):
                buffer: Optional[vk.Array] = None) -> vk.Array:
         """Uniform float32 in [0, 1)."""
         out = _target(vk.Array, self._gpu, shape, buffer)
-        out.job = self.rng.random_float(int(np.prod(out.shape, dtype=np.int64)), out.buffer.info())
+        out.job = self.rng.random_float(math.prod(out.shape), out.buffer.info())
         out._keep = [self]
         return out
 
@@ -126,7 +128,7 @@ class Xoshiro128pp(PRNG):
                 buffer: Optional[vk.U32Array] = None) -> vk.U32Array:
         """Uniform uint32 in [0, 2^32)."""
         out = _target(vk.U32Array, self._gpu, shape, buffer)
-        out.job = self.rng.random_uint32(int(np.prod(out.shape, dtype=np.int64)), out.buffer.info())
+        out.job = self.rng.random_uint32(math.prod(out.shape), out.buffer.info())
         out._keep = [self]
         return out
 
@@ -136,7 +138,7 @@ class Xoshiro128pp(PRNG):
         if self.rng.size % 2:
             return super().normal(shape=shape, buffer=buffer, mean=mean, stddev=stddev)
         out = _target(vk.Array, self._gpu, shape, buffer)
-        n = int(np.prod(out.shape, dtype=np.int64))
+        n = math.prod(out.shape)
         out.job = self.rng.normal(n, out.buffer.info(), mean, stddev)
         out._keep = [self]
         return out
