@@ -122,3 +122,19 @@ def test_skinny_and_split_k(gpu, rs, M, N, K, ta, tb):
     assert (np.abs(got - (want + bias + c0)) / (mag + 2)).max() < TOL
     got2 = gemm(gpu, a, b, ta, tb, bias=bias, flags=ACC, c0=c0)
     np.testing.assert_array_equal(got, got2)          # deterministic
+
+
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False), (True, True)])
+def test_tc_gemm_presplit_path(gpu, rs, ta, tb):
+    """M, N >= 2048 takes the pre-split variant (lo tiles produced once in HBM, fused with the
+    transpose; 4-stage BK=16 ring): several k-block ring wraps per tile, same bound."""
+    M, N, K = 2048, 2304, 272
+    a = rs.uniform(-1, 1, (K, M) if ta else (M, K)).astype(F)
+    b = rs.uniform(-1, 1, (N, K) if tb else (K, N)).astype(F)
+    got = gemm(gpu, a, b, ta, tb, flags=TC)
+    want, mag = exact(a, b, ta, tb)
+    assert (np.abs(got - want) / mag).max() < TOL
+    bias = rs.normal(size=N).astype(F)
+    c0 = rs.normal(size=(M, N)).astype(F)
+    got = gemm(gpu, a, b, ta, tb, bias=bias, flags=TC | ACC, c0=c0)
+    assert (np.abs(got - (want + bias + c0)) / (mag + 2)).max() < TOL

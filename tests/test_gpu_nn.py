@@ -269,3 +269,37 @@ def test_fused_kernels_match_the_op_by_op_compositions(gpu, rs, monkeypatch):
         np.testing.assert_array_equal(a[k], b[k], err_msg=what)
     np.testing.assert_allclose(b[6], softmax64(b[7].astype(np.float64)), rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(a[6], b[6], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("dims", [(33, 20, 24, 5), (256, 128, 256, 16)])
+def test_sequence_step_fused_equals_op_by_op(gpu, rs, monkeypatch, dims):
+    """Sequence.train with the one-launch zero_grad / Adam+update, `grad += dy^T x` in the GEMM
+    epilogue and no input gradient for the first layer gives bit-identical parameters, moments and
+    loss to the reference's op-by-op order (nn/models.py:55-78, nn/parameters.py:81-95,
+    nn/optimizers.py:235-253), over several steps."""
+    import vulkpy_b200.nn.optimizers as O
+    B, d_in, hidden, classes = dims
+    x = rs.normal(size=(B, d_in)).astype(F)
+    y = np.eye(classes, dtype=F)[rs.integers(0, classes, B)]
+    res = {}
+    for unfused in (True, False):
+        monkeypatch.setattr(O, "UNFUSED", unfused)
+        opt = lambda: nn.Adam(gpu, lr=1e-2)
+        net = nn.Sequence([nn.Dense(gpu, d_in, hidden, w_opt=opt(), b_opt=opt(), w_init=nn.HeNormal(gpu, d_in, seed=3)),
+                           nn.ReLU(),
+                           nn.Dense(gpu, hidden, classes, w_opt=opt(), b_opt=opt(), w_init=nn.HeNormal(gpu, hidden, seed=4)),
+                           nn.Softmax()], nn.CrossEntropyLoss())
+        losses = []
+        for _ in range(3):
+            _, loss = net.train(vk.Array(gpu, data=x), vk.Array(gpu, data=y))
+            losses.append(np.asarray(loss).copy())
+        state = []
+        for layer in (net.L[0], net.L[2]):
+            for p in (layer.w, layer.b):
+                state += [np.asarray(p.value).copy(), np.asarray(p.grad).copy(),
+                          np.asarray(p.opt_state.m).copy(), np.asarray(p.opt_state.v).copy()]
+        res[unfused] = (losses, state)
+    for u, f in zip(res[True][0], res[False][0]):
+        np.testing.assert_array_equal(u, f)
+    for k, (u, f) in enumerate(zip(res[True][1], res[False][1])):
+        np.testing.assert_array_equal(u, f, err_msg=f"state {k}")
