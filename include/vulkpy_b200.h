@@ -210,13 +210,12 @@ VKP_API int vkp_comm_allreduce_multi(vkp_ctx* ctx, float* const* bufs, const siz
                                      float scale, vkp_job** job);
 VKP_API int vkp_comm_allgather(vkp_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank, vkp_job** job);
 /* Row-sharded matmul (vkarray.py:585-605 on a sharded pair): C[M,N] = A[M,K] @ B[K,N] with A, C the
- * local row blocks and B_shard the local [K/nranks, N] row block of B.  The peers' shards are pulled
- * over NVLink (CUDA IPC peer memory, copy engines) while ONE tcgen05 GEMM already runs on the local
- * K range and enters each further range as its flag is raised; collective, same shapes on every rank. */
+ * local row blocks and B_shard the local [K/nranks, N] row block of B.  ONE tcgen05 GEMM kernel: it
+ * starts on the local K range while its spare warps pull the peers' shards over NVLink (CUDA IPC
+ * peer memory) and enters each further range as its flag is raised; collective, same shapes on
+ * every rank, at most 16 ranks. */
 VKP_API int vkp_comm_matmul_allgather(vkp_ctx* ctx, uint32_t M, uint32_t N, uint32_t K, const float* A,
                                       const float* B_shard, float* C, vkp_job** job);
-/* diagnostics: device milliseconds the last vkp_comm_matmul_allgather spent pulling (synchronises) */
-VKP_API int vkp_comm_last_pull_ms(vkp_ctx* ctx, float* ms);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,5 @@
-"""Pull-phase probe for the row-sharded matmul at the 8-GPU geometry (32 MiB ranges, 4 KB rows), runnable on 2 GPUs:
-    VKP_PULL_PARTS=p python -m torch.distributed.run --nproc-per-node 2 ... scripts/pull_probe.py"""
+"""Row-sharded matmul timing at the 8-GPU range geometry (32 MiB ranges, 4 KB rows), runnable on 2 GPUs:
+    python -m torch.distributed.run --nproc-per-node 2 ... scripts/pull_probe.py"""
 import ctypes as C, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -22,11 +22,9 @@ for (M, N, K) in ((1024 * world, 8192, 1024 * world), (4096 * world, 8192, 8192)
         c = A @ Bm; del c
     t1.record()
     ms = t0.elapsed_ms(t1) / 5
-    pm = C.c_float()
-    b._check(b.lib.vkp_comm_last_pull_ms(gpu.gpu._ctx, C.byref(pm)))
     per_rank_bytes = (world - 1) * (K // world) * N * 4
-    out[f"{M}x{N}x{K}"] = {"ms": round(ms, 4), "pull_ms": round(pm.value, 4),
-                           "pull_gbs": round(per_rank_bytes / pm.value / 1e6, 1), "tflops_agg": round(2 * M * N * K / ms / 1e9, 1)}
+    out[f"{M}x{N}x{K}"] = {"ms": round(ms, 4), "pulled_MB_per_rank": round(per_rank_bytes / 1e6, 1),
+                           "tflops_agg": round(2 * M * N * K / ms / 1e9, 1)}
     del A, Bm
 if rank == 0:
     print(json.dumps(out))

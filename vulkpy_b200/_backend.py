@@ -92,7 +92,6 @@ PROTOTYPES = {
     "vkp_comm_allreduce": (C.c_int, [_vp, _vp, _vp, _sz, C.c_int, C.POINTER(_vp)]),
     "vkp_comm_allgather": (C.c_int, [_vp, _vp, _vp, _sz, C.POINTER(_vp)]),
     "vkp_comm_allreduce_multi": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_sz), C.c_int, C.c_int, C.c_float, C.POINTER(_vp)]),
-    "vkp_comm_last_pull_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "vkp_comm_matmul_allgather": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.POINTER(_vp)]),
 }
 

@@ -71,35 +71,22 @@ int load_nccl() {
 
 // vkp_gemm_tc.cu
 int vkp_tc_split_lo(vkp_ctx* ctx, cudaStream_t stream, const float* in, float* lo, size_t elems);
-int vkp_tc_split_lo_2d(vkp_ctx* ctx, cudaStream_t stream, const float* in, float* lo, uint32_t rows, uint32_t cols,
-                       size_t ld);
 int vkp_tc_transpose_split(vkp_ctx* ctx, cudaStream_t stream, const float* in, uint32_t rows, uint32_t cols,
                            float* hi, float* lo, size_t ldo);
 int vkp_gemm_tc_chunked(vkp_ctx* ctx, uint32_t M, uint32_t N, uint32_t K, const float* A, const float* Alo,
-                        const float* Bt, const float* Btlo, float* C, vkp_tc_chunks ch);
+                        const float* Bt, const float* Btlo, float* C, vkp_tc_chunks ch, const vkp_tc_pull* pull);
 int vkp_gemm_tc_supported(int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
                           const float* B, float* C, int forced);
 
-#define VKP_MAX_RANKS 64
 #define VKP_MAX_BUCKET 16
 
 struct vkp_comm_state {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
   // ---- row-sharded matmul over peer memory (vkp_comm_matmul_allgather) ----
-  cudaStream_t pull_stream = nullptr;     // copy-engine pulls of the peers' shards + their lo split + flags
-  // one copy engine does not fill an NVLink port with 4 KB rows: each range is pulled as `parts`
-  // row bands on as many streams (part 0 on pull_stream, which then joins the others)
-  static constexpr int MAX_PARTS = 8;
-  int parts = 1;
-  cudaStream_t part_stream[MAX_PARTS] = {};
-  cudaEvent_t part_ev[MAX_PARTS] = {};
-  cudaEvent_t pull_t0 = nullptr, pull_t1 = nullptr;   // timing of the last call's pull phase (diagnostics)
-  cudaEvent_t ready_ev = nullptr;         // this rank's shard is staged and every rank passed the barrier
-  cudaEvent_t pull_done_ev = nullptr;     // last pull of the previous call has finished
   float* barrier_word = nullptr;          // 1-element all-reduce = stream-ordered barrier
-  uint32_t* flags = nullptr;              // [2 * VKP_MAX_RANKS]: flags, then the pull kernel's arrival counters;
-                                          // K-range c is valid once flags[c] == epoch
+  uint32_t* flags = nullptr;              // [2 * VKP_MAX_RANKS]: range flags, then arrival counters;
+                                          // K range c is valid once flags[c] == epoch
   uint32_t epoch = 0;
   // symmetric staging: two [N, K] K-major copies of B (alternating per call), exported with CUDA IPC
   void* symm = nullptr;
@@ -145,22 +132,12 @@ extern "C" int vkp_comm_destroy(vkp_ctx* ctx) {
   VKP_TRY(vkp_make_current(ctx));
   cudaStreamSynchronize(ctx->stream);
   vkp_comm_state* st = ctx->comm;
-  if (st->pull_stream) cudaStreamSynchronize(st->pull_stream);
   for (int r = 0; r < st->nranks; r++)
     if (r != st->rank && st->peer[r]) cudaIpcCloseMemHandle(st->peer[r]);
   g_nccl.CommDestroy(st->comm);          // collective: every rank has stopped reading this rank's memory
   if (st->symm) cudaFree(st->symm);
   if (st->flags) cudaFree(st->flags);
   if (st->barrier_word) cudaFree(st->barrier_word);
-  if (st->ready_ev) cudaEventDestroy(st->ready_ev);
-  if (st->pull_done_ev) cudaEventDestroy(st->pull_done_ev);
-  for (int i = 1; i < vkp_comm_state::MAX_PARTS; i++) {
-    if (st->part_stream[i]) { cudaStreamSynchronize(st->part_stream[i]); cudaStreamDestroy(st->part_stream[i]); }
-    if (st->part_ev[i]) cudaEventDestroy(st->part_ev[i]);
-  }
-  if (st->pull_t0) cudaEventDestroy(st->pull_t0);
-  if (st->pull_t1) cudaEventDestroy(st->pull_t1);
-  if (st->pull_stream) cudaStreamDestroy(st->pull_stream);
   delete ctx->comm;
   ctx->comm = nullptr;
   return VKP_OK;
@@ -245,16 +222,16 @@ extern "C" int vkp_comm_allgather(vkp_ctx* ctx, const void* send, void* recv, si
 // Row-sharded matmul  C_r[M_r, N] = A_r[M_r, K] @ B[K, N],  B sharded by rows: rank s owns B_s[K/w, N]
 // ("all-gather of B chunked by K-block and overlapped with the GEMM").
 //
-// No all-gather call and no gathered copy of B in its original layout:
-//   1. every rank transposes + TF32-splits ITS shard once into the K-range it owns of a symmetric
+// No all-gather call, no gathered copy of B in its original layout, no communication kernel:
+//   1. every rank transposes + TF32-splits ITS shard once into the K range it owns of a symmetric
 //      [N, K] staging matrix (K-major, what the tensor-core kernel wants) that is mapped into every
 //      peer with CUDA IPC; a one-word all-reduce is the barrier "all shards are staged";
-//   2. ONE persistent tcgen05 GEMM starts at once on the local K-range; its TMA producer walks the
-//      other ranges in ring order (rank+1, rank+2, ...) and before entering a range waits on a flag
-//      word in device memory;
-//   3. meanwhile a second stream pulls the peers' ranges over NVLink with the copy engines (no SM
-//      does communication), splits off their lo parts and raises the flags.  At step j every rank
-//      reads from a different owner, so all NVSwitch ports are busy.
+//   2. ONE persistent tcgen05 GEMM (vkp_gemm_tc.cu) does the rest.  Its TMA producer starts on the
+//      local K range at once and walks the others in ring order (rank+1, rank+2, ...), waiting on a
+//      flag word before it enters a range; the four warps per CTA that the pre-split variant leaves
+//      idle fetch exactly those ranges, in the same order, with 16-byte loads from the mapped peer
+//      pointers over NVLink, store them with their lo parts and raise the flags (pull_ranges).  At
+//      step j every rank reads from a different owner, so all NVSwitch ports are busy.
 // The accumulators never leave TMEM between ranges, C is written once.  The staging matrix is
 // double-buffered by call parity, which makes the single barrier sufficient: a rank can overwrite
 // copy n%2 in call n only after it passed barrier n-1, i.e. after every peer finished GEMM n-2 and
@@ -262,83 +239,9 @@ extern "C" int vkp_comm_allgather(vkp_ctx* ctx, const void* send, void* recv, si
 // ======================================================================================================
 namespace {
 
-// All K ranges of the peers in one launch: CTAs stream each range out of the owner's exported
-// staging matrix with 16-byte volatile loads (peer memory over NVLink, never cached), store it
-// into the local matrix together with its TF32 low part, and the last CTA to finish a range
-// raises its flag.  Ring order (rank+1, rank+2, ...): at any time every owner serves one reader.
-// Co-resident with the persistent GEMM (no shared memory, 256 threads); no CTA waits on another.
-struct PullArgs {
-  const float* src[VKP_MAX_RANKS];   // src[s]: rank s's staging matrix (this call's copy) mapped here
-  float* hi;
-  float* lo;
-  uint32_t* flags;
-  uint32_t* counters;
-  uint32_t N, K, kc, w, rank, epoch;
-};
-
-__device__ __forceinline__ uint4 ld_peer16(const float* p) {
-  uint4 v;
-  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ uint32_t tf32_lo_bits(uint32_t xb) {
-  const float x = __uint_as_float(xb);
-  const float h = __uint_as_float(xb & 0xffffe000u);
-  return (__float_as_uint(x - h) + 0x1000u) & 0xffffe000u;
-}
-
-__global__ void __launch_bounds__(256) pull_split_kernel(const __grid_constant__ PullArgs a) {
-  const uint32_t c4 = a.kc / 4;
-  const size_t n4 = (size_t)a.N * c4;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  constexpr int U = 8;
-  for (uint32_t j = 1; j < a.w; j++) {
-    uint32_t s = a.rank + j;
-    if (s >= a.w) s -= a.w;
-    const float* src = a.src[s] + (size_t)s * a.kc;
-    float* hi = a.hi + (size_t)s * a.kc;
-    float* lo = a.lo + (size_t)s * a.kc;
-    for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
-      uint4 v[U];
-      size_t off[U];
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        const size_t i = i0 + u * stride;
-        const size_t r = i / c4;
-        off[u] = r * a.K + (i - r * c4) * 4;
-        if (i < n4) v[u] = ld_peer16(src + off[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        if (i0 + u * stride < n4) {
-          *reinterpret_cast<uint4*>(hi + off[u]) = v[u];
-          *reinterpret_cast<uint4*>(lo + off[u]) =
-              make_uint4(tf32_lo_bits(v[u].x), tf32_lo_bits(v[u].y), tf32_lo_bits(v[u].z), tf32_lo_bits(v[u].w));
-        }
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      if (atomicAdd(a.counters + s, 1u) == gridDim.x - 1) {
-        a.counters[s] = 0;             // ready for the next call (launches on this stream are ordered)
-        __threadfence();
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.flags + s), "r"(a.epoch) : "memory");
-      }
-    }
-  }
-}
-
-__global__ void set_flag_kernel(uint32_t* flag, uint32_t epoch) {
-  __threadfence_system();
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
-}
-
 int symm_reserve(vkp_ctx* ctx, vkp_comm_state* st, size_t bytes_one) {
   if (bytes_one <= st->symm_bytes) return VKP_OK;
   // collective growth (all ranks see the same shapes): quiesce, drop the old mappings, re-export
-  VKP_CUDA(cudaStreamSynchronize(ctx->stream));
-  VKP_CUDA(cudaStreamSynchronize(st->pull_stream));
   VKP_NCCL(g_nccl.AllReduce(st->barrier_word, st->barrier_word, 1, ncclFloat32, ncclSum, st->comm, ctx->stream));
   VKP_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int r = 0; r < st->nranks; r++) {
@@ -391,21 +294,7 @@ extern "C" int vkp_comm_matmul_allgather(vkp_ctx* ctx, uint32_t M, uint32_t N, u
   std::lock_guard<std::mutex> g(ctx->mu);
   void* bufs[3] = {(void*)A, (void*)B_shard, (void*)C};
   VKP_TRY(vkp_prepare_buffers(ctx, bufs, 3));
-  if (!st->pull_stream) {
-    int lo_p = 0, hi_p = 0;
-    VKP_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
-    VKP_CUDA(cudaStreamCreateWithPriority(&st->pull_stream, cudaStreamNonBlocking, hi_p));
-    if (const char* e = getenv("VKP_PULL_PARTS")) st->parts = atoi(e);
-    if (st->parts < 1) st->parts = 1;
-    if (st->parts > vkp_comm_state::MAX_PARTS) st->parts = vkp_comm_state::MAX_PARTS;
-    for (int i = 1; i < st->parts; i++) {
-      VKP_CUDA(cudaStreamCreateWithPriority(&st->part_stream[i], cudaStreamNonBlocking, hi_p));
-      VKP_CUDA(cudaEventCreateWithFlags(&st->part_ev[i], cudaEventDisableTiming));
-    }
-    VKP_CUDA(cudaEventCreate(&st->pull_t0));
-    VKP_CUDA(cudaEventCreate(&st->pull_t1));
-    VKP_CUDA(cudaEventCreateWithFlags(&st->ready_ev, cudaEventDisableTiming));
-    VKP_CUDA(cudaEventCreateWithFlags(&st->pull_done_ev, cudaEventDisableTiming));
+  if (!st->flags) {
     VKP_CUDA(cudaMalloc(&st->barrier_word, 256));
     VKP_CUDA(cudaMemsetAsync(st->barrier_word, 0, 256, ctx->stream));
     VKP_CUDA(cudaMalloc(&st->flags, sizeof(uint32_t) * 2 * VKP_MAX_RANKS));
@@ -423,64 +312,20 @@ extern "C" int vkp_comm_matmul_allgather(vkp_ctx* ctx, uint32_t M, uint32_t N, u
   st->calls++;
   st->epoch++;
 
-  // 1. stage the local operands (compute stream): A_lo, and B_shard^T (hi into the exported matrix)
+  // 1. stage the local operands: A_lo, and B_shard^T (hi into the exported matrix, lo beside it)
   VKP_TRY(vkp_tc_split_lo(ctx, ctx->stream, A, a_lo, mk));
   VKP_TRY(vkp_tc_transpose_split(ctx, ctx->stream, B_shard, kc, N, bt_hi + (size_t)rank * kc, bt_lo + (size_t)rank * kc, K));
   // barrier: every rank's shard is staged (and every rank is done with the copy used two calls ago)
   VKP_NCCL(g_nccl.AllReduce(st->barrier_word, st->barrier_word, 1, ncclFloat32, ncclSum, st->comm, ctx->stream));
-  VKP_CUDA(cudaEventRecord(st->ready_ev, ctx->stream));
 
-  // 2. pulls over NVLink on the copy engines, ring order, then the lo split and the flag of that range
-  VKP_CUDA(cudaStreamWaitEvent(st->pull_stream, st->ready_ev, 0));
-  VKP_CUDA(cudaEventRecord(st->pull_t0, st->pull_stream));
-  static const bool use_ce = getenv("VKP_PULL_CE") != nullptr;   // copy-engine pulls (first version; ~350 GB/s)
-  if (!use_ce && w > 1) {
-    PullArgs pa;
-    for (uint32_t r = 0; r < w; r++)
-      pa.src[r] = reinterpret_cast<const float*>(static_cast<const char*>(st->peer[r]) + copy_off);
-    pa.hi = bt_hi; pa.lo = bt_lo; pa.flags = st->flags; pa.counters = st->flags + VKP_MAX_RANKS;
-    pa.N = N; pa.K = K; pa.kc = kc; pa.w = w; pa.rank = rank; pa.epoch = st->epoch;
-    static const int pull_ctas_per_sm = getenv("VKP_PULL_CTAS") ? atoi(getenv("VKP_PULL_CTAS")) : 1;
-    pull_split_kernel<<<ctx->sms * pull_ctas_per_sm, 256, 0, st->pull_stream>>>(pa);
-    VKP_TRY(vkp_after_launch(ctx, "pull_split"));
-  }
-  const int parts = (N >= 64u * st->parts) ? st->parts : 1;
-  for (int i = 1; use_ce && i < parts; i++) VKP_CUDA(cudaStreamWaitEvent(st->part_stream[i], st->ready_ev, 0));
-  for (uint32_t j = 1; use_ce && j < w; j++) {
-    const uint32_t s = (rank + j) % w;
-    const float* src = reinterpret_cast<const float*>(static_cast<const char*>(st->peer[s]) + copy_off) + (size_t)s * kc;
-    float* dst = bt_hi + (size_t)s * kc;
-    for (int i = 0; i < parts; i++) {
-      const uint32_t r0 = (uint32_t)((uint64_t)N * i / parts), r1 = (uint32_t)((uint64_t)N * (i + 1) / parts);
-      cudaStream_t cs = i ? st->part_stream[i] : st->pull_stream;
-      VKP_CUDA(cudaMemcpy2DAsync(dst + (size_t)r0 * K, (size_t)K * 4, src + (size_t)r0 * K, (size_t)K * 4,
-                                 (size_t)kc * 4, r1 - r0, cudaMemcpyDeviceToDevice, cs));
-      if (i) {
-        VKP_CUDA(cudaEventRecord(st->part_ev[i], cs));
-        VKP_CUDA(cudaStreamWaitEvent(st->pull_stream, st->part_ev[i], 0));
-      }
-    }
-    VKP_TRY(vkp_tc_split_lo_2d(ctx, st->pull_stream, dst, bt_lo + (size_t)s * kc, N, kc, K));
-    set_flag_kernel<<<1, 1, 0, st->pull_stream>>>(st->flags + s, st->epoch);
-    VKP_TRY(vkp_after_launch(ctx, "set_flag"));
-  }
-  VKP_CUDA(cudaEventRecord(st->pull_t1, st->pull_stream));
-  VKP_CUDA(cudaEventRecord(st->pull_done_ev, st->pull_stream));
-
-  // 3. one GEMM over all ranges, starting with the local one
+  // 2. one kernel: GEMM over all K ranges + the NVLink pulls of the ranges it does not have yet
   vkp_tc_chunks ch{st->flags, st->epoch, 0, rank, w};
-  VKP_TRY(vkp_gemm_tc_chunked(ctx, M, N, K, A, a_lo, bt_hi, bt_lo, C, ch));
-  // later work on the compute stream may reuse the workspace: order it after the pull stream too
-  VKP_CUDA(cudaStreamWaitEvent(ctx->stream, st->pull_done_ev, 0));
+  vkp_tc_pull pl;
+  memset(&pl, 0, sizeof(pl));
+  for (uint32_t r = 0; r < w; r++)
+    pl.src[r] = reinterpret_cast<const float*>(static_cast<const char*>(st->peer[r]) + copy_off);
+  pl.hi = bt_hi; pl.lo = bt_lo; pl.counters = st->flags + VKP_MAX_RANKS;
+  pl.rows = N; pl.ld = K; pl.kc = kc;
+  VKP_TRY(vkp_gemm_tc_chunked(ctx, M, N, K, A, a_lo, bt_hi, bt_lo, C, ch, &pl));
   return vkp_finish_op(ctx, job);
-}
-
-/* diagnostics: device time of the last call's pull phase (first copy .. last flag); synchronises */
-extern "C" int vkp_comm_last_pull_ms(vkp_ctx* ctx, float* ms) {
-  VKP_CHECK(ctx && ctx->comm && ms, "vkp_comm_last_pull_ms: null argument");
-  VKP_CHECK(ctx->comm->pull_t1, "vkp_comm_last_pull_ms: no row-sharded matmul has run");
-  VKP_TRY(vkp_make_current(ctx));
-  VKP_CUDA(cudaEventSynchronize(ctx->comm->pull_t1));
-  VKP_CUDA(cudaEventElapsedTime(ms, ctx->comm->pull_t0, ctx->comm->pull_t1));
-  return VKP_OK;
 }

@@ -94,12 +94,23 @@ struct vkp_job {
 };
 
 // K ranges of a GEMM that become valid while the kernel runs (vkp_gemm_tc.cu, vkp_comm.cu)
+#define VKP_MAX_RANKS 16
 struct vkp_tc_chunks {
-  const uint32_t* flags;   // [n_chunks] device words; range c may be read once flags[c] == epoch
+  uint32_t* flags;         // [n_chunks] device words; range c may be read once flags[c] == epoch
   uint32_t epoch;
   uint32_t kb_per_chunk;   // filled in by the launcher
   uint32_t first;          // range that is valid from the start (no flag), walked first
   uint32_t n_chunks;       // <= 1: plain GEMM
+};
+// Where those ranges come from: the spare warps of the same GEMM kernel copy range s of the
+// K-major [rows, ld] matrix of B^T out of rank s's memory (mapped peer pointer) into the local
+// hi matrix, write its TF32 low part next to it, and the last CTA to finish a range raises its flag.
+struct vkp_tc_pull {
+  const float* src[VKP_MAX_RANKS];   // src[s]: rank s's hi matrix as mapped here (nullptr: nothing to pull)
+  float* hi;
+  float* lo;
+  uint32_t* counters;                // [n_chunks] arrival counters, zero between calls
+  uint32_t rows, ld, kc;             // N, K, K / n_chunks
 };
 
 struct vkp_timer {

@@ -99,6 +99,63 @@ __device__ __forceinline__ void chunk_wait(const uint32_t* flag, uint32_t epoch)
   asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy acquire -> TMA (async proxy) reads
 }
 
+__device__ __forceinline__ uint4 ld_peer16(const float* p) {   // peer memory over NVLink: never cached
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t tf32_lo_bits(uint32_t xb) {
+  const float h = __uint_as_float(xb & 0xffffe000u);            // what the tensor core reads of x
+  return (__float_as_uint(__uint_as_float(xb) - h) + 0x1000u) & 0xffffe000u;
+}
+
+// The communication half of the row-sharded matmul, run by the four warps that have nothing to
+// convert in the pre-split variant (tid 0..127 of every CTA): stream the peers' K ranges in ring
+// order (first+1, first+2, ...: at any time every owner serves one reader) with 16-byte loads from
+// the mapped peer pointers, 8 in flight per thread, store hi and lo locally, then count the CTA
+// in; the last one publishes the range to every producer warp (release / acquire on the flag).
+__device__ __forceinline__ void pull_ranges(const vkp_tc_pull& pl, const vkp_tc_chunks& ch, int tid) {
+  constexpr int U = 8, PT = 128;
+  const uint32_t c4 = pl.kc / 4;
+  const size_t n4 = (size_t)pl.rows * c4;
+  const size_t stride = (size_t)gridDim.x * PT;
+  for (uint32_t j = 1; j < ch.n_chunks; j++) {
+    uint32_t s = ch.first + j;
+    if (s >= ch.n_chunks) s -= ch.n_chunks;
+    const float* src = pl.src[s] + (size_t)s * pl.kc;
+    float* hi = pl.hi + (size_t)s * pl.kc;
+    float* lo = pl.lo + (size_t)s * pl.kc;
+    for (size_t i0 = blockIdx.x * (size_t)PT + tid; i0 < n4; i0 += stride * U) {
+      uint4 v[U];
+      size_t off[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + u * stride;
+        const size_t r = i / c4;
+        off[u] = r * pl.ld + (i - r * c4) * 4;
+        if (i < n4) v[u] = ld_peer16(src + off[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (i0 + u * stride < n4) {
+          *reinterpret_cast<uint4*>(hi + off[u]) = v[u];
+          *reinterpret_cast<uint4*>(lo + off[u]) =
+              make_uint4(tf32_lo_bits(v[u].x), tf32_lo_bits(v[u].y), tf32_lo_bits(v[u].z), tf32_lo_bits(v[u].w));
+        }
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");     // the four pulling warps of this CTA
+    if (tid == 0) {
+      __threadfence();
+      if (atomicAdd(pl.counters + s, 1u) == gridDim.x - 1) {
+        pl.counters[s] = 0;                            // ready for the next call (stream-ordered)
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ch.flags + s), "r"(ch.epoch) : "memory");
+      }
+    }
+  }
+}
+
 // K-major, swizzled rows of BK fp32 (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B), 8-row groups
 // 8*row bytes apart (SBO), version 1 (sm_100)
 template <int BK>
@@ -171,11 +228,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
                float* __restrict__ C, const float* __restrict__ bias, uint32_t M, uint32_t N, uint32_t K,
-               int accumulate, uint32_t splits, uint32_t kb_per_split, vkp_tc_chunks ch) {
+               int accumulate, uint32_t splits, uint32_t kb_per_split, vkp_tc_chunks ch,
+               const __grid_constant__ vkp_tc_pull pl) {
   // ch.n_chunks > 1 (row-sharded matmul, vkp_comm.cu): K is cut into n_chunks ranges that become
-  // valid one after the other while this kernel runs (peers' shards of B arriving over NVLink);
-  // the producer walks them starting at ch.first (the local shard) and, before the first load of
-  // another range, waits until ch.flags[range] == ch.epoch.
+  // valid one after the other while this kernel runs -- the peers' shards of B, fetched over NVLink
+  // by this kernel's own spare warps (pull_ranges); the producer walks them starting at ch.first
+  // (the local shard) and, before the first load of another range, waits until
+  // ch.flags[range] == ch.epoch.
   // splits > 1 (split-K for problems with fewer output tiles than SMs): work item = (tile, split),
   // C is then a [splits][M][N] partial buffer and bias / accumulate are applied by splitk_reduce.
   using cfg = Cfg<BN, BK>;
@@ -317,7 +376,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 8) {
     // ===================================== converters =======================================
-    if (PRESPLIT) goto teardown;          // the lo tiles arrive by TMA: nothing to convert
+    if (PRESPLIT) {                       // the lo tiles arrive by TMA: nothing to convert
+      if (ch.n_chunks > 1 && pl.hi) pull_ranges(pl, ch, threadIdx.x - 256);
+      goto teardown;
+    }
     const int ctid = threadIdx.x - 256;   // 0..127
     uint32_t stage = 0, phase = 0;
     for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -439,19 +501,6 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
   }
 }
 
-// lo[r, c] = tf32_lo(in[r, c]) for a [rows, cols] window of matrices with leading dimension ld
-// (cols % 4 == 0, 16-byte aligned rows)
-__global__ void __launch_bounds__(256) split_lo_2d_kernel(const float* __restrict__ in, float* __restrict__ lo,
-                                                          uint32_t rows, uint32_t cols, size_t ld) {
-  const uint32_t c4 = cols / 4;
-  const size_t n4 = (size_t)rows * c4;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = i / c4, c = (i - r * c4) * 4;
-    const float4 x = *reinterpret_cast<const float4*>(in + r * ld + c);
-    *reinterpret_cast<float4*>(lo + r * ld + c) = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
-  }
-}
-
 // lo[i] = tf32_lo(in[i]): the low part of the 3xTF32 split for an operand that is already K-major
 __global__ void __launch_bounds__(256) split_lo_kernel(const float4* __restrict__ in, float4* __restrict__ lo, size_t n4) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -495,7 +544,7 @@ int make_map(CUtensorMap* map, const float* ptr, uint32_t rows, uint32_t K, uint
 template <int BN, int BK>
 int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, const float* Alo, const float* Btlo, float* C,
               const float* bias, uint32_t M, uint32_t N, uint32_t K, int accumulate,
-              vkp_tc_chunks ch = vkp_tc_chunks{nullptr, 0, 0, 0, 1}) {
+              vkp_tc_chunks ch = vkp_tc_chunks{nullptr, 0, 0, 0, 1}, const vkp_tc_pull* pull = nullptr) {
   using cfg = Cfg<BN, BK>;
   const bool presplit = Alo != nullptr;
   CUtensorMap tmA, tmB, tmAlo, tmBlo;
@@ -526,10 +575,13 @@ int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, const float* Alo, c
     VKP_TRY(vkp_workspace(ctx, 0, (size_t)splits * M * N * sizeof(float), &ws));
     dst = static_cast<float*>(ws);
   }
+  vkp_tc_pull pl;
+  memset(&pl, 0, sizeof(pl));
+  if (pull) pl = *pull;
   const uint32_t work = tiles * splits;
   const unsigned grid = work < (uint32_t)ctx->sms ? work : (unsigned)ctx->sms;
   kernel<<<grid, NUM_THREADS, cfg::SMEM_BYTES, ctx->stream>>>(
-      tmA, tmB, tmAlo, tmBlo, dst, splits > 1 ? nullptr : bias, M, N, K, splits > 1 ? 0 : accumulate, splits, kb_per, ch);
+      tmA, tmB, tmAlo, tmBlo, dst, splits > 1 ? nullptr : bias, M, N, K, splits > 1 ? 0 : accumulate, splits, kb_per, ch, pl);
   VKP_TRY(vkp_after_launch(ctx, "gemm_tc(tcgen05 3xTF32)"));
   if (splits > 1) {
     const unsigned rgrid = vkp_grid_for(ctx, ((size_t)M * N + 3) / 4, 256, 8);
@@ -631,12 +683,6 @@ int vkp_tc_split_lo(vkp_ctx* ctx, cudaStream_t stream, const float* in, float* l
   return vkp_after_launch(ctx, "split_lo");
 }
 
-int vkp_tc_split_lo_2d(vkp_ctx* ctx, cudaStream_t stream, const float* in, float* lo, uint32_t rows, uint32_t cols,
-                       size_t ld) {
-  split_lo_2d_kernel<<<vkp_grid_for(ctx, (size_t)rows * cols / 4, 256, 4), 256, 0, stream>>>(in, lo, rows, cols, ld);
-  return vkp_after_launch(ctx, "split_lo_2d");
-}
-
 // in: [rows, cols] row-major  ->  hi[c * ldo + r] = in[r, c], lo[...] = its TF32 low part
 int vkp_tc_transpose_split(vkp_ctx* ctx, cudaStream_t stream, const float* in, uint32_t rows, uint32_t cols,
                            float* hi, float* lo, size_t ldo) {
@@ -646,9 +692,9 @@ int vkp_tc_transpose_split(vkp_ctx* ctx, cudaStream_t stream, const float* in, u
 }
 
 int vkp_gemm_tc_chunked(vkp_ctx* ctx, uint32_t M, uint32_t N, uint32_t K, const float* A, const float* Alo,
-                        const float* Bt, const float* Btlo, float* C, vkp_tc_chunks ch) {
+                        const float* Bt, const float* Btlo, float* C, vkp_tc_chunks ch, const vkp_tc_pull* pull) {
   VKP_CHECK(ch.n_chunks >= 1 && K % ch.n_chunks == 0 && (K / ch.n_chunks) % 32 == 0,
             "vkp_gemm_tc_chunked: K = %u does not split into %u ranges of whole k-blocks", K, ch.n_chunks);
-  if (N % 256 == 0 || N >= 1024) return launch_tc<256, 16>(ctx, A, Bt, Alo, Btlo, C, nullptr, M, N, K, 0, ch);
-  return launch_tc<128, 32>(ctx, A, Bt, Alo, Btlo, C, nullptr, M, N, K, 0, ch);
+  if (N % 256 == 0 || N >= 1024) return launch_tc<256, 16>(ctx, A, Bt, Alo, Btlo, C, nullptr, M, N, K, 0, ch, pull);
+  return launch_tc<128, 32>(ctx, A, Bt, Alo, Btlo, C, nullptr, M, N, K, 0, ch, pull);
 }
