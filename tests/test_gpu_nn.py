@@ -271,35 +271,65 @@ def test_fused_kernels_match_the_op_by_op_compositions(gpu, rs, monkeypatch):
     np.testing.assert_allclose(a[6], b[6], rtol=1e-6, atol=1e-9)
 
 
+def _mlp(gpu, d_in, hidden, classes):
+    opt = lambda: nn.Adam(gpu, lr=1e-2)
+    return nn.Sequence([nn.Dense(gpu, d_in, hidden, w_opt=opt(), b_opt=opt(), w_init=nn.HeNormal(gpu, d_in, seed=3)),
+                        nn.ReLU(),
+                        nn.Dense(gpu, hidden, classes, w_opt=opt(), b_opt=opt(), w_init=nn.HeNormal(gpu, hidden, seed=4)),
+                        nn.Softmax()], nn.CrossEntropyLoss())
+
+
+def _state(net):
+    out = []
+    for layer in (net.L[0], net.L[2]):
+        for p in (layer.w, layer.b):
+            out += [np.asarray(p.value).copy(), np.asarray(p.grad).copy(),
+                    np.asarray(p.opt_state.m).copy(), np.asarray(p.opt_state.v).copy()]
+    return out
+
+
 @pytest.mark.parametrize("dims", [(33, 20, 24, 5), (256, 128, 256, 16)])
-def test_sequence_step_fused_equals_op_by_op(gpu, rs, monkeypatch, dims):
-    """Sequence.train with the one-launch zero_grad / Adam+update, `grad += dy^T x` in the GEMM
-    epilogue and no input gradient for the first layer gives bit-identical parameters, moments and
-    loss to the reference's op-by-op order (nn/models.py:55-78, nn/parameters.py:81-95,
-    nn/optimizers.py:235-253), over several steps."""
-    import vulkpy_b200.nn.optimizers as O
+def test_sequence_step_one_launch_paths_equal_per_layer_calls(gpu, rs, dims):
+    """Sequence.train (one-launch zero_grad, one-launch Adam + `value += diff`, no input gradient for
+    the first layer) leaves bit-identical parameters, gradients, moments and loss to the same step
+    driven layer by layer through the public methods the reference's Sequence calls
+    (nn/models.py:37-78: layer.zero_grad(), layer.backward(dx) for EVERY layer, layer.update())."""
     B, d_in, hidden, classes = dims
     x = rs.normal(size=(B, d_in)).astype(F)
     y = np.eye(classes, dtype=F)[rs.integers(0, classes, B)]
+    a, b = _mlp(gpu, d_in, hidden, classes), _mlp(gpu, d_in, hidden, classes)
+    for _ in range(3):
+        _, la = a.train(vk.Array(gpu, data=x), vk.Array(gpu, data=y))
+        pred = b._forward(vk.Array(gpu, data=x))
+        lb = b.loss(pred, vk.Array(gpu, data=y))
+        for layer in b.L:
+            layer.zero_grad()
+        dx = b.loss.grad()
+        for layer in reversed(b.L):
+            dx = layer.backward(dx)
+        for layer in b.L:
+            layer.update()
+        np.testing.assert_array_equal(np.asarray(la), np.asarray(lb))
+    for k, (u, f) in enumerate(zip(_state(a), _state(b))):
+        np.testing.assert_array_equal(u, f, err_msg=f"state {k}")
+
+
+@pytest.mark.parametrize("dims", [(33, 20, 24), (512, 256, 128)])
+def test_dense_backward_epilogue_accumulate_equals_add_grad(gpu, rs, monkeypatch, dims):
+    """`grad += dy^T x` inside the GEMM epilogue == GEMM into a temporary followed by add_grad
+    (nn/layers.py:126-141, nn/parameters.py:69-79), bit for bit, also on a non-zero gradient."""
+    import vulkpy_b200.nn.optimizers as O
+    B, d_in, d_out = dims
+    x = rs.normal(size=(B, d_in)).astype(F)
+    dy = rs.normal(size=(B, d_out)).astype(F)
     res = {}
     for unfused in (True, False):
         monkeypatch.setattr(O, "UNFUSED", unfused)
-        opt = lambda: nn.Adam(gpu, lr=1e-2)
-        net = nn.Sequence([nn.Dense(gpu, d_in, hidden, w_opt=opt(), b_opt=opt(), w_init=nn.HeNormal(gpu, d_in, seed=3)),
-                           nn.ReLU(),
-                           nn.Dense(gpu, hidden, classes, w_opt=opt(), b_opt=opt(), w_init=nn.HeNormal(gpu, hidden, seed=4)),
-                           nn.Softmax()], nn.CrossEntropyLoss())
-        losses = []
-        for _ in range(3):
-            _, loss = net.train(vk.Array(gpu, data=x), vk.Array(gpu, data=y))
-            losses.append(np.asarray(loss).copy())
-        state = []
-        for layer in (net.L[0], net.L[2]):
-            for p in (layer.w, layer.b):
-                state += [np.asarray(p.value).copy(), np.asarray(p.grad).copy(),
-                          np.asarray(p.opt_state.m).copy(), np.asarray(p.opt_state.v).copy()]
-        res[unfused] = (losses, state)
-    for u, f in zip(res[True][0], res[False][0]):
+        layer = nn.Dense(gpu, d_in, d_out, w_init=nn.HeNormal(gpu, d_in, seed=9))
+        layer(vk.Array(gpu, data=x))
+        dxs = [np.asarray(layer.backward(vk.Array(gpu, data=dy))).copy() for _ in range(2)]   # second call accumulates
+        res[unfused] = dxs + [np.asarray(layer.w.grad).copy(), np.asarray(layer.b.grad).copy()]
+    for u, f in zip(res[True], res[False]):
         np.testing.assert_array_equal(u, f)
-    for k, (u, f) in enumerate(zip(res[True][1], res[False][1])):
-        np.testing.assert_array_equal(u, f, err_msg=f"state {k}")
+    want = 2 * (dy.astype(np.float64).T @ x.astype(np.float64))
+    np.testing.assert_allclose(res[False][2], want, rtol=1e-4, atol=1e-4)

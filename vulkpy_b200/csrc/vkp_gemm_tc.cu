@@ -480,25 +480,62 @@ __device__ __forceinline__ float tf32_lo(float x) {
 
 // out[c, r] = in[r, c]   (in: rows x cols); with lo != nullptr also lo[c, r] = tf32_lo(in[r, c])
 // (ldo = leading dimension of out / lo, >= rows: lets a K-range of a wider [N, K] matrix be filled)
+// 64 x 64 tiles through shared memory, 16-byte global accesses on both sides when the shape allows
+// (cols % 4 == 0 for the reads; rows % 4 == 0, ldo % 4 == 0 and 16-byte aligned bases for the
+// writes -- checked on the host, VEC = false is the scalar fallback).
+template <bool VEC>
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                         float* __restrict__ lo, uint32_t rows, uint32_t cols,
                                                         size_t ldo) {
-  __shared__ float tile[32][33];
-  const uint32_t bx = blockIdx.x * 32, by = blockIdx.y * 32;
-  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-  for (uint32_t j = ty; j < 32; j += 8) {
-    const uint32_t r = by + j, c = bx + tx;
-    tile[j][tx] = (r < rows && c < cols) ? in[(size_t)r * cols + c] : 0.f;
-  }
-  __syncthreads();
-  for (uint32_t j = ty; j < 32; j += 8) {
-    const uint32_t c = bx + j, r = by + tx;
-    if (c < cols && r < rows) {
-      const float x = tile[tx][j];
-      out[(size_t)c * ldo + r] = x;
-      if (lo) lo[(size_t)c * ldo + r] = tf32_lo(x);
+  __shared__ float tile[64][65];
+  const uint32_t bx = blockIdx.x * 64, by = blockIdx.y * 64;   // bx: first column, by: first row of the tile
+  const uint32_t t = threadIdx.x;
+  if (VEC) {
+    const uint32_t c4 = (t & 15) * 4, r0 = t >> 4;             // 16 float4 per tile row, 16 rows per pass
+#pragma unroll
+    for (uint32_t p = 0; p < 4; p++) {
+      const uint32_t r = r0 + 16 * p;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (by + r < rows && bx + c4 < cols) v = *reinterpret_cast<const float4*>(in + (size_t)(by + r) * cols + bx + c4);
+      tile[r][c4] = v.x; tile[r][c4 + 1] = v.y; tile[r][c4 + 2] = v.z; tile[r][c4 + 3] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t p = 0; p < 4; p++) {
+      const uint32_t c = r0 + 16 * p;                          // output row = input column
+      const uint32_t r4 = c4;                                  // 4 consecutive input rows = 16 output bytes
+      if (bx + c < cols && by + r4 < rows) {
+        const float4 v = make_float4(tile[r4][c], tile[r4 + 1][c], tile[r4 + 2][c], tile[r4 + 3][c]);
+        const size_t o = (size_t)(bx + c) * ldo + by + r4;
+        *reinterpret_cast<float4*>(out + o) = v;
+        if (lo) *reinterpret_cast<float4*>(lo + o) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+      }
+    }
+  } else {
+    const uint32_t tx = t & 63, ty = t >> 6;                   // 64 x 4
+    for (uint32_t j = ty; j < 64; j += 4) {
+      const uint32_t r = by + j, c = bx + tx;
+      tile[j][tx] = (r < rows && c < cols) ? in[(size_t)r * cols + c] : 0.f;
+    }
+    __syncthreads();
+    for (uint32_t j = ty; j < 64; j += 4) {
+      const uint32_t c = bx + j, r = by + tx;
+      if (c < cols && r < rows) {
+        const float x = tile[tx][j];
+        out[(size_t)c * ldo + r] = x;
+        if (lo) lo[(size_t)c * ldo + r] = tf32_lo(x);
+      }
     }
   }
+}
+
+static void launch_transpose(cudaStream_t stream, const float* in, float* out, float* lo, uint32_t rows, uint32_t cols,
+                             size_t ldo) {
+  dim3 g((cols + 63) / 64, (rows + 63) / 64);
+  const bool vec = cols % 4 == 0 && rows % 4 == 0 && ldo % 4 == 0 &&
+                   ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)lo)) & 15) == 0;
+  if (vec) transpose_kernel<true><<<g, 256, 0, stream>>>(in, out, lo, rows, cols, ldo);
+  else transpose_kernel<false><<<g, 256, 0, stream>>>(in, out, lo, rows, cols, ldo);
 }
 
 // lo[i] = tf32_lo(in[i]): the low part of the 3xTF32 split for an operand that is already K-major
@@ -642,8 +679,7 @@ int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, ui
       Alo = alo; Blo = blo;
     }
     if (transA) {   // A stored [K, M] -> [M, K]
-      dim3 g((M + 31) / 32, (K + 31) / 32);
-      transpose_kernel<<<g, 256, 0, ctx->stream>>>(A, w, alo, K, M, K);
+      launch_transpose(ctx->stream, A, w, alo, K, M, K);
       VKP_TRY(vkp_after_launch(ctx, "transpose(A)"));
       Ak = w;
       w += a_elems;
@@ -653,8 +689,7 @@ int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, ui
       VKP_TRY(vkp_after_launch(ctx, "split_lo(A)"));
     }
     if (!transB) {  // B stored [K, N] -> [N, K]
-      dim3 g((N + 31) / 32, (K + 31) / 32);
-      transpose_kernel<<<g, 256, 0, ctx->stream>>>(B, w, blo, K, N, K);
+      launch_transpose(ctx->stream, B, w, blo, K, N, K);
       VKP_TRY(vkp_after_launch(ctx, "transpose(B)"));
       Bk = w;
     } else if (presplit) {
@@ -686,8 +721,7 @@ int vkp_tc_split_lo(vkp_ctx* ctx, cudaStream_t stream, const float* in, float* l
 // in: [rows, cols] row-major  ->  hi[c * ldo + r] = in[r, c], lo[...] = its TF32 low part
 int vkp_tc_transpose_split(vkp_ctx* ctx, cudaStream_t stream, const float* in, uint32_t rows, uint32_t cols,
                            float* hi, float* lo, size_t ldo) {
-  dim3 g((cols + 31) / 32, (rows + 31) / 32);
-  transpose_kernel<<<g, 256, 0, stream>>>(in, hi, lo, rows, cols, ldo);
+  launch_transpose(stream, in, hi, lo, rows, cols, ldo);
   return vkp_after_launch(ctx, "transpose_split");
 }
 
