@@ -60,14 +60,18 @@ arg_rows_kernel(const float* __restrict__ a, float* __restrict__ pv, uint32_t* _
   if (((elem0_mod4 + (size_t)row * axis) & 3) == 0) {
     const uint32_t nv = (hi - lo) >> 2;
     const float4* rv = reinterpret_cast<const float4*>(r + lo);
-    for (uint32_t v = threadIdx.x; v < nv; v += 256) {
-      const float4 x = rv[v];
-      const uint32_t i = lo + (v << 2);
+    auto fold4 = [&](const float4 x, uint32_t i) {
       if (b.i == NONE) { b.v = x.x; b.i = i; } else take<MAX>(b, x.x, i);
       take<MAX>(b, x.y, i + 1);
       take<MAX>(b, x.z, i + 2);
       take<MAX>(b, x.w, i + 3);
+    };
+    uint32_t v = threadIdx.x;
+    for (; v + 768 < nv; v += 1024) {   // four independent 16-byte loads in flight
+      const float4 x0 = rv[v], x1 = rv[v + 256], x2 = rv[v + 512], x3 = rv[v + 768];
+      fold4(x0, lo + (v << 2)); fold4(x1, lo + ((v + 256) << 2)); fold4(x2, lo + ((v + 512) << 2)); fold4(x3, lo + ((v + 768) << 2));
     }
+    for (; v < nv; v += 256) fold4(rv[v], lo + (v << 2));
     for (uint32_t i = lo + (nv << 2) + threadIdx.x; i < hi; i += 256) {
       if (b.i == NONE) { b.v = r[i]; b.i = i; } else take<MAX>(b, r[i], i);
     }
@@ -119,29 +123,56 @@ arg_rows_small_kernel(const float* __restrict__ a, uint32_t* __restrict__ out, u
   out[row] = b.i;
 }
 
-// a [prev, axis, post], threads along post; blockIdx.y = segment, blockIdx.z = prev index
-template <bool MAX>
+// a [prev, axis, post], threads along post; blockIdx.y = segment, blockIdx.z = prev index.
+// VEC = 4: a thread owns four neighbouring columns (16-byte loads, post % 4 == 0, aligned base),
+// four rows in flight = 64 bytes per thread; VEC = 1 is the scalar form for any shape.
+template <bool MAX, int VEC>
 __global__ void __launch_bounds__(256)
 arg_cols_kernel(const float* __restrict__ a, float* __restrict__ pv, uint32_t* __restrict__ pi, uint32_t* __restrict__ out,
                 uint32_t axis, uint32_t post, uint32_t seg_len, uint32_t nseg) {
-  const uint32_t q = blockIdx.x * 256 + threadIdx.x;
+  const uint32_t q = (blockIdx.x * 256 + threadIdx.x) * VEC;
   if (q >= post) return;
   const uint32_t p = blockIdx.z, seg = blockIdx.y;
   const uint32_t lo = seg * seg_len, hi = min(axis, lo + seg_len);
   const float* col = a + (size_t)p * axis * post + q;
-  VI b{col[(size_t)lo * post], lo};
+  VI b[VEC];
+  auto load = [&](uint32_t i, float (&x)[VEC]) {
+    if constexpr (VEC == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(col + (size_t)i * post);
+      x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    } else {
+      x[0] = col[(size_t)i * post];
+    }
+  };
+  {
+    float x[VEC];
+    load(lo, x);
+#pragma unroll
+    for (int c = 0; c < VEC; c++) b[c] = VI{x[c], lo};
+  }
   uint32_t i = lo + 1;
   for (; i + 3 < hi; i += 4) {   // four independent loads in flight
-    const float x0 = col[(size_t)i * post], x1 = col[(size_t)(i + 1) * post];
-    const float x2 = col[(size_t)(i + 2) * post], x3 = col[(size_t)(i + 3) * post];
-    take<MAX>(b, x0, i); take<MAX>(b, x1, i + 1); take<MAX>(b, x2, i + 2); take<MAX>(b, x3, i + 3);
+    float x0[VEC], x1[VEC], x2[VEC], x3[VEC];
+    load(i, x0); load(i + 1, x1); load(i + 2, x2); load(i + 3, x3);
+#pragma unroll
+    for (int c = 0; c < VEC; c++) {
+      take<MAX>(b[c], x0[c], i); take<MAX>(b[c], x1[c], i + 1); take<MAX>(b[c], x2[c], i + 2); take<MAX>(b[c], x3[c], i + 3);
+    }
   }
-  for (; i < hi; i++) take<MAX>(b, col[(size_t)i * post], i);
-  if (nseg == 1) out[(size_t)p * post + q] = b.i;
-  else {
-    const size_t o = ((size_t)p * nseg + seg) * post + q;
-    pv[o] = b.v;
-    pi[o] = b.i;
+  for (; i < hi; i++) {
+    float x[VEC];
+    load(i, x);
+#pragma unroll
+    for (int c = 0; c < VEC; c++) take<MAX>(b[c], x[c], i);
+  }
+#pragma unroll
+  for (int c = 0; c < VEC; c++) {
+    if (nseg == 1) out[(size_t)p * post + q + c] = b[c].i;
+    else {
+      const size_t o = ((size_t)p * nseg + seg) * post + q + c;
+      pv[o] = b[c].v;
+      pi[o] = b[c].i;
+    }
   }
 }
 
@@ -158,6 +189,41 @@ arg_final_kernel(const float* __restrict__ pv, const uint32_t* __restrict__ pi, 
   VI b{pv[base], pi[base]};
   for (uint32_t s = 1; s < nseg; s++) take<MAX>(b, pv[base + (size_t)s * post], pi[base + (size_t)s * post]);
   out[t] = b.i;
+}
+
+// the same fold with one WARP per output, for many segments per output (a full reduction has 8 CTAs
+// per SM = 1184 partials for its single output: a lone thread would walk them for ~0.1 ms)
+template <bool MAX>
+__global__ void __launch_bounds__(256)
+arg_final_warp_kernel(const float* __restrict__ pv, const uint32_t* __restrict__ pi, uint32_t* __restrict__ out,
+                      uint64_t total, uint32_t post, uint32_t nseg) {
+  const uint64_t t = (blockIdx.x * (uint64_t)256 + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (t >= total) return;
+  const uint64_t p = t / post, q = t % post;
+  const size_t base = (size_t)p * nseg * post + q;
+  VI b{0.0f, NONE};
+  for (uint32_t s = lane; s < nseg; s += 32) {
+    const float v = pv[base + (size_t)s * post];
+    const uint32_t i = pi[base + (size_t)s * post];
+    if (b.i == NONE) { b.v = v; b.i = i; } else take<MAX>(b, v, i);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float v = __shfl_xor_sync(0xffffffffu, b.v, o);
+    const uint32_t i = __shfl_xor_sync(0xffffffffu, b.i, o);
+    if (i != NONE && (b.i == NONE || better<MAX>(v, i, b.v, b.i))) { b.v = v; b.i = i; }
+  }
+  if (lane == 0) out[t] = b.i;
+}
+
+template <bool MAX>
+void launch_arg_final(vkp_ctx* ctx, const float* pv, const uint32_t* pi, uint32_t* out, uint64_t outputs, uint32_t post,
+                      uint32_t nseg) {
+  if (nseg >= 64 && outputs <= (1u << 20))
+    arg_final_warp_kernel<MAX><<<(unsigned)((outputs * 32 + 255) / 256), 256, 0, ctx->stream>>>(pv, pi, out, outputs, post, nseg);
+  else
+    launch_arg_final<MAX>(ctx, pv, pi, out, outputs, post, nseg);
 }
 
 template <bool MAX>
@@ -193,12 +259,13 @@ int arg_launch(vkp_ctx* ctx, const float* in, uint32_t* out, uint32_t prev, uint
       VKP_TRY(vkp_after_launch(ctx, "arg_rows"));
     }
     if (nseg > 1) {
-      arg_final_kernel<MAX><<<(unsigned)((outputs + 255) / 256), 256, 0, ctx->stream>>>(pv, pi, out, outputs, 1, nseg);
+      launch_arg_final<MAX>(ctx, pv, pi, out, outputs, 1, nseg);
       VKP_TRY(vkp_after_launch(ctx, "arg_final"));
     }
     return VKP_OK;
   }
-  const uint32_t bx = (post + 255) / 256;
+  const bool vec = post % 4 == 0 && ((((uintptr_t)in) & 15) == 0) && post >= 1024;
+  const uint32_t bx = vec ? (post / 4 + 255) / 256 : (post + 255) / 256;
   uint32_t nseg = (uint32_t)std::min<uint64_t>((want_ctas + (uint64_t)bx * prev - 1) / ((uint64_t)bx * prev), (axis + 63) / 64);
   if (nseg < 1) nseg = 1;
   if (nseg > 65535) nseg = 65535;
@@ -214,13 +281,18 @@ int arg_launch(vkp_ctx* ctx, const float* in, uint32_t* out, uint32_t prev, uint
   }
   for (uint64_t p0 = 0; p0 < prev; p0 += 65535) {
     const uint32_t np = (uint32_t)std::min<uint64_t>(65535, prev - p0);
-    arg_cols_kernel<MAX><<<dim3(bx, nseg, np), 256, 0, ctx->stream>>>(
-        in + p0 * axis * post, pv ? pv + p0 * nseg * post : nullptr, pi ? pi + p0 * nseg * post : nullptr,
-        out + p0 * post, axis, post, seg_len, nseg);
+    if (vec)
+      arg_cols_kernel<MAX, 4><<<dim3(bx, nseg, np), 256, 0, ctx->stream>>>(
+          in + p0 * axis * post, pv ? pv + p0 * nseg * post : nullptr, pi ? pi + p0 * nseg * post : nullptr,
+          out + p0 * post, axis, post, seg_len, nseg);
+    else
+      arg_cols_kernel<MAX, 1><<<dim3(bx, nseg, np), 256, 0, ctx->stream>>>(
+          in + p0 * axis * post, pv ? pv + p0 * nseg * post : nullptr, pi ? pi + p0 * nseg * post : nullptr,
+          out + p0 * post, axis, post, seg_len, nseg);
     VKP_TRY(vkp_after_launch(ctx, "arg_cols"));
   }
   if (nseg > 1) {
-    arg_final_kernel<MAX><<<(unsigned)((outputs + 255) / 256), 256, 0, ctx->stream>>>(pv, pi, out, outputs, post, nseg);
+    launch_arg_final<MAX>(ctx, pv, pi, out, outputs, post, nseg);
     VKP_TRY(vkp_after_launch(ctx, "arg_final"));
   }
   return VKP_OK;

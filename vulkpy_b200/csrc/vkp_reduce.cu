@@ -293,12 +293,19 @@ int reduce_axis(vkp_ctx* ctx, const float* in, float* out, uint32_t prev, uint32
     reduce_cols<OP, 1><<<grid, block, 0, ctx->stream>>>(in, dst, prev, axis, post, nsplit, seg);
   VKP_TRY(vkp_after_launch(ctx, "reduce_cols"));
   if (nsplit > 1) {
-    // second pass over [prev, nsplit, post]; nsplit is small so it never splits again
-    const unsigned grid2 = (unsigned)base_jobs;
+    // second pass over [prev, nsplit, post]; nsplit is small so it never splits again.  With the
+    // first pass's wide tiles it would be a handful of CTAs whose threads walk nsplit / by rows
+    // one dependent load after the other (20 us for [256, 1024] on 4 CTAs); narrower tiles give
+    // more CTAs and more threads along the (short) axis.
+    uint32_t bx2 = bx;
+    while (bx2 > 8 && (uint64_t)prev * ((post + bx2 * (vec ? 4 : 1) - 1) / (bx2 * (vec ? 4 : 1))) < 2ull * ctx->sms) bx2 >>= 1;
+    const uint32_t ctile2 = bx2 * (vec ? 4 : 1);
+    const unsigned grid2 = (unsigned)((uint64_t)prev * ((post + ctile2 - 1) / ctile2));
+    dim3 block2(bx2, 256 / bx2);
     if (vec)
-      reduce_cols<OP, 4><<<grid2, block, 0, ctx->stream>>>(dst, out, prev, nsplit, post, 1, nsplit);
+      reduce_cols<OP, 4><<<grid2, block2, 0, ctx->stream>>>(dst, out, prev, nsplit, post, 1, nsplit);
     else
-      reduce_cols<OP, 1><<<grid2, block, 0, ctx->stream>>>(dst, out, prev, nsplit, post, 1, nsplit);
+      reduce_cols<OP, 1><<<grid2, block2, 0, ctx->stream>>>(dst, out, prev, nsplit, post, 1, nsplit);
     VKP_TRY(vkp_after_launch(ctx, "reduce_cols(pass2)"));
   }
   return VKP_OK;
