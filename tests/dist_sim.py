@@ -129,3 +129,19 @@ class GlooTransport:
 
     def new_array(self, shape):
         return NumpyLocal(np.zeros(shape, F))
+
+
+class GlooBucketTransport(GlooTransport):
+    """Same, plus the bucket entry point of the NCCL transport (``allreduce_many``): every tensor of
+    the bucket crosses in ONE collective, then ``x *= scale`` in float32 on each."""
+
+    def allreduce_many(self, arrs, op, scale=1.0):
+        flat = torch.from_numpy(np.concatenate([np.ascontiguousarray(a.a).reshape(-1) for a in arrs]))
+        td.all_reduce(flat, op=_TD[op])
+        self.calls.append(("allreduce_many", int(flat.numel()), len(arrs)))
+        off = 0
+        for a in arrs:
+            n = a.a.size
+            a.a = np.asarray(flat[off:off + n].numpy().reshape(a.a.shape) * F(scale), dtype=F)
+            off += n
+        return arrs

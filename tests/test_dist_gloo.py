@@ -191,6 +191,58 @@ def body_data_parallel(g, dist, sim):
     np.testing.assert_allclose(np.asarray(loss).reshape(-1)[0], (D * D).sum(axis=1).mean(), rtol=1e-5)
 
 
+def body_data_parallel_bucket(g, dist, sim):
+    """With a transport that offers `allreduce_many`, DataParallel sends gradients AND the loss as one
+    bucket (one collective per step) and gets the same step as the per-tensor path."""
+    g.t.__class__ = sim.GlooBucketTransport
+    body_data_parallel_checked(g, dist, sim, [("allreduce_many", 16, 2)])
+
+
+def body_data_parallel_checked(g, dist, sim, want_calls):
+    class P:
+        def __init__(self, v):
+            self.value, self.grad = sim.NumpyLocal(v), sim.NumpyLocal(np.zeros_like(v))
+
+    class Lin:
+        def __init__(self, w):
+            self.w = P(w)
+
+    class Net:
+        def __init__(self, w, lr):
+            self.L, self.lr = (Lin(w),), lr
+
+        def _forward(self, x):
+            self._x = x
+            return x @ sim.NumpyLocal(self.L[0].w.value.a.T)
+
+        def loss(self, pred, y):
+            self._d = pred - y
+            return ((self._d * self._d).sum(axis=1)).sum(axis=0) * (1.0 / pred.shape[0])
+
+        def _zero_grad(self):
+            self.L[0].w.grad = sim.NumpyLocal(np.zeros_like(self.L[0].w.value.a))
+
+        def _backward(self):
+            d = self._d.a * (2.0 / self._d.a.shape[0])
+            self.L[0].w.grad += sim.NumpyLocal(d.T @ self._x.a)
+
+        def _update(self):
+            self.L[0].w.value += self.L[0].w.grad * (-self.lr)
+
+    W = _full((3, 5), 10, -1, 1)
+    X, Y = _full((8, 5), 11, -1, 1), _full((8, 3), 12, -1, 1)
+    lo, hi = g.bounds(8)
+    net = Net(W.copy(), 0.1)
+    dp = dist.DataParallel(net, g)
+    g.t.calls.clear()
+    _, loss = dp.train(sim.NumpyLocal(X[lo:hi]), sim.NumpyLocal(Y[lo:hi]))
+    assert list(g.t.calls) == want_calls, g.t.calls
+    D = X @ W.T - Y
+    want_W = W - 0.1 * (2.0 / 8) * D.T @ X
+    np.testing.assert_allclose(net.L[0].w.value.a, want_W, rtol=1e-5)
+    np.testing.assert_allclose(np.asarray(loss).reshape(-1)[0], (D * D).sum(axis=1).mean(), rtol=1e-5)
+
+
 # ---- pytest entry points ----------------------------------------------------------------------------
 def test_shard_bounds():
     from vulkpy_b200.dist import shard_bounds
@@ -225,3 +277,7 @@ def test_matmul_and_gather_world2():
 
 def test_data_parallel_world2():
     run("body_data_parallel", 2)
+
+
+def test_data_parallel_bucket_world2():
+    run("body_data_parallel_bucket", 2)
