@@ -2,7 +2,7 @@
 # One gpurun call: GPU tests, smoke, bench and the ncu launch list.  Outputs under gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -q --maxfail=40 --timeout 600 > gpurun_out/pytest_gpu.log 2>&1
+timeout 400 python -m pytest tests -m gpu -q --maxfail=10 --timeout 120 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -40 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -5 gpurun_out/smoke.log

@@ -308,6 +308,10 @@ def test_mean(gpu):
 @pytest.mark.parametrize("shape,axis", [
     ((1000,), 0), ((37, 129), 0), ((37, 129), 1), ((5, 7, 9), 1), ((3, 2000), 1), ((2000, 3), 0),
     ((300, 5000), 0), ((300, 5000), 1), ((4, 100000), 1), ((16, 64, 32), 1), ((2, 70000, 4), 1), ((70000, 8), 0),
+    # TMA-staged column kernel (post >= 128, post % 4 == 0, axis >= 512): ragged last box / last column tile,
+    # several prev slabs, split axis with a second pass; and shapes just below its thresholds
+    ((515, 128), 0), ((3, 600, 132), 1), ((2, 1000, 260), 1), ((512, 256), 0), ((20000, 1024), 0), ((5, 530, 4, 64), 1),
+    ((70, 128), 0), ((511, 256), 0),
 ])
 @pytest.mark.parametrize("name", ["sum", "maximum", "minimum"])
 def test_axis_reduce_vs_oracle(gpu, rs, shape, axis, name):
@@ -324,6 +328,20 @@ def test_axis_reduce_vs_oracle(gpu, rs, shape, axis, name):
         np.testing.assert_array_equal(got, want)
     rb = np.asarray(getattr(A(gpu, x), name)(axis=axis, rebroadcast=True))
     np.testing.assert_array_equal(rb, np.broadcast_to(np.expand_dims(got, axis), shape))
+
+
+def test_axis_reduce_tma_path_signs_and_prod(gpu, rs):
+    """Rows that TMA zero-fills past the end of the axis (or that belong to the next split) must not
+    leak into max of negatives / min of positives / prod."""
+    x = rs.uniform(-2.0, -1.0, (3, 547, 260)).astype(F)
+    np.testing.assert_array_equal(np.asarray(A(gpu, x).maximum(axis=1)), x.max(axis=1))
+    np.testing.assert_array_equal(np.asarray(A(gpu, -x).minimum(axis=1)), (-x).min(axis=1))
+    y = rs.uniform(0.995, 1.005, (2, 700, 128)).astype(F)
+    np.testing.assert_allclose(np.asarray(A(gpu, y).prod(axis=1)), y.astype(np.float64).prod(axis=1), rtol=5e-5)
+    z = rs.uniform(-1, 1, (4000, 384)).astype(F)
+    np.testing.assert_allclose(np.asarray(A(gpu, z).sum(axis=0)), z.astype(np.float64).sum(axis=0), rtol=0,
+                               atol=4000 * 1.2e-7)
+    np.testing.assert_allclose(np.asarray(A(gpu, z).mean(axis=0)), z.astype(np.float64).mean(axis=0), rtol=0, atol=2e-7)
 
 
 @pytest.mark.parametrize("n", [1, 63, 64, 65, 4096, 4097, 100003, 3_000_001])

@@ -223,7 +223,7 @@ void launch_arg_final(vkp_ctx* ctx, const float* pv, const uint32_t* pi, uint32_
   if (nseg >= 64 && outputs <= (1u << 20))
     arg_final_warp_kernel<MAX><<<(unsigned)((outputs * 32 + 255) / 256), 256, 0, ctx->stream>>>(pv, pi, out, outputs, post, nseg);
   else
-    launch_arg_final<MAX>(ctx, pv, pi, out, outputs, post, nseg);
+    arg_final_kernel<MAX><<<(unsigned)((outputs + 255) / 256), 256, 0, ctx->stream>>>(pv, pi, out, outputs, post, nseg);
 }
 
 template <bool MAX>

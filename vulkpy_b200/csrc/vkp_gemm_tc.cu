@@ -732,3 +732,19 @@ int vkp_gemm_tc_chunked(vkp_ctx* ctx, uint32_t M, uint32_t N, uint32_t K, const 
   if (N % 256 == 0 || N >= 1024) return launch_tc<256, 16>(ctx, A, Bt, Alo, Btlo, C, nullptr, M, N, K, 0, ch, pull);
   return launch_tc<128, 32>(ctx, A, Bt, Alo, Btlo, C, nullptr, M, N, K, 0, ch, pull);
 }
+
+// 3-D tiled tensor map over a float32 [d2, d1, d0] array (d0 contiguous), no swizzle, zero fill out
+// of bounds: used by the TMA-staged strided-axis reduction (vkp_reduce.cu).
+int vkp_tma_map_3d(void* map_out, const float* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1) {
+  EncodeTiledFn enc = get_encode();
+  VKP_CHECK(enc, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {(cuuint64_t)d0 * 4, (cuuint64_t)d0 * d1 * 4};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(static_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VKP_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with %d", (int)r);
+  return VKP_OK;
+}

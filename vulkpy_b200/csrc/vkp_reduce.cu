@@ -9,15 +9,22 @@
 // SURVEY Q2).  Here an array viewed as [prev, axis, post] is reduced by one of two kernels:
 //   * post == 1  -> "row" kernels: lanes run along the contiguous axis with float4 loads;
 //                   short rows use a lane group per row, long rows a CTA per (row, split);
-//   * post  > 1  -> "column" kernel: threads run along `post` (coalesced, float4 when
-//                   post % 4 == 0), the axis is split over threadIdx.y and over CTAs.
+//   * post  > 1  -> "column" kernels: threads run along `post`, the axis is split over thread
+//                   groups and over CTAs.  Wide arrays (post >= 128, post % 4 == 0) take the
+//                   TMA-staged kernel: 32-row x 128-column boxes of the strided axis land in a
+//                   6-deep shared-memory ring (cp.async.bulk.tensor + mbarriers, one issuing
+//                   thread), all 256 threads only add out of shared memory; other shapes use
+//                   plain (float4 when post % 4 == 0) global loads.
 // When the output alone cannot fill 148 SMs the axis is split across CTAs; partials go to a
 // device workspace and a second launch of the same kernel folds them, in a fixed order
 // (deterministic, no atomics).  Accumulation is float32; the order differs from the
 // reference's serial k = 0..axis-1 order, the parity tolerance is stated in tests/.
 #include "vkp_common.cuh"
 
+#include <cuda.h>
 #include <cstdlib>
+
+int vkp_tma_map_3d(void* map_out, const float* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1);  // vkp_gemm_tc.cu
 
 int vkp_broadcast_copy_3d(vkp_ctx* ctx, const float* src, float* dst, uint32_t prev, uint32_t axis,
                           uint32_t post);  // vkp_broadcast.cu
@@ -198,6 +205,108 @@ reduce_cols(const float* __restrict__ in, float* __restrict__ out, uint32_t prev
   }
 }
 
+// ---- column kernel, TMA-staged: in [prev, axis, post] -> out [prev, nsplit, post] ------------
+// One CTA per (prev index, 128-column tile, axis split).  Thread 0 keeps CT_STAGES boxes of
+// CT_ROWS x CT_COLS floats in flight through a 3-D tensor map (dims post, axis, prev; rows of the
+// strided axis are post * 4 bytes apart in HBM, 512 contiguous bytes each inside a box); a box
+// row past `axis` is zero-filled by TMA and a row past the CTA's segment belongs to the next
+// split, so consumers bound the rows they add by k1, never by the box.  Thread (tx, ty) owns
+// columns 4 tx .. 4 tx + 3 and rows ty, ty + 8, ...; the 8 row groups are folded in order.
+constexpr int CT_ROWS = 32, CT_COLS = 128, CT_STAGES = 6;
+constexpr int CT_STAGE_BYTES = CT_ROWS * CT_COLS * 4;
+constexpr int CT_SMEM = CT_STAGES * CT_STAGE_BYTES + 128 /*align*/ + 64 /*barriers*/;
+
+__device__ __forceinline__ uint32_t ct_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ct_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; spin++) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();   // a protocol bug must fail the launch, not hang the GPU
+  }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256)
+reduce_cols_tma(const __grid_constant__ CUtensorMap tm, float* __restrict__ out, uint32_t prev, uint32_t axis,
+                uint32_t post, uint32_t nsplit, uint32_t seg) {
+  extern __shared__ uint8_t ct_raw[];
+  uint8_t* smem = ct_raw + ((128 - (ct_smem_u32(ct_raw) & 127)) & 127);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + CT_STAGES * CT_STAGE_BYTES);
+  const uint32_t ntile = (post + CT_COLS - 1) / CT_COLS;
+  const uint32_t job = blockIdx.x;
+  const uint32_t tile = job % ntile;
+  const uint32_t rest = job / ntile;
+  const uint32_t split = rest % nsplit;
+  const uint32_t pi = rest / nsplit;
+  const uint32_t k0 = split * seg;
+  const uint32_t k1 = (k0 + seg < axis) ? k0 + seg : axis;
+  const uint32_t nbox = (k1 - k0 + CT_ROWS - 1) / CT_ROWS;
+  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm) : "memory");
+    for (int s = 0; s < CT_STAGES; s++)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ct_smem_u32(&full[s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](uint32_t b) {   // box b of this CTA into slot b % CT_STAGES (thread 0 only)
+    const uint32_t slot = b % CT_STAGES;
+    const uint32_t bar = ct_smem_u32(&full[slot]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)CT_STAGE_BYTES) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(ct_smem_u32(smem + slot * CT_STAGE_BYTES)), "l"(&tm), "r"(bar), "r"((int)(tile * CT_COLS)),
+          "r"((int)(k0 + b * CT_ROWS)), "r"((int)pi)
+        : "memory");
+  };
+  if (threadIdx.x == 0)
+    for (uint32_t b = 0; b < nbox && b < CT_STAGES; b++) issue(b);
+
+  float acc[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) acc[c] = Red<OP>::id();
+  for (uint32_t b = 0; b < nbox; b++) {
+    const uint32_t slot = b % CT_STAGES;
+    ct_mbar_wait(ct_smem_u32(&full[slot]), (b / CT_STAGES) & 1);
+    const float* st = reinterpret_cast<const float*>(smem + slot * CT_STAGE_BYTES);
+    const uint32_t rows_here = min((uint32_t)CT_ROWS, k1 - (k0 + b * CT_ROWS));
+#pragma unroll
+    for (uint32_t r = 0; r < CT_ROWS / 8; r++) {
+      const uint32_t row = ty + 8 * r;
+      if (row < rows_here) {
+        const float4 x = *reinterpret_cast<const float4*>(st + row * CT_COLS + tx * 4);
+        acc[0] = Red<OP>::op(acc[0], x.x);
+        acc[1] = Red<OP>::op(acc[1], x.y);
+        acc[2] = Red<OP>::op(acc[2], x.z);
+        acc[3] = Red<OP>::op(acc[3], x.w);
+      }
+    }
+    __syncthreads();                                   // every thread is done with this slot
+    if (threadIdx.x == 0 && b + CT_STAGES < nbox) issue(b + CT_STAGES);
+  }
+  // fold the 8 row groups in order through shared memory (slot 0 is free: all boxes consumed)
+  float* fold = reinterpret_cast<float*>(smem);
+#pragma unroll
+  for (int c = 0; c < 4; c++) fold[(ty * 32 + tx) * 4 + c] = acc[c];
+  __syncthreads();
+  const uint32_t col = tile * CT_COLS + tx * 4;
+  if (ty == 0 && col < post) {
+    float r[4] = {acc[0], acc[1], acc[2], acc[3]};
+    for (uint32_t y = 1; y < 8; y++) {
+#pragma unroll
+      for (int c = 0; c < 4; c++) r[c] = Red<OP>::op(r[c], fold[(y * 32 + tx) * 4 + c]);
+    }
+    *reinterpret_cast<float4*>(out + ((uint64_t)pi * nsplit + split) * post + col) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
 // ---- literal sum.comp semantics for sizeB > 1: out[i] = reduce_{j = i, i+sizeB, ...} a[j] -----
 template <int OP>
 __global__ void reduce_strided(const float* __restrict__ in, float* __restrict__ out, uint32_t sizeA,
@@ -256,6 +365,49 @@ int reduce_axis(vkp_ctx* ctx, const float* in, float* out, uint32_t prev, uint32
   if ((uint64_t)prev * post == 0) return VKP_OK;
   if (post == 1) return reduce_rows<OP>(ctx, in, out, prev, axis);
   const bool vec = (post % 4 == 0) && ((((uintptr_t)in) & 15) == 0) && ((((uintptr_t)out) & 15) == 0);
+  // TMA-staged kernel for wide arrays (VKP_REDUCE_TMA=0 keeps the plain-load kernel everywhere)
+  static const bool tma_on = !(getenv("VKP_REDUCE_TMA") && getenv("VKP_REDUCE_TMA")[0] == '0');
+  if (tma_on && vec && post >= CT_COLS && axis >= 16 * CT_ROWS) {   // short axes: too few boxes per CTA to pipeline (measured: 4.5 vs 6.7 TB/s at axis = 64)
+    const uint32_t ntile = (post + CT_COLS - 1) / CT_COLS;
+    const uint64_t base_jobs = (uint64_t)prev * ntile;
+    const uint64_t target_ctas = (uint64_t)ctx->sms * 16;
+    uint32_t nsplit = 1;
+    if (base_jobs < target_ctas) {
+      uint64_t want = target_ctas / base_jobs;          // floor: at most 8 full waves of 2 CTAs per SM
+      const uint64_t max_split = (axis + 4 * CT_ROWS - 1) / (4 * CT_ROWS);   // >= 4 boxes per CTA
+      if (want > max_split) want = max_split;
+      nsplit = (uint32_t)(want < 1 ? 1 : want);
+    }
+    uint32_t seg = (axis + nsplit - 1) / nsplit;
+    seg = (seg + CT_ROWS - 1) / CT_ROWS * CT_ROWS;      // whole boxes: no box is fetched by two CTAs
+    nsplit = (axis + seg - 1) / seg;
+    const uint64_t jobs = base_jobs * nsplit;
+    if (jobs < (1ull << 31)) {
+      CUtensorMap tm;
+      VKP_TRY(vkp_tma_map_3d(&tm, in, post, axis, prev, CT_COLS, CT_ROWS));
+      float* dst = out;
+      if (nsplit > 1) {
+        void* ws;
+        VKP_TRY(vkp_workspace(ctx, 0, (uint64_t)prev * nsplit * post * sizeof(float), &ws));
+        dst = (float*)ws;
+      }
+      static bool attr_set[4] = {false, false, false, false};
+      if (!attr_set[OP]) {
+        VKP_CUDA(cudaFuncSetAttribute(reduce_cols_tma<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
+        attr_set[OP] = true;
+      }
+      reduce_cols_tma<OP><<<(unsigned)jobs, 256, CT_SMEM, ctx->stream>>>(tm, dst, prev, axis, post, nsplit, seg);
+      VKP_TRY(vkp_after_launch(ctx, "reduce_cols_tma"));
+      if (nsplit > 1) {   // fold the split partials [prev, nsplit, post] with the plain-load kernel
+        uint32_t bx2 = 64;
+        while (bx2 > 8 && (uint64_t)prev * ((post + bx2 * 4 - 1) / (bx2 * 4)) < 2ull * ctx->sms) bx2 >>= 1;
+        const unsigned grid2 = (unsigned)((uint64_t)prev * ((post + bx2 * 4 - 1) / (bx2 * 4)));
+        reduce_cols<OP, 4><<<grid2, dim3(bx2, 256 / bx2), 0, ctx->stream>>>(dst, out, prev, nsplit, post, 1, nsplit);
+        VKP_TRY(vkp_after_launch(ctx, "reduce_cols(pass2)"));
+      }
+      return VKP_OK;
+    }
+  }
   const uint32_t cols = vec ? post / 4 : post;
   // threads along `post`: up to VKP_COLS_BX (default 128) lanes wide so that a CTA row is a long
   // contiguous run (2 KiB with float4), the rest of the 256 threads split the axis
