@@ -11,8 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("script,args", [("00_arithmetic.py", ["--n", "1024"]), ("01_random.py", []),
-                                         ("02_nn_iris.py", ["--nepoch", "30"]),
-                                         ("02_nn_iris.py", ["--nepoch", "30", "--optimizer", "sgd"])])
+                                         ("02_nn_iris.py", ["--nepoch", "60"]),
+                                         ("02_nn_iris.py", ["--nepoch", "60", "--optimizer", "sgd"])])
 def test_example_runs(script, args):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "examples", script), *args], capture_output=True, text=True,
                        timeout=300)
