@@ -46,7 +46,7 @@ for epoch in range(args.nepoch):
     for lo in range(0, len(train) - args.batch + 1, args.batch):
         idx = vk.U32Array(gpu, data=np.arange(lo, lo + args.batch, dtype=np.uint32))
         _, loss = net.train(xs.gather(idx, axis=0), ys.gather(idx, axis=0))
-        total += float(np.asarray(loss)[0])
+        total += float(np.asarray(loss).reshape(-1)[0])    # reduce="mean" leaves a 0-d array, as in the reference
     if epoch % max(1, args.nepoch // 5) == 0 or epoch == args.nepoch - 1:
         pred = np.asarray(net.predict(Xt).argmax(axis=1))
         print(f"epoch {epoch:4d}  train loss {total / (len(train) // args.batch):.4f}  test accuracy {(pred == y_all[test]).mean():.3f}")
