@@ -138,3 +138,28 @@ def test_tc_gemm_presplit_path(gpu, rs, ta, tb):
     c0 = rs.normal(size=(M, N)).astype(F)
     got = gemm(gpu, a, b, ta, tb, bias=bias, flags=TC | ACC, c0=c0)
     assert (np.abs(got - (want + bias + c0)) / (mag + 2)).max() < TOL
+
+
+@pytest.mark.parametrize("case", ["n16", "n10", "m16", "m7", "k16", "k5"])
+def test_skinny_gemm_kernels(gpu, rs, case):
+    """The three streaming kernels behind nn.Dense with few classes (forward N <= 16, weight gradient
+    M <= 16, input gradient K <= 16; vkp_gemm.cu): float32 FMA accumulation, bound 2e-6 * |A||B|, with
+    bias / accumulate where the callers use them."""
+    if case[0] == "n":      # Y = X W^T + b   (batch_affine.comp:25-39)
+        N = int(case[1:]); M, K, ta, tb = 2048, 1024, False, True
+    elif case[0] == "m":    # dW = dy^T x     (nn/layers.py:126-141 as one contraction)
+        M = int(case[1:]); N, K, ta, tb = 1024, 4096, True, False
+    else:                   # dx = dy W
+        K = int(case[1:]); M, N, ta, tb = 2048, 1024, False, False
+    a = rs.uniform(-1, 1, (K, M) if ta else (M, K)).astype(F)
+    b = rs.uniform(-1, 1, (N, K) if tb else (K, N)).astype(F)
+    want, mag = exact(a, b, ta, tb)
+    got = gemm(gpu, a, b, ta, tb)
+    assert (np.abs(got - want) / (mag + 1e-30)).max() < 2e-6
+    c0 = rs.normal(size=(M, N)).astype(F)
+    bias = rs.normal(size=N).astype(F) if case[0] != "k" else None
+    got = gemm(gpu, a, b, ta, tb, bias=bias, flags=ACC, c0=c0)
+    ref = want + c0 + (bias if bias is not None else 0)
+    assert (np.abs(got - ref) / (mag + 2)).max() < 2e-6
+    simt = gemm(gpu, a, b, ta, tb, flags=SIMT)
+    assert (np.abs(got - (simt + c0 + (bias if bias is not None else 0))) / (mag + 2)).max() < 2e-6

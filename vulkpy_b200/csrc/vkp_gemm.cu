@@ -12,6 +12,9 @@
 //     when the shape is tile-aligned.
 #include "vkp_common.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 int vkp_gemm_tc_supported(int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
                           const float* B, float* C, int forced);
 int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
@@ -109,6 +112,177 @@ simt_splitk_reduce(const float* __restrict__ part, float* __restrict__ C, const 
   }
 }
 
+// ---- skinny shapes of nn.Dense with few classes (config 5: 1024 -> 16) -------------------------
+// The 64x64-tile kernel above wastes 3/4 of its tile on a 16-wide operand and the tensor-core
+// kernel needs >= 128 on both sides; these three contractions are bandwidth problems (one pass
+// over a [batch, 1024] matrix) and get one streaming kernel each
+// (profiles/r01_launches_mlp_step_v2.md: 62 + 49 + 17 us of a 494 us step before).
+
+// forward:  C[M, N] (+)= A[M, K] B[N, K]^T + bias[N],  N <= 32, K % 4 == 0, B (N*K floats) in shared memory.
+// One warp per row of A at a time: lane l owns k = 4l, 4l+1, .. (float4, stride 128), N accumulators
+// per lane, butterfly-reduced; lane n writes C[m, n].
+template <int NMAX>
+__global__ void __launch_bounds__(256)
+gemm_skinny_n_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                     const float* __restrict__ bias, uint32_t M, uint32_t N, uint32_t K, int accumulate) {
+  extern __shared__ float4 sk_b[];                  // [N][K/4]
+  const uint32_t k4 = K / 4;
+  for (uint32_t i = threadIdx.x; i < N * k4; i += 256) sk_b[i] = reinterpret_cast<const float4*>(B)[i];
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t warps = gridDim.x * 8;
+  for (uint32_t m = blockIdx.x * 8 + warp; m < M; m += warps) {
+    const float4* a = reinterpret_cast<const float4*>(A + (size_t)m * K);
+    float acc[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; n++) acc[n] = 0.f;
+    for (uint32_t j = lane; j < k4; j += 32) {
+      const float4 x = a[j];
+#pragma unroll
+      for (int n = 0; n < NMAX; n++) {
+        if (n < (int)N) {
+          const float4 w = sk_b[n * k4 + j];
+          acc[n] = fmaf(x.x, w.x, acc[n]);
+          acc[n] = fmaf(x.y, w.y, acc[n]);
+          acc[n] = fmaf(x.z, w.z, acc[n]);
+          acc[n] = fmaf(x.w, w.w, acc[n]);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NMAX; n++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+    }
+    // every lane now holds all N sums; lane n stores column n
+    float v = 0.f;
+#pragma unroll
+    for (int n = 0; n < NMAX; n++)
+      if ((int)lane == n) v = acc[n];
+    if (lane < N) {
+      if (bias) v += bias[lane];
+      float* c = C + (size_t)m * N + lane;
+      *c = accumulate ? (*c + v) : v;
+    }
+  }
+}
+
+// weight gradient:  part[split][M, N] = sum_{k in split} A[k, M]^T B[k, N],  M <= 16, N % 4 == 0.
+// Thread = 4 neighbouring columns of B x all M rows of the result (M x 4 accumulators); the K range
+// is cut over blockIdx.y; simt_splitk_reduce folds the partials (fixed order) and applies
+// bias / accumulate.
+template <int MMAX>
+__global__ void __launch_bounds__(256)
+gemm_skinny_m_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ part,
+                     uint32_t M, uint32_t N, uint32_t K, uint32_t k_per_split) {
+  const uint32_t n4 = blockIdx.x * 256 + threadIdx.x;          // float4 column index
+  const uint32_t k0 = blockIdx.y * k_per_split;
+  const uint32_t k1 = (k0 + k_per_split < K) ? k0 + k_per_split : K;
+  if (n4 * 4 >= N) return;
+  float4 acc[MMAX];
+#pragma unroll
+  for (int m = 0; m < MMAX; m++) acc[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (uint32_t k = k0; k < k1; k++) {
+    const float4 b = *reinterpret_cast<const float4*>(B + (size_t)k * N + n4 * 4);
+    const float* a = A + (size_t)k * M;                          // same address for the whole warp: broadcast
+#pragma unroll
+    for (int m = 0; m < MMAX; m++) {
+      if (m < (int)M) {
+        const float am = __ldg(a + m);
+        acc[m].x = fmaf(am, b.x, acc[m].x);
+        acc[m].y = fmaf(am, b.y, acc[m].y);
+        acc[m].z = fmaf(am, b.z, acc[m].z);
+        acc[m].w = fmaf(am, b.w, acc[m].w);
+      }
+    }
+  }
+  float* out = part + (size_t)blockIdx.y * M * N;
+#pragma unroll
+  for (int m = 0; m < MMAX; m++)
+    if (m < (int)M) *reinterpret_cast<float4*>(out + (size_t)m * N + n4 * 4) = acc[m];
+}
+
+// input gradient:  C[M, N] (+)= A[M, K] B[K, N],  K <= 16, N % 4 == 0.  Thread = 4 neighbouring
+// columns; its K x 4 slice of B stays in registers while it walks the rows of A.
+template <int KMAX>
+__global__ void __launch_bounds__(256)
+gemm_skinny_k_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
+                     uint32_t M, uint32_t N, uint32_t K, int accumulate, uint32_t rows_per_block) {
+  const uint32_t n4 = blockIdx.x * 256 + threadIdx.x;
+  if (n4 * 4 >= N) return;
+  float4 b[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; k++)
+    b[k] = (k < (int)K) ? *reinterpret_cast<const float4*>(B + (size_t)k * N + n4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint32_t m0 = blockIdx.y * rows_per_block;
+  const uint32_t m1 = (m0 + rows_per_block < M) ? m0 + rows_per_block : M;
+  for (uint32_t m = m0; m < m1; m++) {
+    const float* a = A + (size_t)m * K;                          // warp-uniform address: broadcast
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) {
+      if (k < (int)K) {
+        const float ak = __ldg(a + k);
+        acc.x = fmaf(ak, b[k].x, acc.x);
+        acc.y = fmaf(ak, b[k].y, acc.y);
+        acc.z = fmaf(ak, b[k].z, acc.z);
+        acc.w = fmaf(ak, b[k].w, acc.w);
+      }
+    }
+    float4* c = reinterpret_cast<float4*>(C + (size_t)m * N + n4 * 4);
+    if (accumulate) {
+      const float4 o = *c;
+      acc.x = o.x + acc.x; acc.y = o.y + acc.y; acc.z = o.z + acc.z; acc.w = o.w + acc.w;
+    }
+    *c = acc;
+  }
+}
+
+// returns 1 and launches when one of the skinny kernels takes the problem, 0 otherwise, < 0 on error
+int gemm_skinny(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
+                const float* B, float* C, const float* bias, int accumulate) {
+  static const bool off = getenv("VKP_DISABLE_SKINNY") != nullptr;
+  if (off) return 0;
+  const bool aligned = ((((uintptr_t)A) | ((uintptr_t)B) | ((uintptr_t)C)) & 15) == 0;
+  if (!aligned || (uint64_t)M * N * K < (1ull << 22)) return 0;       // small problems keep the tiled kernel
+  if (!transA && transB && N <= 16 && K % 4 == 0 && K >= 128 && M >= 1024 && (size_t)N * K * 4 <= 96 * 1024) {
+    const size_t smem = (size_t)N * K * 4;
+    static bool attr = false;
+    if (!attr) {
+      if (cudaFuncSetAttribute(gemm_skinny_n_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)
+        return vkp_set_error("gemm_skinny: cannot raise the shared-memory limit") ? -1 : -1;
+      attr = true;
+    }
+    const unsigned grid = (unsigned)std::min<uint64_t>((M + 7) / 8, (uint64_t)ctx->sms * 2);
+    gemm_skinny_n_kernel<16><<<grid, 256, smem, ctx->stream>>>(A, B, C, bias, M, N, K, accumulate);
+    return vkp_after_launch(ctx, "gemm_skinny_n") == VKP_OK ? 1 : -1;
+  }
+  if (transA && !transB && M <= 16 && N % 4 == 0 && N >= 256 && K >= 1024) {
+    const uint32_t nblk = (N / 4 + 255) / 256;
+    uint32_t splits = (uint32_t)std::max<uint64_t>(1, (uint64_t)ctx->sms * 2 / nblk);
+    if (splits > K / 16) splits = K / 16;
+    uint32_t k_per = (K + splits - 1) / splits;
+    splits = (K + k_per - 1) / k_per;
+    void* ws;
+    if (vkp_workspace(ctx, 0, (size_t)splits * M * N * sizeof(float), &ws) != VKP_OK) return -1;
+    float* part = static_cast<float*>(ws);
+    gemm_skinny_m_kernel<16><<<dim3(nblk, splits), 256, 0, ctx->stream>>>(A, B, part, M, N, K, k_per);
+    if (vkp_after_launch(ctx, "gemm_skinny_m") != VKP_OK) return -1;
+    simt_splitk_reduce<<<vkp_grid_for(ctx, (size_t)M * N, 256, 8), 256, 0, ctx->stream>>>(part, C, bias, M, N, splits, accumulate);
+    return vkp_after_launch(ctx, "gemm_skinny_m_reduce") == VKP_OK ? 1 : -1;
+  }
+  if (!transA && !transB && K <= 16 && N % 4 == 0 && N >= 256 && M >= 1024 && !bias) {
+    const uint32_t nblk = (N / 4 + 255) / 256;
+    uint32_t yb = (uint32_t)std::max<uint64_t>(1, (uint64_t)ctx->sms * 4 / nblk);
+    uint32_t rows_per = (M + yb - 1) / yb;
+    if (rows_per < 8) rows_per = 8;
+    yb = (M + rows_per - 1) / rows_per;
+    gemm_skinny_k_kernel<16><<<dim3(nblk, yb), 256, 0, ctx->stream>>>(A, B, C, M, N, K, accumulate, rows_per);
+    return vkp_after_launch(ctx, "gemm_skinny_k") == VKP_OK ? 1 : -1;
+  }
+  return 0;
+}
+
 int gemm_simt(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
               const float* B, float* C, const float* bias, int accumulate) {
   dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, 1);
@@ -158,6 +332,11 @@ int vkp_launch_gemm(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N
   const bool tc_ok = !force_simt && vkp_gemm_tc_supported(transA, transB, M, N, K, A, B, C, force_tc);
   VKP_CHECK(!(force_tc && !tc_ok), "vkp_gemm: tensor-core path forced but the shape (%u,%u,%u) is not supported", M, N, K);
   if (tc_ok) return vkp_gemm_tc(ctx, transA, transB, M, N, K, A, B, C, bias, accumulate);
+  if (!force_simt) {
+    const int r = gemm_skinny(ctx, transA, transB, M, N, K, A, B, C, bias, accumulate);
+    if (r < 0) return VKP_ERR;
+    if (r > 0) return VKP_OK;
+  }
   return gemm_simt(ctx, transA, transB, M, N, K, A, B, C, bias, accumulate);
 }
 
