@@ -145,3 +145,26 @@ class GlooBucketTransport(GlooTransport):
             a.a = np.asarray(flat[off:off + n].numpy().reshape(a.a.shape) * F(scale), dtype=F)
             off += n
         return arrs
+
+
+
+class GlooPullTransport(GlooTransport):
+    """Stand-in for ``NcclTransport.matmul_allgather``: the row-sharded matmul as the device kernel
+    does it -- start on the local K range, then walk the peers' ranges in ring order
+    (rank+1, rank+2, ...), accumulating in that order.  Shapes it "does not take" (fewer than
+    ``min_rows`` local rows) return ``None`` so that the caller's all-gather fallback is exercised."""
+    min_rows = 4
+
+    def matmul_allgather(self, a, b_shard, n_cols):
+        M, K = a.a.shape
+        kc = K // self.world
+        if K % self.world or b_shard.a.shape[0] != kc or M < self.min_rows:
+            return None
+        parts = [torch.empty_like(torch.from_numpy(b_shard.a)) for _ in range(self.world)]
+        td.all_gather(parts, torch.from_numpy(np.ascontiguousarray(b_shard.a)))     # the "peer memory"
+        self.calls.append(("pull", b_shard.a.size * (self.world - 1)))
+        acc = np.zeros((M, n_cols), F)
+        for j in range(self.world):
+            s = (self.rank + j) % self.world
+            acc = acc + a.a[:, s * kc:(s + 1) * kc] @ parts[s].numpy()
+        return NumpyLocal(acc)

@@ -145,6 +145,27 @@ def body_matmul(g, dist, sim):
     np.testing.assert_allclose(out.to_numpy(), A_f.reshape(-1)[idx])
 
 
+def body_matmul_pull(g, dist, sim):
+    """A transport with `matmul_allgather` takes the sharded x sharded product (no all-gather call);
+    when it declines the shape, ShardedArray falls back to all-gather + local GEMM."""
+    g.t.__class__ = sim.GlooPullTransport
+    A_f, B_f = _full((8 * g.world, 6 * g.world), 7, -1, 1), _full((6 * g.world, 4), 8, -1, 1)
+    A, B = _shard(g, sim, A_f), _shard(g, sim, B_f)
+    g.t.calls.clear()
+    C = A @ B
+    assert g.t.calls == [("pull", (B_f.size // g.world) * (g.world - 1))], g.t.calls
+    assert C.shape == (A_f.shape[0], 4)
+    np.testing.assert_allclose(C.to_numpy(), A_f @ B_f, rtol=1e-5, atol=1e-6)
+    # declined (too few local rows): the all-gather path
+    A2_f = _full((2 * g.world, 6 * g.world), 9, -1, 1)
+    g.t.calls.clear()
+    C2 = _shard(g, sim, A2_f) @ B
+    assert [c[0] for c in g.t.calls] == ["allgather"], g.t.calls
+    np.testing.assert_allclose(C2.to_numpy(), A2_f @ B_f, rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        A @ _shard(g, sim, _full((4 * g.world, 4), 10))      # inner dimensions differ
+
+
 def body_data_parallel(g, dist, sim):
     """Gradient all-reduce + 1/world scaling reproduces the single-process full-batch SGD step."""
     class P:  # minimal Parameter / layer / loss / Sequence surface used by DataParallel
@@ -273,6 +294,14 @@ def test_uneven_world3():
 
 def test_matmul_and_gather_world2():
     run("body_matmul", 2)
+
+
+def test_matmul_pull_world2():
+    run("body_matmul_pull", 2)
+
+
+def test_matmul_pull_world3():
+    run("body_matmul_pull", 3)
 
 
 def test_data_parallel_world2():
