@@ -10,7 +10,9 @@ Pinning: the reference cannot be built or imported in this imag
 libvulkan, glslc and a Vulkan ICD), so the oracle is pinned against the value-level vectors
 the reference itself publishes -- the ``Xoshiro128pp(seed=0)`` docstring of
 vulkpy/random.py:12-24 and the known answers of test/test_vulkpy.py, test/test_nn.py and
-doc/broadcasting.md -- see tests/test_oracle.py and tests/golden/.
+doc/broadcasting.md -- see tests/test_oracle.py and tests/golden/ -- and, wholesale, against the
+reference's own 233 unit tests, which tests/test_reference_suite_cpu.py runs unchanged from
+/root/reference/test with this oracle answering every kernel behind the Python layer.
 GLSL built-ins (exp, log, pow, sin, ...) are implemented by the Vulkan driver, which the
 reference does not pin (Dockerfile:1-10); for those the oracle is the correctly rounded
 float32 value of the float64 result, and tests state their tolerance: "parity unpinned
