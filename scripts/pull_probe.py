@@ -1,16 +1,16 @@
 """Row-sharded matmul timing at the 8-GPU range geometry (32 MiB ranges, 4 KB rows), runnable on 2 GPUs:
     python -m torch.distributed.run --nproc-per-node 2 ... scripts/pull_probe.py"""
-import ctypes as C, json, os, sys
+import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import vulkpy_b200 as vk
-from vulkpy_b200 import dist, _backend as b
+from vulkpy_b200 import dist
 from vulkpy_b200._backend import Timer
 
 g = dist.Group.from_env()
 gpu, rank, world = g.gpu, g.rank, g.world
 rng = vk.random.Xoshiro128pp(gpu, size=1 << 20, seed=5)
-out = {"parts": os.environ.get("VKP_PULL_PARTS", "default"), "world": world}
+out = {"world": world}
 for (M, N, K) in ((1024 * world, 8192, 1024 * world), (4096 * world, 8192, 8192)):
     A = g.random(rng, (M, K), "random"); Bm = g.random(rng, (K, N), "random")
     for _ in range(3):
