@@ -352,3 +352,67 @@ def test_regularizers_and_parameter(vk, gpu):
     frozen = Parameter(gpu, shape=(2,), trainable=False)
     assert not frozen.is_trainable() and frozen.grad is None
     frozen.update()                                  # no-op
+
+
+# ---- property tests (hypothesis): random shapes through the broadcasting / reduction / gather rules ---------
+from hypothesis import given, settings, HealthCheck, strategies as st   # noqa: E402
+from hypothesis.extra import numpy as hnp   # noqa: E402
+
+_shapes2 = hnp.mutually_broadcastable_shapes(num_shapes=2, min_dims=0, max_dims=4, min_side=1, max_side=4)
+_prop = settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+
+
+@_prop
+@given(shapes=_shapes2, op=st.sampled_from(["add", "sub", "mul", "div", "max", "min"]), seed=st.integers(0, 1000))
+def test_property_broadcast_matches_numpy(vk, gpu, shapes, op, seed):
+    (sa, sb), out_shape = shapes.input_shapes, shapes.result_shape
+    if not sa or not sb:          # 0-d arrays do not exist in the reference (data is always ravelled to >= 1-d)
+        return
+    rs = np.random.default_rng(seed)
+    x, y = rs.uniform(1, 2, sa).astype(F), rs.uniform(1, 2, sb).astype(F)
+    f = {"add": np.add, "sub": np.subtract, "mul": np.multiply, "div": np.divide, "max": np.maximum, "min": np.minimum}[op]
+    a, b = A(vk, gpu, x), A(vk, gpu, y)
+    got = {"add": lambda: a + b, "sub": lambda: a - b, "mul": lambda: a * b, "div": lambda: a / b,
+           "max": lambda: a.max(b), "min": lambda: a.min(b)}[op]()
+    assert tuple(got.shape) == tuple(out_shape)
+    np.testing.assert_array_equal(np.asarray(got), f(x, y).astype(F))
+    if tuple(sa) == tuple(out_shape) and op in ("add", "sub", "mul", "div"):     # in-place form keeps the target's shape
+        {"add": a.__iadd__, "sub": a.__isub__, "mul": a.__imul__, "div": a.__itruediv__}[op](b)
+        np.testing.assert_array_equal(np.asarray(a), f(x, y).astype(F))
+    np.testing.assert_array_equal(np.asarray(b.broadcast_to(out_shape)), np.broadcast_to(y, out_shape))
+
+
+@_prop
+@given(shape=hnp.array_shapes(min_dims=1, max_dims=4, min_side=1, max_side=5), data=st.data())
+def test_property_reductions_match_numpy(vk, gpu, shape, data):
+    nd = len(shape)
+    axes = data.draw(st.lists(st.integers(-nd, nd - 1), min_size=1, max_size=nd))
+    keep = data.draw(st.booleans())
+    name, f = data.draw(st.sampled_from([("sum", np.sum), ("maximum", np.max), ("minimum", np.min), ("mean", np.mean), ("prod", np.prod)]))
+    x = np.random.default_rng(0).uniform(0.5, 1.5, shape).astype(F)
+    np_axes = tuple(sorted({a % nd for a in axes}))
+    want = f(x.astype(np.float64), axis=np_axes, keepdims=keep)
+    got = getattr(A(vk, gpu, x), name)(axis=axes, keepdims=keep)
+    assert tuple(got.shape) == tuple(want.shape)
+    np.testing.assert_allclose(np.asarray(got), want, rtol=2e-6)
+    ax = axes[0]
+    rb = getattr(A(vk, gpu, x), name)(axis=ax, rebroadcast=True)
+    np.testing.assert_allclose(np.asarray(rb), np.broadcast_to(f(x.astype(np.float64), axis=ax, keepdims=True), shape), rtol=2e-6)
+    am = A(vk, gpu, x).argmax(axis=ax)
+    np.testing.assert_array_equal(np.asarray(am).reshape(np.argmax(x, axis=ax).shape), np.argmax(x, axis=ax))
+
+
+@_prop
+@given(shape=hnp.array_shapes(min_dims=1, max_dims=4, min_side=1, max_side=4), data=st.data())
+def test_property_gather_matches_numpy(vk, gpu, shape, data):
+    nd = len(shape)
+    axis = data.draw(st.integers(0, nd - 1))
+    idx_shape = data.draw(hnp.array_shapes(min_dims=1, max_dims=2, min_side=1, max_side=3))
+    x = np.arange(int(np.prod(shape)), dtype=F).reshape(shape)
+    idx = np.random.default_rng(1).integers(0, shape[axis], idx_shape).astype(np.uint32)
+    got = A(vk, gpu, x).gather(vk.U32Array(gpu, data=idx), axis=axis)
+    want = np.moveaxis(np.take(x, idx.astype(np.int64), axis=axis), list(range(axis, axis + idx.ndim)), list(range(idx.ndim)))
+    assert tuple(got.shape) == tuple(want.shape)       # index dimensions lead, then prev, then post
+    np.testing.assert_array_equal(np.asarray(got), want)
+    flat = np.random.default_rng(2).integers(0, x.size, idx_shape).astype(np.uint32)
+    np.testing.assert_array_equal(np.asarray(A(vk, gpu, x).gather(vk.U32Array(gpu, data=flat))), x.reshape(-1)[flat])
