@@ -29,3 +29,25 @@ def test_reference_suite_against_oracle_backed_layer():
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
     n = int(r.stdout.strip().splitlines()[-1].split(" passed")[0].split()[-1])
     assert n >= 230, tail
+
+
+EXAMPLES = "/root/reference/example"
+
+
+@pytest.mark.skipif(not os.path.isdir(EXAMPLES), reason="reference checkout not present")
+@pytest.mark.parametrize("script,args", [("00-arithmetic.py", []), ("01-random.py", []),
+                                         ("02-nn.py", ["--nepoch", "1", "--optimizer", "adam"]),
+                                         ("02-nn.py", ["--nepoch", "1", "--optimizer", "sgd"])])
+def test_reference_examples_run_unmodified(script, args):
+    """The reference's CI runs its three examples as integration tests (Dockerfile:49-57); here they
+    run unmodified, in place, against this repository's Python layer (oracle-backed device)."""
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([ROOT, os.path.join(ROOT, "tests"), env.get("PYTHONPATH", "")])
+    env["PYTHONDONTWRITEBYTECODE"] = "1"
+    code = ("import sys, runpy\nimport ref_suite_plugin\n"
+            f"sys.argv = [{script!r}] + {args!r}\n"
+            f"runpy.run_path({os.path.join(EXAMPLES, script)!r}, run_name='__main__')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp", timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    if script == "01-random.py":     # the stream the reference documents for seed 0 (random.py:12-24)
+        assert "0.42977667 0.8235899  0.90622926" in r.stdout and "-2.3403292" in r.stdout
