@@ -416,3 +416,27 @@ def test_property_gather_matches_numpy(vk, gpu, shape, data):
     np.testing.assert_array_equal(np.asarray(got), want)
     flat = np.random.default_rng(2).integers(0, x.size, idx_shape).astype(np.uint32)
     np.testing.assert_array_equal(np.asarray(A(vk, gpu, x).gather(vk.U32Array(gpu, data=flat))), x.reshape(-1)[flat])
+
+
+# ---- sharded generator: every rank draws its rows of the single-GPU stream (dist.Group.random) ----------------
+@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("kind", ["random", "randint", "normal"])
+def test_sharded_generator_equals_single_stream(vk, gpu, world, kind):
+    from vulkpy_b200 import dist
+    shape, size, seed = (12, 8), 4, 3
+    single = vk.random.Xoshiro128pp(gpu, size=size, seed=seed)
+    want = np.asarray(getattr(single, kind)(shape=shape)).copy()
+    parts, states = [], []
+    for rank in range(world):
+        g = dist.Group(None, rank, world, gpu=gpu)
+        r = vk.random.Xoshiro128pp(gpu, size=size, seed=seed)      # identical seed on every rank
+        sh = g.random(r, shape, kind)
+        lo, hi = g.bounds(shape[0])
+        assert tuple(sh.shape) == shape and tuple(sh.local.shape) == (hi - lo, shape[1])
+        parts.append(np.asarray(sh.local).copy())
+        states.append(r.rng.state())
+    np.testing.assert_array_equal(np.concatenate(parts, axis=0), want)   # bit-identical to one GPU
+    for s in states:                                                      # and every generator ends in the same state
+        np.testing.assert_array_equal(s, single.rng.state())
+    with pytest.raises(ValueError):
+        dist.Group(None, 0, world, gpu=gpu).random(vk.random.Xoshiro128pp(gpu, size=64, seed=1), (world, 5), "random")
