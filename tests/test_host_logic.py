@@ -440,3 +440,64 @@ def test_sharded_generator_equals_single_stream(vk, gpu, world, kind):
         np.testing.assert_array_equal(s, single.rng.state())
     with pytest.raises(ValueError):
         dist.Group(None, 0, world, gpu=gpu).random(vk.random.Xoshiro128pp(gpu, size=64, seed=1), (world, 5), "random")
+
+
+# ---- DataParallel over real nn.Sequence replicas (threads as ranks, in-process sum as the exchange) -----------
+class _ThreadTransport:
+    """All-reduce among threads of one process: the bucket entry point of the NCCL transport."""
+
+    def __init__(self, shared, rank, world):
+        self.shared, self.rank, self.world = shared, rank, world
+
+    def allreduce_many(self, arrs, op, scale=1.0):
+        assert op == "sum"
+        sh = self.shared
+        sh["slots"][self.rank] = [np.asarray(a).astype(F).copy() for a in arrs]
+        sh["barrier"].wait()
+        total = [sum(sh["slots"][r][i] for r in range(self.world)).astype(F) for i in range(len(arrs))]
+        sh["barrier"].wait()
+        for a, t in zip(arrs, total):
+            a[...] = (t * F(scale)).astype(F)
+        return arrs
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_data_parallel_equals_full_batch_step(vk, gpu, world):
+    """Gradient bucket all-reduce + 1/world scaling reproduces the single-process full-batch Adam
+    steps (reduce="mean" losses: nn/losses.py:41-46) with the real layers and their fused paths."""
+    import threading
+    from vulkpy_b200 import dist, nn
+    rs = np.random.default_rng(11)
+    B = 8 * world
+    x = rs.normal(size=(B, 5)).astype(F)
+    y = np.eye(3, dtype=F)[rs.integers(0, 3, B)]
+    opt = lambda: nn.Adam(gpu, lr=1e-2)
+    single = _mlp(vk, gpu, nn, opt)
+    for _ in range(3):
+        _, want_loss = single.train(A(vk, gpu, x), A(vk, gpu, y))
+    shared = {"slots": [None] * world, "barrier": threading.Barrier(world)}
+    nets, losses, errors = [None] * world, [None] * world, []
+
+    def rank_main(rank):
+        try:
+            g = dist.Group(_ThreadTransport(shared, rank, world), rank, world, gpu=gpu)
+            nets[rank] = _mlp(vk, gpu, nn, opt)
+            dp = dist.DataParallel(nets[rank], g)
+            lo, hi = g.bounds(B)
+            for _ in range(3):
+                _, losses[rank] = dp.train(A(vk, gpu, x[lo:hi]), A(vk, gpu, y[lo:hi]))
+        except Exception as e:   # pragma: no cover
+            errors.append(e)
+            shared["barrier"].abort()
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors, errors
+    for net in nets:
+        for ls, ld in ((single.L[0], net.L[0]), (single.L[2], net.L[2])):
+            np.testing.assert_allclose(np.asarray(ld.w.value), np.asarray(ls.w.value), rtol=2e-5, atol=1e-6)
+            np.testing.assert_allclose(np.asarray(ld.b.value), np.asarray(ls.b.value), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(float(np.asarray(losses[0]).reshape(-1)[0]), float(np.asarray(want_loss).reshape(-1)[0]), rtol=1e-5)
