@@ -11,14 +11,22 @@ per second, aggregated over all ranks (weak scaling: every rank owns its own 2^2
 shard, no data-path collective -- SURVEY.md 8(e)).  Timing: CUDA events recorded on the stream
 the kernels are launched on (vkp_timer_*), barrier + device sync on both sides, max over ranks.
 
-Prints ONE JSON line.  --impl reference times the CPU restatement of the reference's shaders
-(oracle/cpu_ref.c, OpenMP over all host cores; the reference itself needs Vulkan and cannot run
-in this image) on a bounded sample of the same workload.
+Prints ONE JSON line.  Besides the contract keys it carries
+  roofline         dominant kernel of the step (+ `worst`: the op furthest below the copy peak)
+  roofline_matmul  the other half of BASELINE.json's metric: 8192^2 fp32 `@`, burst and sustained
+  configs          C3 (axis reductions, 16384^2), C4 (gather, 2^26 indices), C5 (Xoshiro128pp 2^30
+                   samples at 64 and 2^20 lanes; one MLP train step) -- each with its own clock record
+  sharded          (N > 1) the exchange rows of SURVEY 8(e) on the PRODUCT's communicator
+                   (vulkpy_b200.dist: peer-mailbox all-reduce, fused row-sharded tcgen05 matmul,
+                   data-parallel MLP step, sharded generator), each parity-checked first
+--impl reference times the CPU restatement of the reference's shaders (oracle/cpu_ref.c, OpenMP over
+all host cores; the reference itself needs Vulkan and cannot run in this image) on the same workload.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -51,8 +59,7 @@ def ncu_traffic(op, n_elems):
     """DRAM bytes per launch of the op's kernel (dram__bytes_read.sum + dram__bytes_write.sum of the
     committed `ncu --set full` capture, which ran this same step on 2^28 elements), or None."""
     import csv, glob
-    root = os.path.dirname(os.path.abspath(__file__))
-    files = sorted(glob.glob(os.path.join(root, "profiles", "*ncu_elementwise*.csv")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_elementwise*.csv")))
     if not files or n_elems != 1 << 28:
         return None, None
     try:
@@ -62,7 +69,7 @@ def ncu_traffic(op, n_elems):
         unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[rows[1][rd]]
         for r in rows[2:]:
             if NCU_KERNEL[op] in r[kn]:
-                return int((float(r[rd]) + float(r[wr])) * unit), os.path.relpath(files[-1], root)
+                return int((float(r[rd]) + float(r[wr])) * unit), os.path.relpath(files[-1], ROOT)
     except Exception:
         pass
     return None, None
@@ -95,21 +102,23 @@ def run_step(a, b, row, col):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md).  One process
+    samples for the whole run; `window(t0, t1)` summarises the samples that arrived in a region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.samples = []       # (arrival time, sm, max, power, [reasons])
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
@@ -117,42 +126,47 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
+            f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                power.append(float(f[3]))
+                self.samples.append((time.time(), float(f[1]), float(f[2]), float(f[3]),
+                                     [n for n, v in zip(self.NAMES, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, val in zip(names, f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.1)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def window(self, t0: float, t1: float):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        rows = [s for s in self.samples if t0 <= s[0] <= t1 + 0.03]
+        if not rows:     # region shorter than the sampling period: nearest sample
+            rows = sorted(self.samples, key=lambda s: abs(s[0] - 0.5 * (t0 + t1)))[:1]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sample"]}
+        return {"sm_mhz": statistics.median(s[1] for s in rows), "sm_max_mhz": max(s[2] for s in rows),
+                "power_w_max": max(s[3] for s in rows), "samples": len(rows),
+                "reasons": sorted({r for s in rows for r in s[4]})}
 
 
-def measured_peak():
+def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+            j = json.load(f)
+        return {"hbm": float(j["hbm_gbs"]), "bf16": float(j["bf16_tflops"]),
+                "bf16_sustained": float(j.get("bf16_tflops_sustained", j["bf16_tflops"])),
+                "src": "MEASURED_PEAKS.json (driver-measured copy bandwidth / cuBLAS bf16 on this pool)"}
     except (OSError, KeyError, ValueError):
-        return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+        return {"hbm": 6650.0, "bf16": 1590.0, "bf16_sustained": 1400.0,
+                "src": "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"}
 
 
 # ------------------------------------------------------------------------------------- CPU arm
@@ -183,8 +197,8 @@ def cpu_arm(log2n_sample: int, steps: int, warmup: int):
     rows = 1 << (log2n_sample // 2)
     cols = (1 << log2n_sample) // rows
     rs = np.random.default_rng(1234)
-    a = rs.uniform(0.5, 2.0, (rows, cols)).astype(np.float32)
-    b = rs.uniform(-2.0, 2.0, (rows, cols)).astype(np.float32)
+    a = rs.random((rows, cols), dtype=np.float32) * np.float32(1.5) + np.float32(0.5)
+    b = rs.random((rows, cols), dtype=np.float32) * np.float32(4.0) - np.float32(2.0)
     row, col = b[0].copy(), b[:, 0].copy()
     c, out = np.empty_like(a), np.empty_like(a)
     shapes = {"row": np.array([rows, cols, 1, cols, rows, cols], np.uint32),
@@ -202,12 +216,14 @@ def cpu_arm(log2n_sample: int, steps: int, warmup: int):
 def reference_main(args, rank, world):
     if rank != 0:
         return
+    rows = 1 << (args.cpu_log2n // 2)
+    cols = (1 << args.cpu_log2n) // rows
     gbs, ms, cores, sample = cpu_arm(args.cpu_log2n, max(1, args.steps), max(1, min(args.warmup, 1)))
     line = {
         "impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: 12 elementwise/broadcast/transcendental ops, float32", "sample": sample},
+        "config": workload_config(rows, cols, sample=sample),
         "cpu_baseline": {"value": round(gbs, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "note": "C restatement of the reference shaders (oracle/cpu_ref.c, OpenMP); the "
                                  "reference's own SPIR-V needs Vulkan+lavapipe, absent from this image"},
@@ -215,6 +231,15 @@ def reference_main(args, rank, world):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def workload_config(rows, cols, **extra):
+    cfg = {"workload": f"C2: {len(OPS)} elementwise/broadcast/transcendental ops on "
+                       f"{rows}x{cols} float32 per GPU ({BYTES_PER_ELEM} algorithmic B/elem)",
+           "ops": [o for o, _ in OPS], "l2": "inputs (1 GiB each) are larger than the 126 MB L2",
+           "memory": "cudaMalloc pool (buffers move to managed memory only when the host views them)"}
+    cfg.update(extra)
+    return cfg
 
 
 # ------------------------------------------------------------------------------------- GPU arm
@@ -232,8 +257,429 @@ def bind_near_gpu(local_rank):
         cpus &= os.sched_getaffinity(0)
         if cpus:
             os.sched_setaffinity(0, cpus)
+            return {"bus": bus, "cpus": len(cpus), "numa_node": open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip()}
+    except Exception as e:
+        return {"error": str(e)[:100]}
+    return None
+
+
+class Bench:
+    """Shared helpers of the GPU arm: device events on the launch stream, max over ranks."""
+
+    def __init__(self, vk, gpu, rank, world, local_rank, tdist, sampler, peaks):
+        from vulkpy_b200._backend import Timer
+        self.vk, self.gpu, self.dev = vk, gpu, gpu.gpu
+        self.rank, self.world, self.local_rank, self.td = rank, world, local_rank, tdist
+        self.Timer, self.sampler, self.peaks = Timer, sampler, peaks
+
+    def barrier(self):
+        self.gpu.wait()
+        if self.td is not None:
+            import torch
+            self.td.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.td is None:
+            return x
+        import torch
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        self.td.all_reduce(t, op=self.td.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, fn, min_ms: float = 60.0, reps_cap: int = 400, warm: int = 3, collective: bool = False):
+        """Median-free: `inner` back-to-back calls between one event pair (device time per call),
+        inner chosen so that the region lasts >= min_ms.  collective=True: barrier first, max over ranks."""
+        for _ in range(warm):
+            r = fn()
+            del r
+        self.gpu.wait()
+        t0, t1 = self.Timer(self.dev), self.Timer(self.dev)
+        t0.record()
+        r = fn()
+        t1.record()
+        est = max(t0.elapsed_ms(t1), 1e-3)
+        del r
+        inner = int(min(reps_cap, max(5, math.ceil(min_ms / est))))
+        if collective:
+            inner = int(self.max_over_ranks(float(inner)))
+            self.barrier()
+        l0 = self.dev.launch_count()
+        t0.record()
+        for _ in range(inner):
+            r = fn()
+        t1.record()
+        ms = t0.elapsed_ms(t1) / inner
+        launches = (self.dev.launch_count() - l0) // inner
+        del r
+        if collective:
+            ms = self.max_over_ranks(ms)
+        return ms, launches, inner
+
+
+def hbm_row(B, name, fn, nbytes, note=None):
+    ms, launches, inner = B.timed(fn)
+    gbs = nbytes / ms / 1e6
+    r = {"ms": round(ms, 4), "gbs": round(gbs, 1), "frac": round(gbs / B.peaks["hbm"], 4), "alg_bytes": int(nbytes),
+         "launches": launches, "calls_timed": inner}
+    if note:
+        r["note"] = note
+    return name, r
+
+
+def config_c3(B, a, R):
+    """C3: axis reductions on 16384^2 float32 (vkarray.py:1194-1276): 4*N_in + 4*N_out algorithmic bytes."""
+    t0 = time.time()
+    rows = {}
+    B4 = 4 * R * R
+    for op in ("sum", "maximum", "mean"):
+        for axis, nout in ((0, R), (1, R), (None, 1)):
+            k, v = hbm_row(B, f"{op}(axis={axis})", (lambda o, ax: (lambda: getattr(a, o)(axis=ax)))(op, axis), B4 + 4 * nout)
+            rows[k] = v
+    k, v = hbm_row(B, "sum(axis=1,rebroadcast)", lambda: a.sum(axis=1, rebroadcast=True), 2 * B4)
+    rows[k] = v
+    k, v = hbm_row(B, "maximum(axis=0,rebroadcast)", lambda: a.maximum(axis=0, rebroadcast=True), 2 * B4)
+    rows[k] = v
+    B.gpu.wait()
+    return {"workload": f"sum/maximum/mean over axis 0 / 1 / None and rebroadcast on {R}x{R} float32 (input 1 GiB > L2)",
+            "rows": rows, "clocks": B.sampler.window(t0, time.time()),
+            "worst": min(rows, key=lambda k: rows[k]["frac"]), "bound": "hbm", "peak": B.peaks["hbm"]}
+
+
+def config_c4(B, rng):
+    """C4 gather half: 2^26 uint32 indices into an 8192^2 table (vkarray.py:1490-1521), 12 B per index."""
+    vk, gpu = B.vk, B.gpu
+    t0 = time.time()
+    G, NI = 8192, 1 << 26
+    table = rng.random(shape=(G, G))
+    idx_h = np.random.default_rng(99).integers(0, G * G, NI, dtype=np.uint32)
+    idx = vk.U32Array(gpu, data=idx_h)
+    idx_sorted = vk.U32Array(gpu, data=np.sort(idx_h))
+    del idx_h
+    rows = {}
+    k, v = hbm_row(B, "gather 2^26 random idx", lambda: table.gather(idx), 12 * NI,
+                   note="sector-bound: every 4-byte payload costs a 32-byte DRAM sector (ncu: profiles/r02_ncu_rows.md)")
+    v["sector_gbs"] = round((32 + 8) * NI / v["ms"] / 1e6, 1)
+    rows[k] = v
+    k, v = hbm_row(B, "gather 2^26 sorted idx", lambda: table.gather(idx_sorted), 12 * NI)
+    rows[k] = v
+    B.gpu.wait()
+    return {"workload": "table 8192^2 float32 (256 MiB), 2^26 uint32 indices from np.random.default_rng(99), and a sorted copy",
+            "rows": rows, "clocks": B.sampler.window(t0, time.time()), "bound": "hbm (sectors)", "peak": B.peaks["hbm"]}
+
+
+def config_c5(B):
+    """C5: Xoshiro128pp random / randint / normal, 2^30 samples, default 64 lanes and 2^20 lanes
+    (_vkarray.cc:697-717, random.py:60-124), 4 B per sample; one MLP train step (nn/models.py:55-78)."""
+    vk, gpu = B.vk, B.gpu
+    from vulkpy_b200 import nn
+    t0 = time.time()
+    P = 1 << 30
+    rows = {}
+    buf = vk.Array(gpu, shape=(P,))
+    ubuf = vk.U32Array(gpu, shape=(P,))
+    for size in (64, 1 << 20):
+        g = vk.random.Xoshiro128pp(gpu, size=size, seed=7)
+        for kind, target in (("random", buf), ("randint", ubuf), ("normal", buf)):
+            k, v = hbm_row(B, f"{kind} 2^30 (size={size})",
+                           (lambda gg, kk, tt: (lambda: getattr(gg, kk)(buffer=tt)))(g, kind, target), 4 * P)
+            rows[k] = v
+    del buf, ubuf
+    prng_clocks = B.sampler.window(t0, time.time())
+    t1 = time.time()
+    Bsz, D, H, C = 8192, 1024, 1024, 16
+    opt = nn.Adam(gpu, lr=1e-3)
+    net = nn.Sequence([nn.Dense(gpu, D, H, w_opt=opt, b_opt=opt, w_init=nn.HeNormal(gpu, D, seed=1)), nn.ReLU(),
+                       nn.Dense(gpu, H, C, w_opt=opt, b_opt=opt, w_init=nn.HeNormal(gpu, H, seed=2)), nn.Softmax()],
+                      nn.CrossEntropyLoss())
+    x = vk.random.Xoshiro128pp(gpu, size=1 << 16, seed=3).normal(shape=(Bsz, D))
+    y = vk.random.Xoshiro128pp(gpu, seed=4).randrange(shape=(Bsz,), low=0, high=C).to_onehot(C)
+    gpu.wait()
+    ms, launches, inner = B.timed(lambda: net.train(x, y)[1], min_ms=150.0)
+    flops = 6 * Bsz * (D * H + H * C)
+    w0 = time.perf_counter()
+    for _ in range(20):
+        net.train(x, y)
+    gpu.wait()
+    wall = (time.perf_counter() - w0) / 20 * 1e3
+    tf32_peak = B.peaks["bf16_sustained"] / 2
+    mlp = {"workload": f"Sequence[Dense({D},{H}), ReLU, Dense({H},{C}), Softmax] + CrossEntropyLoss + Adam, batch {Bsz}",
+           "ms": round(ms, 4), "launches": launches, "calls_timed": inner, "rows_per_s": round(Bsz / ms * 1e3, 1),
+           "tflops_fp32": round(flops / ms / 1e9, 2), "wall_ms_per_step": round(wall, 3),
+           "frac_of_tf32_pipe": round(3 * flops / ms / 1e9 / tf32_peak, 4),
+           "peak": tf32_peak, "peak_note": "TF32 dense = bf16_tflops_sustained / 2; 3 tensor-core MMAs per useful fp32 product",
+           "clocks": B.sampler.window(t1, time.time())}
+    return {"workload": "Xoshiro128pp random / randint / normal, 2^30 samples (4 GiB written), size=64 (reference default) and 2^20",
+            "rows": rows, "clocks": prng_clocks, "worst": min(rows, key=lambda k: rows[k]["frac"]),
+            "bound": "hbm (writes); normal: instruction issue", "peak": B.peaks["hbm"], "mlp_step": mlp}
+
+
+def matmul_block(B, rng, seconds: float):
+    """8192^2 fp32 `@` (vkarray.py:585-605, shader/matmul.comp): burst (3 calls) and sustained."""
+    vk, gpu, dev, Timer = B.vk, B.gpu, B.dev, B.Timer
+    m = 8192
+    ma = rng.random(shape=(m, m))
+    mb = rng.random(shape=(m, m))
+    for _ in range(2):
+        mc = ma @ mb
+    gpu.wait()
+    flops = 2 * m ** 3
+    t0, t1 = Timer(dev), Timer(dev)
+    w0 = time.time()
+    t0.record()
+    for _ in range(3):
+        mc = ma @ mb
+    t1.record()
+    burst_ms = t0.elapsed_ms(t1) / 3
+    w1 = time.time()
+    n = max(4, int(seconds * 1e3 / burst_ms))
+    l0 = dev.launch_count()
+    t0.record()
+    for _ in range(n):
+        mc = ma @ mb
+    t1.record()
+    sus_ms = t0.elapsed_ms(t1) / n
+    launches = (dev.launch_count() - l0) // n
+    w2 = time.time()
+    del ma, mb, mc
+    pk_b, pk_s = B.peaks["bf16"] / 2, B.peaks["bf16_sustained"] / 2
+    tb, ts = flops / burst_ms / 1e9, flops / sus_ms / 1e9
+    return {"bound": "tensor", "kernel": "gemm_tc_kernel<256,16,PRESPLIT> (tcgen05 kind::tf32, 3xTF32 split) + transpose/split pre-pass",
+            "shape": [m, m, m], "unit": "TFLOP/s", "launches_per_call": launches,
+            "burst": {"ms": round(burst_ms, 3), "achieved": round(tb, 2), "issued": round(3 * tb, 1), "peak": round(pk_b, 1),
+                      "frac": round(3 * tb / pk_b, 4), "calls": 3, "clocks": B.sampler.window(w0, w1)},
+            "sustained": {"ms": round(sus_ms, 3), "achieved": round(ts, 2), "issued": round(3 * ts, 1), "peak": round(pk_s, 1),
+                          "frac": round(3 * ts / pk_s, 4), "calls": n, "seconds": round(n * sus_ms / 1e3, 2),
+                          "clocks": B.sampler.window(w1, w2)},
+            "frac_of_nominal_tf32_1100": round(3 * ts / 1100.0, 4),
+            "peak_source": B.peaks["src"] + "; TF32 dense peak taken as bf16 / 2; `achieved` = useful fp32 FLOP/s, "
+                           "`issued` = 3x that (three TF32 MMAs per product), frac = issued / peak"}
+
+
+# ------------------------------------------------------------------------------------- sharded rows (N > 1)
+def nvlink_bytes(index):
+    """Sum of the NVLink data counters of GPU `index` in bytes (tx, rx), or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True,
+                             timeout=10).stdout
+        tx = rx = 0
+        for ln in out.splitlines():
+            if "Data Tx" in ln:
+                tx += int(ln.split(":")[-1].strip().split()[0])
+            elif "Data Rx" in ln:
+                rx += int(ln.split(":")[-1].strip().split()[0])
+        return tx * 1024, rx * 1024
     except Exception:
-        pass
+        return None
+
+
+def sharded_block(B):
+    """SURVEY 8(e) exchange rows through vulkpy_b200.dist on the product's own communicator.  Every
+    row is first asserted against the single-GPU / NumPy answer (a mismatch raises: non-zero exit),
+    then timed on the device (barrier first, max over ranks)."""
+    vk, gpu, rank, world = B.vk, B.gpu, B.rank, B.world
+    from vulkpy_b200 import dist, nn
+    F = np.float32
+    g = dist.Group.from_env()
+    out = {"world": world, "communicator": "vulkpy_b200.dist.NcclTransport (vkp_comm_*: NCCL via dlopen + CUDA-IPC peer mailbox)"}
+    rs = np.random.default_rng(0)
+
+    # ---- parity on moderate sizes, against NumPy -------------------------------------------------------
+    R, Cc = 64 * world, 96
+    a_f = rs.uniform(0.5, 2, (R, Cc)).astype(F)
+    b_f = rs.uniform(0.5, 2, (R, Cc)).astype(F)
+    a, b = g.shard(a_f), g.shard(b_f)
+    for mode in (1, 0):                        # peer mailbox, then plain NCCL
+        peer = g.t.peer_mode(mode)
+        np.testing.assert_array_equal((a + b).to_numpy(), a_f + b_f)
+        np.testing.assert_allclose(np.asarray(a.sum()), [a_f.astype(np.float64).sum()], rtol=2e-6)
+        np.testing.assert_array_equal(np.asarray(a.maximum()), [a_f.max()])
+        np.testing.assert_array_equal(np.asarray(a.minimum(axis=0)), a_f.min(axis=0))
+        np.testing.assert_allclose(np.asarray(a.sum(axis=0)), a_f.astype(np.float64).sum(axis=0), rtol=2e-6)
+        np.testing.assert_allclose(np.asarray(a.prod(axis=0)), a_f.astype(np.float64).prod(axis=0), rtol=2e-5)
+        np.testing.assert_allclose(a.sum(axis=1).to_numpy(), a_f.astype(np.float64).sum(axis=1), rtol=2e-6)
+        np.testing.assert_allclose(np.asarray(a.mean()), [a_f.astype(np.float64).mean()], rtol=2e-6)
+        np.testing.assert_allclose(a.maximum(axis=0, rebroadcast=True).to_numpy(),
+                                   np.broadcast_to(a_f.max(axis=0, keepdims=True), a_f.shape))
+        if mode == 1:
+            out["peer_mailbox_active"] = peer
+    g.t.peer_mode(1)
+    Mg, Kg, Ng = 256 * world, 64 * world, 384
+    A_f, B_f = rs.uniform(-1, 1, (Mg, Kg)).astype(F), rs.uniform(-1, 1, (Kg, Ng)).astype(F)
+    for rep in range(3):      # three calls: both staging copies and the epoch flags get reused
+        Cm = g.shard(A_f) @ g.shard(B_f)
+        want = A_f.astype(np.float64) @ B_f
+        mag = np.abs(A_f).astype(np.float64) @ np.abs(B_f)
+        err = float((np.abs(Cm.to_numpy() - want) / mag).max())
+        assert err < 6e-6, f"fused row-sharded matmul: error {err}"
+        B_f = B_f + F(0.25)
+    out["fused_matmul_used"] = not g.t._fused_broken
+    out["fused_matmul_err_vs_float64"] = err
+    shape = (16 * world, 256)
+    ref = np.asarray(vk.random.Xoshiro128pp(gpu, seed=11).random(shape=shape))
+    np.testing.assert_array_equal(g.random(vk.random.Xoshiro128pp(gpu, seed=11), shape, "random").to_numpy(), ref)
+    refn = np.asarray(vk.random.Xoshiro128pp(gpu, seed=12).normal(shape=shape))
+    np.testing.assert_array_equal(g.random(vk.random.Xoshiro128pp(gpu, seed=12), shape, "normal").to_numpy(), refn)
+
+    def make_small():
+        sgd = nn.SGD(0.05)
+        return nn.Sequence([nn.Dense(gpu, 16, 32, w_opt=sgd, b_opt=sgd, w_init=nn.HeNormal(gpu, 16, seed=1)), nn.ReLU(),
+                            nn.Dense(gpu, 32, 4, w_opt=sgd, b_opt=sgd, w_init=nn.HeNormal(gpu, 32, seed=2))],
+                           nn.SoftmaxCrossEntropyLoss())
+    Bg = 8 * world
+    x_f = rs.normal(size=(Bg, 16)).astype(F)
+    y_f = np.eye(4, dtype=F)[rs.integers(0, 4, Bg)]
+    single = make_small()
+    single.train(vk.Array(gpu, data=x_f), vk.Array(gpu, data=y_f))
+    lo, hi = g.bounds(Bg)
+    net = make_small()
+    dist.DataParallel(net, g).train(vk.Array(gpu, data=x_f[lo:hi]), vk.Array(gpu, data=y_f[lo:hi]))
+    for ls, ld in zip(single.L, net.L):
+        if hasattr(ls, "w"):
+            np.testing.assert_allclose(np.asarray(ld.w.value), np.asarray(ls.w.value), rtol=2e-5, atol=1e-6)
+            np.testing.assert_allclose(np.asarray(ld.b.value), np.asarray(ls.b.value), rtol=2e-5, atol=1e-6)
+    out["parity_moderate_sizes"] = "ok (element-wise, sum/max/min/prod/mean over None / 0 / 1, rebroadcast, fused matmul x3, PRNG bit-exact, DP step)"
+
+    # ---- full size: properties + timings (weak scaling: 2^28 elements per GPU) ---------------------------
+    rows_t = {}
+    rowsN = 16384
+    big = (rowsN * world, 16384)
+    rng = vk.random.Xoshiro128pp(gpu, size=1 << 20, seed=5)
+    x = g.random(rng, big, "random")
+    y = g.random(rng, big, "random")
+    n_total = big[0] * big[1]
+
+    def gathered(v):               # every rank's host value through torch.distributed (independent path)
+        objs = [None] * world
+        B.td.all_gather_object(objs, v)
+        return objs
+
+    # property: sharded sum == float64 sum of the ranks' local sums; axis-0 likewise
+    s_sh = float(np.asarray(x.sum())[0])
+    s_loc = gathered(float(np.asarray(x.local.sum())[0]))
+    assert abs(s_sh - sum(s_loc)) <= 2e-6 * abs(s_sh), (s_sh, s_loc)
+    v_sh = np.asarray(x.sum(axis=0)).astype(np.float64)
+    v_loc = np.sum(gathered(np.asarray(x.local.sum(axis=0)).astype(np.float64)), axis=0)
+    np.testing.assert_allclose(v_sh, v_loc, rtol=2e-6)
+    m_sh = np.asarray(x.maximum(axis=0))
+    m_loc = np.max(gathered(np.asarray(x.local.maximum(axis=0))), axis=0)
+    np.testing.assert_array_equal(m_sh, m_loc)
+    chk = gathered(v_sh.tobytes())
+    assert all(c == chk[0] for c in chk), "all-reduce results differ between ranks"
+    out["parity_full_size"] = "ok (2^28 elements per GPU: sharded sum / sum(axis=0) / maximum(axis=0) == combination of the ranks' local results; results bit-identical on all ranks)"
+
+    def row(name, fn, single_fn, unit_work, unit, weak=True, note=None, **kw):
+        ms, launches, inner = B.timed(fn, collective=True, **kw)
+        ms1 = B.max_over_ranks(B.timed(single_fn, **kw)[0]) if single_fn else None
+        r = {"ms": round(ms, 4), "launches": launches, "agg": round(unit_work / ms, 1), "unit": unit}
+        if ms1:
+            r["ms_one_gpu_same_local_work" if weak else "ms_one_gpu_whole_problem"] = round(ms1, 4)
+            r["x_over_one_gpu"] = round((world * ms1 if weak else ms1) / ms, 2)
+        if note:
+            r["note"] = note
+        rows_t[name] = r
+        return r
+
+    GB = 1e6   # bytes / ms -> GB/s
+    row("a+b (16384^2 per GPU, no exchange)", lambda: x + y, None, 12 * n_total / GB, "GB/s aggregate")
+    row("sum() + all-reduce of 1 float", lambda: x.sum(), lambda: x.local.sum(), 4 * n_total / GB, "GB/s aggregate")
+    row("sum(axis=0) + all-reduce of 16384 floats", lambda: x.sum(axis=0), lambda: x.local.sum(axis=0), 4 * n_total / GB, "GB/s aggregate")
+    row("maximum(axis=0) + all-reduce", lambda: x.maximum(axis=0), lambda: x.local.maximum(axis=0), 4 * n_total / GB, "GB/s aggregate")
+    row("sum(axis=1) (no exchange)", lambda: x.sum(axis=1), lambda: x.local.sum(axis=1), 4 * n_total / GB, "GB/s aggregate")
+    g.t.peer_mode(0)
+    row("sum(axis=0), exchange through ncclAllReduce (A/B)", lambda: x.sum(axis=0), None, 4 * n_total / GB, "GB/s aggregate")
+    row("sum(), exchange through ncclAllReduce (A/B)", lambda: x.sum(), None, 4 * n_total / GB, "GB/s aggregate")
+    g.t.peer_mode(1)
+    del x, y
+
+    # sharded generator: this rank's rows of ONE 2^30*world-sample stream (jump-ahead), bit-exact
+    P = 1 << 30
+    prng = vk.random.Xoshiro128pp(gpu, size=1 << 20, seed=21)
+    shp = (world * 1024, P // 1024)
+    sh = g.random(prng, shp, "random")
+    lo, hi = g.bounds(shp[0])
+    probe = vk.random.Xoshiro128pp(gpu, size=1 << 20, seed=21)
+    probe.rng.advance(lo * shp[1])
+    head = np.asarray(probe.random(shape=(1 << 20,)))
+    first = vk.U32Array(gpu, data=np.arange(1 << 20, dtype=np.uint32))
+    np.testing.assert_array_equal(np.asarray(sh.local.gather(first)), head)
+    del first
+    buf = sh.local
+    del sh
+
+    def sharded_draw():
+        r = g.random(prng, shp, "random")
+        return r
+    local_rng = vk.random.Xoshiro128pp(gpu, size=1 << 20, seed=22)
+    row("Xoshiro128pp.random, 2^30 samples per GPU of one global stream", sharded_draw,
+        lambda: local_rng.random(buffer=buf), 4.0 * P * world / GB, "GB/s aggregate",
+        note="each rank jumps its lanes over the lower ranks' chunks (GF(2) matrices), draws, jumps over the rest")
+    del buf
+
+    # row-sharded matmul: fixed size and weak scaling
+    M = 8192
+    A = g.random(rng, (M, M), "random")
+    Bm = g.random(rng, (M, M), "random")
+    Cf = A @ Bm
+    g.t._fused_broken, keep = True, g.t._fused_broken
+    Cg = A @ Bm                                   # ncclAllGather(B) + the same GEMM: independent exchange path
+    g.t._fused_broken = keep
+    d = np.abs(Cf.local.to_host() - Cg.local.to_host()).max()
+    assert d <= 0.03, f"fused vs all-gather matmul differ by {d}"     # 2 x 6e-6 x sum|a||b| (~2048)
+    del Cf, Cg
+    A1 = rng.random(shape=(M, M))
+    B1 = rng.random(shape=(M, M))
+    nv0 = nvlink_bytes(B.local_rank)
+    r = row("matmul 8192^3 row-sharded (fixed size), peers' B pulled inside one tcgen05 GEMM", lambda: A @ Bm,
+            lambda: A1 @ B1, 2 * M ** 3 / 1e9, "TFLOP/s aggregate", weak=False, min_ms=40.0)
+    nv1 = nvlink_bytes(B.local_rank)
+    tiles = (M // world // 128) * (M // 256) if (M // world) % 128 == 0 else None
+    if tiles:
+        waves = tiles / 148.0
+        r["limiter"] = (f"wave quantisation: {M // world} local rows x {M} columns = {tiles} tiles of 128x256 on 148 SMs = "
+                        f"{waves:.2f} waves -> {math.ceil(waves)} (ideal {r.get('ms_one_gpu_whole_problem', 0) / world:.3f} ms "
+                        f"x {math.ceil(waves) / waves:.2f}) + transpose/split pre-pass of the local shard + barrier")
+    if nv0 and nv1:
+        r["nvlink_rx_bytes_per_call_counter"] = None     # the counters move with every rank's calls; reported raw below
+        r["nvlink_counter_delta_bytes"] = {"tx": nv1[0] - nv0[0], "rx": nv1[1] - nv0[1]}
+    r["nvlink_pull_bytes_per_call"] = int(4 * M * M * (world - 1) / world)
+    r["nvlink_pull_gbs_lower_bound"] = round(4 * M * M * (world - 1) / world / r["ms"] / 1e6, 1)
+    g.t._fused_broken = True
+    row("matmul 8192^3 row-sharded, ncclAllGather(B) then GEMM (A/B)", lambda: A @ Bm, None, 2 * M ** 3 / 1e9,
+        "TFLOP/s aggregate", weak=False, min_ms=40.0)
+    g.t._fused_broken = False
+    del A
+    Aw = g.random(rng, (M * world, M), "random")
+    row("matmul (8192*world) x 8192 x 8192 weak scaling, fused", lambda: Aw @ Bm, lambda: A1 @ B1,
+        2.0 * world * M ** 3 / 1e9, "TFLOP/s aggregate", weak=True, min_ms=40.0)
+    del Aw, Bm, A1, B1
+
+    # data-parallel MLP step (config 5): 8192 rows per GPU, global batch 8192 * world
+    def make_mlp():
+        opt = lambda: nn.Adam(gpu, lr=1e-3)
+        return nn.Sequence([nn.Dense(gpu, 1024, 1024, w_opt=opt(), b_opt=opt(), w_init=nn.HeNormal(gpu, 1024, seed=1)), nn.ReLU(),
+                            nn.Dense(gpu, 1024, 16, w_opt=opt(), b_opt=opt(), w_init=nn.HeNormal(gpu, 1024, seed=2)), nn.Softmax()],
+                           nn.CrossEntropyLoss())
+    Bl = 8192
+    xb = vk.random.Xoshiro128pp(gpu, size=1 << 16, seed=100 + rank).normal(shape=(Bl, 1024))
+    yb = vk.random.Xoshiro128pp(gpu, size=1 << 16, seed=200 + rank).randrange(shape=(Bl,), low=0, high=16).to_onehot(16)
+    mlp = make_mlp()
+    dpm = dist.DataParallel(mlp, g)
+    single_mlp = make_mlp()
+    row("data-parallel MLP step, 8192 rows per GPU (gradient bucket through the peer mailbox)",
+        lambda: dpm.train(xb, yb)[1], lambda: single_mlp.train(xb, yb)[1], Bl * world * 1e3, "rows/s aggregate", min_ms=100.0)
+    # property: replicas stay identical (same reduced gradients, same optimizer step on every rank)
+    sig = gathered(np.asarray(mlp.L[0].w.value.sum()).tobytes() + np.asarray(mlp.L[2].w.value.sum()).tobytes())
+    assert all(s == sig[0] for s in sig), "data-parallel replicas diverged"
+    g.t.peer_mode(0)
+    row("data-parallel MLP step, gradient bucket through grouped ncclAllReduce (A/B)", lambda: dpm.train(xb, yb)[1],
+        None, Bl * world * 1e3, "rows/s aggregate", min_ms=100.0)
+    g.t.peer_mode(1)
+    out["rows"] = rows_t
+    out["target"] = ">= 7x on 8 GPUs for the comm-free and one-exchange rows (north_star); x_over_one_gpu is measured in this run"
+    B.gpu.wait()
+    g.t.close()
+    return out
 
 
 def main():
@@ -243,9 +689,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=28, help="elements per GPU = 2^log2n")
-    ap.add_argument("--cpu-log2n", type=int, default=26, help="CPU sample size = 2^cpu_log2n elements")
+    ap.add_argument("--cpu-log2n", type=int, default=28, help="CPU arm: 2^cpu_log2n elements (same workload as the GPU arm)")
     ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--matmul-seconds", type=float, default=2.0, help="length of the sustained matmul loop")
     ap.add_argument("--no-matmul", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3/C4/C5 rows")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the exchange rows")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -258,18 +707,26 @@ def main():
 
     args.warmup = max(args.warmup, 3)
     dist = None
+    binding = None
     if world > 1:
+        if "NCCL_DEBUG" not in os.environ:               # the rank count of BOTH communicators (torch's barrier
+            os.environ["NCCL_DEBUG"] = "INFO"            # group and the product's) shows in NCCL's own log;
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")        # stdout stays the one JSON line
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    if world > 1:
-        bind_near_gpu(local_rank)
+        binding = bind_near_gpu(local_rank)
     import vulkpy_b200 as vk
     gpu = vk.GPU(local_rank)
     dev = gpu.gpu
     from vulkpy_b200._backend import Timer
+    peaks = measured_peaks()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    B = Bench(vk, gpu, rank, world, local_rank, dist, sampler, peaks)
 
     rows = 1 << (args.log2n // 2)
     cols = (1 << args.log2n) // rows
@@ -284,21 +741,13 @@ def main():
     row = rng.random(shape=(cols,))
     col = rng.random(shape=(rows, 1))
     gpu.wait()
-
-    def barrier():
-        gpu.wait()
-        if dist is not None:
-            import torch
-            dist.barrier()
-            torch.cuda.synchronize()
+    barrier = B.barrier
 
     for _ in range(args.warmup):
         run_step(a, b, row, col)
     barrier()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    w0 = time.time()
     t0, t1 = Timer(dev), Timer(dev)
     launches0 = dev.launch_count()
     t0.record()
@@ -308,14 +757,11 @@ def main():
     ms_total = t0.elapsed_ms(t1)
     launches = dev.launch_count() - launches0
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.window(w0, time.time()) if rank == 0 else None
 
-    ms_step = ms_total / args.steps
+    ms_step = B.max_over_ranks(ms_total / args.steps)
     if dist is not None:
         import torch
-        t = torch.tensor([ms_step], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step = float(t.item())
         lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
         dist.all_reduce(lt)
         launches = int(lt.item())
@@ -336,18 +782,30 @@ def main():
         gpu.wait()
     op_ms = {k: statistics.median(p.elapsed_ms(q) for p, q in v) for k, v in per_op.items()}
     op_gbs = {name: bpe * n / (op_ms[name] * 1e-3) / 1e9 for name, bpe in OPS}
-    dominant = max(op_ms, key=op_ms.get)
-    peak, peak_src = measured_peak()
+    # dominant kernel = largest share of the step over all launches of that kernel (a+b and c+=b are
+    # the same ew_kernel<2,FAdd>): stable across runs, unlike "longest single launch"
+    share = {}
+    for name, _ in OPS:
+        share[NCU_KERNEL[name]] = share.get(NCU_KERNEL[name], 0.0) + op_ms[name]
+    dom_kernel = max(share, key=share.get)
+    dominant = [nm for nm, _ in OPS if NCU_KERNEL[nm] == dom_kernel][0]
+    worst = min(op_gbs, key=op_gbs.get)
+    peak, peak_src = peaks["hbm"], peaks["src"]
     traffic, traffic_src = ncu_traffic(dominant, n)
-    roofline = {"bound": "hbm", "kernel": dominant, "achieved": round(op_gbs[dominant], 1), "peak": peak,
-                "unit": "GB/s", "frac": round(op_gbs[dominant] / peak, 4), "traffic": traffic,
+    wtraffic, _ = ncu_traffic(worst, n)
+    total_ms = sum(op_ms.values())
+    roofline = {"bound": "hbm", "kernel": dominant, "kernel_symbol": dom_kernel, "achieved": round(op_gbs[dominant], 1),
+                "peak": peak, "unit": "GB/s", "frac": round(op_gbs[dominant] / peak, 4), "traffic": traffic,
                 "traffic_source": traffic_src, "algorithmic_bytes": dict(OPS)[dominant] * n,
-                "peak_source": peak_src, "share_of_step": round(op_ms[dominant] / sum(op_ms.values()), 4),
+                "peak_source": peak_src, "share_of_step": round(share[dom_kernel] / total_ms, 4),
+                "worst": {"kernel": worst, "kernel_symbol": NCU_KERNEL[worst], "achieved": round(op_gbs[worst], 1),
+                          "frac": round(op_gbs[worst] / peak, 4), "share_of_step": round(op_ms[worst] / total_ms, 4),
+                          "algorithmic_bytes": dict(OPS)[worst] * n, "traffic": wtraffic,
+                          "bound": "instruction issue + FP64 pipe (binary64 log2 / exp2 for the 0.5001-ulp contract), not HBM"},
                 "per_op_gbs": {k: round(v, 1) for k, v in op_gbs.items()},
                 "per_op_frac": {k: round(v / peak, 4) for k, v in op_gbs.items()}}
 
     # ---- end to end: host buffers in, result out, through the public API
-    e2e = None
     a_h = vk.pinned_empty((rows, cols))
     b_h = vk.pinned_empty((rows, cols))
     out_h = vk.pinned_empty((rows, cols))
@@ -381,61 +839,74 @@ def main():
     w0 = time.perf_counter()
     e2e_run(args.e2e_steps)
     gpu.wait()
-    e2e_ms = (time.perf_counter() - w0) / args.e2e_steps * 1e3
-    if dist is not None:
-        import torch
-        t = torch.tensor([e2e_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = B.max_over_ranks((time.perf_counter() - w0) / args.e2e_steps * 1e3)
     e2e = {"value": round(world * BYTES_PER_ELEM * n / (e2e_ms * 1e-3) / 1e9, 2), "unit": UNIT,
            "h2d_bytes_per_step": int(a_h.nbytes + b_h.nbytes + row_h.nbytes + col_h.nbytes),
            "d2h_bytes_per_step": int(out_h.nbytes), "ms_per_step": round(e2e_ms, 2),
            "path": "Array.from_host(pinned) x2 + Array(data=) x2 -> 12 ops -> Array.to_host(pinned, wait=False); "
                    "steps software-pipelined over the two copy engines"}
+    if world > 1:
+        # the host bound beside it: the bare pinned transfers of one step (2 GiB in, 1 GiB out, both copy
+        # engines at once) on all ranks together, no kernels
+        def copies_only(steps):
+            for i in range(steps):
+                ua, ub = vk.Array.from_host(gpu, a_h), vk.Array.from_host(gpu, b_h)
+                a.to_host(outs[i % 2], wait=False)
+                ua.wait(); ub.wait(); a.wait()
+        copies_only(1)
+        barrier()
+        w0 = time.perf_counter()
+        copies_only(4)
+        gpu.wait()
+        cp_ms = B.max_over_ranks((time.perf_counter() - w0) / 4 * 1e3)
+        e2e["host_copy_bound"] = {"ms_per_step": round(cp_ms, 2), "note": "bare pinned H2D 2 GiB + D2H 1 GiB per rank, all ranks at once, no kernels: "
+                                  "what the box's PCIe / host memory gives", "h2d_gbs_per_rank": round((a_h.nbytes + b_h.nbytes) / cp_ms / 1e6, 1),
+                                  "e2e_over_bound": round(cp_ms / e2e_ms, 3), "cpu_binding": binding}
     del a_h, b_h, out_h, out2_h, outs
 
-    # ---- the other half of BASELINE.json's metric: 8192^2 fp32 matmul (reported, not in the step)
+    # ---- the other half of BASELINE.json's metric: 8192^2 fp32 matmul
     matmul = None
     if not args.no_matmul:
         try:
-            m = 8192
-            ma = rng.random(shape=(m, m))
-            mb = rng.random(shape=(m, m))
-            for _ in range(2):
-                mc = ma @ mb
-            gpu.wait()
-            tm0, tm1 = Timer(dev), Timer(dev)
-            tm0.record()
-            for _ in range(3):
-                mc = ma @ mb
-            tm1.record()
-            mm_ms = tm0.elapsed_ms(tm1) / 3
-            matmul = {"shape": [m, m, m], "ms": round(mm_ms, 3), "tflops_fp32": round(2 * m ** 3 / (mm_ms * 1e-3) / 1e12, 2)}
-            del ma, mb, mc
+            matmul = matmul_block(B, rng, args.matmul_seconds if world == 1 else 0.5)
         except Exception as e:  # the bench line must still be printed
             matmul = {"error": str(e)[:200]}
 
+    # ---- C3 / C4 / C5 (single-GPU rows; N > 1 runs the exchange rows instead)
+    configs = None
+    if world == 1 and not args.no_configs and args.log2n == 28:
+        configs = {}
+        for key, fn in (("C3", lambda: config_c3(B, a, rows)), ("C4", lambda: config_c4(B, rng)), ("C5", lambda: config_c5(B))):
+            try:
+                configs[key] = fn()
+            except Exception as e:
+                configs[key] = {"error": str(e)[:300]}
+    del a, b, row, col
+
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        sharded = sharded_block(B)      # parity failures raise: non-zero exit, no bench line
+
     if rank == 0:
-        cpu_gbs, cpu_ms, cores, sample = (None, None, None, None)
+        sampler.stop()
         cpu_baseline = None
         if world == 1:
+            dev.trim()
             cpu_gbs, cpu_ms, cores, sample = cpu_arm(args.cpu_log2n, 3, 1)
             cpu_baseline = {"value": round(cpu_gbs, 3), "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": sample + ", 3 passes after 1 warm-up"}
+                            "sample": sample + ", 3 passes after 1 warm-up", "ms_per_step": round(cpu_ms, 1)}
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C2: {len(OPS)} elementwise/broadcast/transcendental ops on "
-                                   f"{rows}x{cols} float32 per GPU ({BYTES_PER_ELEM} algorithmic B/elem)",
-                       "ops": [o for o, _ in OPS], "l2": "inputs (1 GiB each) are larger than the 126 MB L2",
-                       "memory": "cudaMalloc pool (buffers move to managed memory only when the host views them)"},
-            "frac_of_peak": round(value / world / peak, 4),
+            "config": workload_config(rows, cols),
+            "frac_of_peak": round(value / world / peak, 4), "frac_of_nominal_8TBs": round(value / world / 8000.0, 4),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "matmul_8192": matmul,
+            "cpu_baseline": cpu_baseline, "roofline_matmul": matmul, "configs": configs, "sharded": sharded,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -13,8 +13,9 @@
  *     construction (the reference host-blocks on every dependency: _vkarray.cc:430-432).
  *   - sizes that cross the reference boundary are uint32 (_vkarray.cc:132-203); the
  *     parameter structs below keep that layout bit-for-bit.  Kernels index with 64 bits.
- *   - buffers are CUDA managed allocations: the returned pointer is valid on the host
- *     (NumPy view, reference _vkarray.cc:61-72,805-814) and on the device.
+ *   - buffers are plain device memory (cudaMalloc, pooled); the first request for a host view
+ *     (vkp_host_view: NumPy view of the reference, _vkarray.cc:61-72,805-814) moves a buffer into a
+ *     managed block whose pointer is valid on the host and on the device.
  */
 #ifndef VULKPY_B200_H
 #define VULKPY_B200_H
@@ -209,6 +210,21 @@ VKP_API int vkp_comm_allreduce(vkp_ctx* ctx, const float* send, float* recv, siz
 VKP_API int vkp_comm_allreduce_multi(vkp_ctx* ctx, float* const* bufs, const size_t* counts, int n, int op,
                                      float scale, vkp_job** job);
 VKP_API int vkp_comm_allgather(vkp_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank, vkp_job** job);
+/* Small all-reduces (reduction partials, the gradient bucket: anything that fits an 8 MiB mailbox slot)
+ * and barriers do not call NCCL: every rank owns a mailbox block mapped into all peers with CUDA IPC and
+ * ONE kernel copies the operands in, raises a flag in every peer's mailbox, waits for the peers' flags and
+ * folds the w slots in rank order with 16-byte loads over NVLink (bit-identical results on all ranks).
+ * VKP_COMM_PEER=0, a failed IPC mapping on any rank, or a larger operand select NCCL on ALL ranks.
+ * vkp_comm_reduce_allreduce fuses the local reduction of a shard with that exchange: in [prev, axis, post]
+ * -> local partials written straight into the mailbox slot -> out [prev, post] reduced over the ranks
+ * (full reduction: prev = 1, axis = n, post = 1).  The reference reduces one array on one device
+ * (vkarray.py:1194-1276); these are its sharded forms. */
+VKP_API int vkp_comm_reduce_allreduce(vkp_ctx* ctx, int op, const float* in, float* out, uint32_t prev,
+                                      uint32_t axis, uint32_t post, vkp_job** job);
+VKP_API int vkp_comm_barrier(vkp_ctx* ctx, vkp_job** job);
+/* mode 0: NCCL for every later collective, 1: peer mailbox where it applies (default), -1: query.
+ * *active = 1 when the mailbox is mapped and selected.  Collective (same point on every rank). */
+VKP_API int vkp_comm_peer_mode(vkp_ctx* ctx, int mode, int* active);
 /* Row-sharded matmul (vkarray.py:585-605 on a sharded pair): C[M,N] = A[M,K] @ B[K,N] with A, C the
  * local row blocks and B_shard the local [K/nranks, N] row block of B.  ONE tcgen05 GEMM kernel: it
  * starts on the local K range while its spare warps pull the peers' shards over NVLink (CUDA IPC

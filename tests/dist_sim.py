@@ -131,6 +131,19 @@ class GlooTransport:
         return NumpyLocal(np.zeros(shape, F))
 
 
+class GlooFusedTransport(GlooTransport):
+    """Same, plus the fused entry point of the NCCL transport (``reduce_allreduce``): the local
+    ``[prev, axis, post] -> [prev, post]`` reduction and its exchange as one call."""
+
+    def reduce_allreduce(self, arr, op, prev, axis, post, out_shape):
+        assert arr.a.size == prev * axis * post
+        part = _RED[op](arr.a.reshape(prev, axis, post), axis=1) if axis else np.full((prev, post), {"sum": 0, "prod": 1, "maximum": -np.inf, "minimum": np.inf}[op], F)
+        t = torch.from_numpy(np.ascontiguousarray(part, dtype=F))
+        td.all_reduce(t, op=_TD[op])
+        self.calls.append(("reduce_allreduce", int(t.numel())))
+        return NumpyLocal(t.numpy().reshape(out_shape))
+
+
 class GlooBucketTransport(GlooTransport):
     """Same, plus the bucket entry point of the NCCL transport (``allreduce_many``): every tensor of
     the bucket crosses in ONE collective, then ``x *= scale`` in float32 on each."""

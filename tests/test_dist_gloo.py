@@ -34,6 +34,9 @@ def _worker(rank, world, port, fn_name, q):
         import dist_sim
         g = dist.Group(dist_sim.GlooTransport(rank, world), rank, world)
         globals()[fn_name](g, dist, dist_sim)
+        if fn_name in ("body_reductions", "body_uneven"):     # again over the fused reduce + exchange seam
+            g = dist.Group(dist_sim.GlooFusedTransport(rank, world), rank, world)
+            globals()[fn_name](g, dist, dist_sim)
         q.put((rank, "ok"))
     except Exception as e:  # surface the failure in the parent
         import traceback
@@ -96,15 +99,19 @@ def body_reductions(g, dist, sim):
     r = a.maximum(axis=(1, 2), keepdims=True)
     assert g.t.calls == [] and r.shape == (12, 1, 1)
     g.t.calls.clear()
+    fused = hasattr(g.t, "reduce_allreduce")
+    kind = "reduce_allreduce" if fused else "allreduce"
     r0 = a.sum(axis=0)                                  # one exchange of `post` floats
-    assert g.t.calls == [("allreduce", 20)]
+    assert g.t.calls == [(kind, 20)] and r0.shape == (5, 4)
     np.testing.assert_allclose(np.asarray(r0), a_f.sum(axis=0), rtol=1e-6)
     for name, f in [("sum", np.sum), ("prod", np.prod), ("maximum", np.max), ("minimum", np.min)]:
         g.t.calls.clear()
         r = getattr(a, name)()
-        assert g.t.calls == [("allreduce", 1)]         # a single float crosses the wire
+        assert g.t.calls == [(kind, 1)] and r.shape == (1,)   # a single float crosses the wire
         np.testing.assert_allclose(np.asarray(r), [f(a_f.astype(np.float64))], rtol=1e-4)
     np.testing.assert_allclose(np.asarray(a.sum(axis=(0, 2))), a_f.sum(axis=(0, 2)), rtol=1e-6)
+    assert a.sum(axis=(0, 2)).shape == (5,) and a.sum(axis=(0, 2), keepdims=True).shape == (1, 5, 1)
+    assert a.maximum(axis=0, keepdims=True).shape == (1, 5, 4)
     np.testing.assert_allclose(np.asarray(a.mean()), [a_f.mean()], rtol=1e-6)            # global count
     np.testing.assert_allclose(np.asarray(a.mean(axis=0)), a_f.mean(axis=0), rtol=1e-6)
     np.testing.assert_allclose(a.mean(axis=2).to_numpy(), a_f.mean(axis=2), rtol=1e-6)

@@ -92,6 +92,9 @@ PROTOTYPES = {
     "vkp_comm_allreduce": (C.c_int, [_vp, _vp, _vp, _sz, C.c_int, C.POINTER(_vp)]),
     "vkp_comm_allgather": (C.c_int, [_vp, _vp, _vp, _sz, C.POINTER(_vp)]),
     "vkp_comm_allreduce_multi": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_sz), C.c_int, C.c_int, C.c_float, C.POINTER(_vp)]),
+    "vkp_comm_reduce_allreduce": (C.c_int, [_vp, C.c_int, _vp, _vp, _u32, _u32, _u32, C.POINTER(_vp)]),
+    "vkp_comm_barrier": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "vkp_comm_peer_mode": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int)]),
     "vkp_comm_matmul_allgather": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp, _vp, C.POINTER(_vp)]),
 }
 

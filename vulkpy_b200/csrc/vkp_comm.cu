@@ -93,6 +93,14 @@ struct vkp_comm_state {
   size_t symm_bytes = 0;                  // bytes of ONE copy
   void* peer[VKP_MAX_RANKS] = {};         // peer[r] = rank r's symm mapped here (peer[rank] = symm)
   uint64_t calls = 0;
+  // ---- peer mailbox: small all-reduces / barriers as ONE kernel over NVLink peer memory ----
+  // block layout: [flags set 0: 16 words][flags set 1: 16 words][grid counter] ... pad to 4 KiB,
+  // then two data slots (call parity) of MBOX_SLOT_BYTES each
+  void* mbox = nullptr;
+  void* mbox_peer[VKP_MAX_RANKS] = {};    // mbox_peer[r] = rank r's mailbox mapped here
+  uint32_t mbox_epoch = 0;
+  int mbox_state = 0;                     // 0 untried, 1 mapped on all ranks, -1 unavailable (NCCL only)
+  bool mbox_off = false;                  // vkp_comm_peer_mode(0): keep the mapping, route through NCCL (A/B runs)
 };
 
 static_assert(VKP_COMM_ID_BYTES == sizeof(ncclUniqueId), "unique id size");
@@ -132,78 +140,18 @@ extern "C" int vkp_comm_destroy(vkp_ctx* ctx) {
   VKP_TRY(vkp_make_current(ctx));
   cudaStreamSynchronize(ctx->stream);
   vkp_comm_state* st = ctx->comm;
-  for (int r = 0; r < st->nranks; r++)
+  for (int r = 0; r < st->nranks; r++) {
     if (r != st->rank && st->peer[r]) cudaIpcCloseMemHandle(st->peer[r]);
+    if (r != st->rank && st->mbox_peer[r]) cudaIpcCloseMemHandle(st->mbox_peer[r]);
+  }
   g_nccl.CommDestroy(st->comm);          // collective: every rank has stopped reading this rank's memory
   if (st->symm) cudaFree(st->symm);
+  if (st->mbox) cudaFree(st->mbox);
   if (st->flags) cudaFree(st->flags);
   if (st->barrier_word) cudaFree(st->barrier_word);
   delete ctx->comm;
   ctx->comm = nullptr;
   return VKP_OK;
-}
-
-extern "C" int vkp_comm_allreduce(vkp_ctx* ctx, const float* send, float* recv, size_t count, int op,
-                                  vkp_job** job) {
-  VKP_CHECK(ctx && ctx->comm, "vkp_comm_allreduce: communicator not initialised");
-  VKP_CHECK(op >= 0 && op <= 3, "vkp_comm_allreduce: bad op %d", op);
-  VKP_TRY(vkp_make_current(ctx));
-  std::lock_guard<std::mutex> g(ctx->mu);
-  void* bufs[2] = {(void*)send, (void*)recv};
-  VKP_TRY(vkp_prepare_buffers(ctx, bufs, 2));
-  if (count) VKP_NCCL(g_nccl.AllReduce(send, recv, count, ncclFloat32, op, ctx->comm->comm, ctx->stream));
-  return vkp_finish_op(ctx, job);
-}
-
-// One bucket for a set of small tensors (the data-parallel gradient exchange): the
-// all-reduces are grouped into a single NCCL launch and one kernel applies the 1/world scale to all
-// of them, instead of a launch pair per parameter.
-namespace {
-struct ScaleMany {
-  float* ptr[VKP_MAX_BUCKET];
-  unsigned long long count[VKP_MAX_BUCKET];
-  int n;
-};
-__global__ void __launch_bounds__(256) scale_many_kernel(ScaleMany p, float scale) {
-  for (int t = 0; t < p.n; t++) {
-    float* x = p.ptr[t];
-    const size_t n = p.count[t];
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-      x[i] = x[i] * scale;
-  }
-}
-}  // namespace
-
-extern "C" int vkp_comm_allreduce_multi(vkp_ctx* ctx, float* const* bufs, const size_t* counts, int n, int op,
-                                        float scale, vkp_job** job) {
-  VKP_CHECK(ctx && ctx->comm, "vkp_comm_allreduce_multi: communicator not initialised");
-  VKP_CHECK(bufs && counts && n >= 1 && n <= VKP_MAX_BUCKET, "vkp_comm_allreduce_multi: 1..%d tensors", VKP_MAX_BUCKET);
-  VKP_CHECK(op >= 0 && op <= 3, "vkp_comm_allreduce_multi: bad op %d", op);
-  VKP_TRY(vkp_make_current(ctx));
-  std::lock_guard<std::mutex> g(ctx->mu);
-  VKP_TRY(vkp_prepare_buffers(ctx, (void* const*)bufs, n));
-  ScaleMany sm;
-  sm.n = n;
-  size_t most = 0;
-  VKP_NCCL(g_nccl.GroupStart());
-  for (int t = 0; t < n; t++) {
-    sm.ptr[t] = bufs[t];
-    sm.count[t] = counts[t];
-    if (counts[t] > most) most = counts[t];
-    if (counts[t]) {
-      ncclResult_t r = g_nccl.AllReduce(bufs[t], bufs[t], counts[t], ncclFloat32, op, ctx->comm->comm, ctx->stream);
-      if (r != 0) {
-        g_nccl.GroupEnd();
-        return vkp_set_error("ncclAllReduce (grouped) failed: %s", g_nccl.GetErrorString(r));
-      }
-    }
-  }
-  VKP_NCCL(g_nccl.GroupEnd());
-  if (scale != 1.0f && most) {
-    scale_many_kernel<<<vkp_grid_for(ctx, most, 256, 4), 256, 0, ctx->stream>>>(sm, scale);
-    VKP_TRY(vkp_after_launch(ctx, "scale_many"));
-  }
-  return vkp_finish_op(ctx, job);
 }
 
 extern "C" int vkp_comm_allgather(vkp_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank,
@@ -239,6 +187,63 @@ extern "C" int vkp_comm_allgather(vkp_ctx* ctx, const void* send, void* recv, si
 // ======================================================================================================
 namespace {
 
+int ensure_words(vkp_ctx* ctx, vkp_comm_state* st) {
+  if (st->flags) return VKP_OK;
+  VKP_CUDA(cudaMalloc(&st->barrier_word, 256));
+  VKP_CUDA(cudaMemsetAsync(st->barrier_word, 0, 256, ctx->stream));
+  VKP_CUDA(cudaMalloc(&st->flags, sizeof(uint32_t) * 2 * VKP_MAX_RANKS));
+  VKP_CUDA(cudaMemsetAsync(st->flags, 0, sizeof(uint32_t) * 2 * VKP_MAX_RANKS, ctx->stream));
+  return VKP_OK;
+}
+
+// Collective: export `local` (a whole cudaMalloc block) with CUDA IPC and map every peer's block into
+// this process.  Opening a handle can fail on SOME ranks only (IPC not permitted for a device pair, a
+// container without a shared PID namespace ...), and a rank that fell back alone would leave the
+// others waiting for its flags: so every rank contributes 1 (all mapped) or 0 to a min all-reduce
+// and all of them either keep the mappings (VKP_OK, peers[] filled, peers[rank] = local) or drop
+// them and report the same "cudaIpc" error (nothing left mapped; `local` still belongs to the caller).
+int ipc_map_all(vkp_ctx* ctx, vkp_comm_state* st, void* local, void** peers) {
+  VKP_TRY(ensure_words(ctx, st));
+  cudaIpcMemHandle_t mine;
+  VKP_CUDA(cudaIpcGetMemHandle(&mine, local));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  unsigned char* dev_handles = nullptr;
+  VKP_CUDA(cudaMalloc(&dev_handles, 64 * (size_t)st->nranks));
+  VKP_CUDA(cudaMemcpyAsync(dev_handles + 64 * st->rank, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+  VKP_NCCL(g_nccl.AllGather(dev_handles + 64 * st->rank, dev_handles, 64, ncclInt8, st->comm, ctx->stream));
+  std::vector<cudaIpcMemHandle_t> all(st->nranks);
+  VKP_CUDA(cudaMemcpyAsync(all.data(), dev_handles, 64 * (size_t)st->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+  VKP_CUDA(cudaStreamSynchronize(ctx->stream));
+  VKP_CUDA(cudaFree(dev_handles));
+  float ok = 1.0f;
+  std::string why;
+  for (int r = 0; r < st->nranks; r++) {
+    if (r == st->rank) { peers[r] = local; continue; }
+    cudaError_t e = cudaIpcOpenMemHandle(&peers[r], all[r], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      peers[r] = nullptr;
+      ok = 0.0f;
+      if (why.empty()) why = std::string("rank ") + std::to_string(r) + ": " + cudaGetErrorString(e);
+    }
+  }
+  float all_ok = 0.0f;
+  VKP_CUDA(cudaMemcpyAsync(st->barrier_word + 1, &ok, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  VKP_NCCL(g_nccl.AllReduce(st->barrier_word + 1, st->barrier_word + 1, 1, ncclFloat32, ncclMin, st->comm, ctx->stream));
+  VKP_CUDA(cudaMemcpyAsync(&all_ok, st->barrier_word + 1, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  VKP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (all_ok == 1.0f) return VKP_OK;
+  for (int r = 0; r < st->nranks; r++) {
+    if (r != st->rank && peers[r]) cudaIpcCloseMemHandle(peers[r]);
+    peers[r] = nullptr;
+  }
+  // every rank has closed (or never opened) its mapping of this rank's block before the caller frees it
+  VKP_NCCL(g_nccl.AllReduce(st->barrier_word, st->barrier_word, 1, ncclFloat32, ncclSum, st->comm, ctx->stream));
+  VKP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return vkp_set_error("cudaIpcOpenMemHandle failed on at least one rank (%s): peer memory disabled on all ranks",
+                       why.empty() ? "a peer" : why.c_str());
+}
+
 int symm_reserve(vkp_ctx* ctx, vkp_comm_state* st, size_t bytes_one) {
   if (bytes_one <= st->symm_bytes) return VKP_OK;
   // collective growth (all ranks see the same shapes): quiesce, drop the old mappings, re-export
@@ -255,30 +260,376 @@ int symm_reserve(vkp_ctx* ctx, vkp_comm_state* st, size_t bytes_one) {
   st->symm_bytes = 0;
   const size_t one = (bytes_one + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
   VKP_CUDA(cudaMalloc(&st->symm, 2 * one));
-  cudaIpcMemHandle_t mine;
-  VKP_CUDA(cudaIpcGetMemHandle(&mine, st->symm));
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  unsigned char* dev_handles = nullptr;
-  VKP_CUDA(cudaMalloc(&dev_handles, 64 * (size_t)st->nranks));
-  VKP_CUDA(cudaMemcpyAsync(dev_handles + 64 * st->rank, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
-  VKP_NCCL(g_nccl.AllGather(dev_handles + 64 * st->rank, dev_handles, 64, ncclInt8, st->comm, ctx->stream));
-  std::vector<cudaIpcMemHandle_t> all(st->nranks);
-  VKP_CUDA(cudaMemcpyAsync(all.data(), dev_handles, 64 * (size_t)st->nranks, cudaMemcpyDeviceToHost, ctx->stream));
-  VKP_CUDA(cudaStreamSynchronize(ctx->stream));
-  VKP_CUDA(cudaFree(dev_handles));
-  for (int r = 0; r < st->nranks; r++) {
-    if (r == st->rank) { st->peer[r] = st->symm; continue; }
-    cudaError_t e = cudaIpcOpenMemHandle(&st->peer[r], all[r], cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) {
-      st->peer[r] = nullptr;
-      return vkp_set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
-    }
+  if (ipc_map_all(ctx, st, st->symm, st->peer) != VKP_OK) {
+    cudaFree(st->symm);
+    st->symm = nullptr;
+    return VKP_ERR;
   }
   st->symm_bytes = one;
   return VKP_OK;
 }
 
+// ======================================================================================================
+// Peer mailbox: all-reduce of small buffers (reduction partials: 1 .. 64 Ki floats; the data-parallel
+// gradient bucket: a few MB) and barriers as ONE kernel over NVLink peer memory instead of an NCCL
+// launch ("partial kernel's last block writes straight into the send buffer").
+//
+// Every rank owns a mailbox block mapped into all peers (CUDA IPC): two flag sets and two data slots,
+// alternating by call parity.  Call n on rank q:
+//   1. the kernel copies the local operands into q's slot n%2 (or a preceding reduction kernel wrote
+//      its result there directly: `staged`); the last CTA to finish fences (system scope) and stores
+//      n into flags[n%2][q] of EVERY rank (st.release.sys through the mapped pointers);
+//   2. every CTA waits until its own flags[n%2][0..w) all equal n (ld.acquire.sys, local memory);
+//   3. every thread reads its elements from all w slots (volatile 16-byte loads; w-1 of them cross
+//      NVLink) and folds them in rank order 0..w-1 -- the same order on every rank, so all ranks get
+//      bit-identical results -- applies the optional scale and stores to the destination.
+// Slot re-use needs no extra barrier: q overwrites slot n%2 in call n+2 only after it left call n+1,
+// i.e. after every peer pushed flag n+1, which each does (stream order) after finishing its reads of
+// call n.  Grids are at most one CTA per SM, so all CTAs are co-resident and the flag waits cannot
+// starve the copies that satisfy them.
+// ======================================================================================================
+constexpr size_t MBOX_HEADER_BYTES = 4096;
+constexpr size_t MBOX_SLOT_BYTES = (size_t)8 << 20;
+
+struct PeerBucket {
+  const float* in[VKP_MAX_BUCKET];
+  float* out[VKP_MAX_BUCKET];
+  unsigned long long count[VKP_MAX_BUCKET];
+  unsigned long long start[VKP_MAX_BUCKET];   // offset of tensor t in the slot, floats, multiple of 4
+  int n;
+};
+struct PeerMbox {
+  float* slot[VKP_MAX_RANKS];          // this call's data slot of every rank, as mapped here
+  uint32_t* flag_out[VKP_MAX_RANKS];   // &flags[set][my rank] inside rank r's mailbox
+  uint32_t* flag_in;                   // my flags[set][0..w)
+  uint32_t* counter;                   // grid arrival counter (local, zero between calls)
+  uint32_t epoch, w, rank;
+};
+
+template <int OP> struct POp;
+template <> struct POp<0> { static __device__ __forceinline__ float f(float a, float b) { return a + b; } };
+template <> struct POp<1> { static __device__ __forceinline__ float f(float a, float b) { return a * b; } };
+template <> struct POp<2> { static __device__ __forceinline__ float f(float a, float b) { return fmaxf(a, b); } };
+template <> struct POp<3> { static __device__ __forceinline__ float f(float a, float b) { return fminf(a, b); } };
+
+__device__ __forceinline__ float4 ld_vol4(const float* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_vol1(const float* p) {
+  float v;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256)
+peer_allreduce_kernel(const __grid_constant__ PeerBucket b, const __grid_constant__ PeerMbox m, float scale, int staged) {
+  const size_t gtid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t gstride = (size_t)gridDim.x * blockDim.x;
+  float* mine = m.slot[m.rank];
+  // ---- 1. local operands -> my slot ----
+  if (!staged) {
+    for (int t = 0; t < b.n; t++) {
+      const float* src = b.in[t];
+      float* dst = mine + b.start[t];
+      const size_t n = b.count[t];
+      if ((((uintptr_t)src) & 15) == 0) {
+        const size_t n4 = n >> 2;
+        for (size_t i = gtid; i < n4; i += gstride)
+          reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+        for (size_t i = (n4 << 2) + gtid; i < n; i += gstride) dst[i] = src[i];
+      } else {
+        for (size_t i = gtid; i < n; i += gstride) dst[i] = src[i];
+      }
+    }
+  }
+  // ---- publish: the last CTA to arrive raises my flag in every rank's mailbox ----
+  __syncthreads();
+  __shared__ uint32_t s_last;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(m.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x == 0) *m.counter = 0;                 // ready for the next call (stream-ordered)
+    if (threadIdx.x < m.w) {
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(m.flag_out[threadIdx.x]), "r"(m.epoch) : "memory");
+    }
+  }
+  // ---- 2. wait for every rank's flag ----
+  if (threadIdx.x < m.w) {
+    // Ranks reach a collective at different times (first-use allocations, host work): wait up to a
+    // minute of wall clock, then trap -- a lost flag must fail the call, not hang the GPU.
+    uint32_t v;
+    unsigned long long t0 = 0;
+    for (uint32_t spin = 0;; spin++) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(m.flag_in + threadIdx.x) : "memory");
+      if (v == m.epoch) break;
+      __nanosleep(spin < 64 ? 20 : 200);
+      if ((spin & 1023u) == 1023u) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 60000000000ull) __trap();
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 3. fold the w slots in rank order ----
+  for (int t = 0; t < b.n; t++) {
+    float* dst = b.out[t];
+    const size_t n = b.count[t];
+    const size_t off = b.start[t];
+    const bool vec = (((uintptr_t)dst) & 15) == 0;
+    const size_t n4 = vec ? (n >> 2) : 0;
+    for (size_t i = gtid; i < n4; i += gstride) {
+      const size_t o = off + (i << 2);
+      float4 acc = ld_vol4(m.slot[0] + o);
+      for (uint32_t base = 1; base < m.w; base += 7) {
+        float4 v[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++)
+          if (base + j < m.w) v[j] = ld_vol4(m.slot[base + j] + o);
+#pragma unroll
+        for (int j = 0; j < 7; j++)
+          if (base + j < m.w) {
+            acc.x = POp<OP>::f(acc.x, v[j].x); acc.y = POp<OP>::f(acc.y, v[j].y);
+            acc.z = POp<OP>::f(acc.z, v[j].z); acc.w = POp<OP>::f(acc.w, v[j].w);
+          }
+      }
+      if (scale != 1.0f) { acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale; }
+      reinterpret_cast<float4*>(dst)[i] = acc;
+    }
+    for (size_t i = (n4 << 2) + gtid; i < n; i += gstride) {
+      float acc = ld_vol1(m.slot[0] + off + i);
+      for (uint32_t r = 1; r < m.w; r++) acc = POp<OP>::f(acc, ld_vol1(m.slot[r] + off + i));
+      if (scale != 1.0f) acc *= scale;
+      dst[i] = acc;
+    }
+  }
+}
+
+// collective, first use: allocate + map the mailboxes.  Returns with st->mbox_state = 1 or -1.
+int mbox_reserve(vkp_ctx* ctx, vkp_comm_state* st) {
+  if (st->mbox_state != 0) return VKP_OK;
+  static const bool off = getenv("VKP_COMM_PEER") && getenv("VKP_COMM_PEER")[0] == '0';
+  if (off || st->nranks < 2 || st->nranks > VKP_MAX_RANKS) { st->mbox_state = -1; return VKP_OK; }
+  const size_t bytes = MBOX_HEADER_BYTES + 2 * MBOX_SLOT_BYTES;
+  VKP_CUDA(cudaMalloc(&st->mbox, bytes));
+  VKP_CUDA(cudaMemsetAsync(st->mbox, 0, MBOX_HEADER_BYTES, ctx->stream));
+  VKP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ipc_map_all(ctx, st, st->mbox, st->mbox_peer) != VKP_OK) {   // the same verdict on every rank
+    cudaFree(st->mbox);
+    st->mbox = nullptr;
+    st->mbox_state = -1;
+    return VKP_OK;
+  }
+  st->mbox_state = 1;
+  return VKP_OK;
+}
+
+// launches the mailbox kernel for the next epoch; `staged`: slot already holds the local operands
+int peer_launch(vkp_ctx* ctx, vkp_comm_state* st, int op, PeerBucket& b, size_t total_floats, float scale, int staged) {
+  st->mbox_epoch++;
+  const uint32_t set = st->mbox_epoch & 1u;
+  PeerMbox m;
+  memset(&m, 0, sizeof(m));
+  for (int r = 0; r < st->nranks; r++) {
+    char* base = static_cast<char*>(st->mbox_peer[r]);
+    m.slot[r] = reinterpret_cast<float*>(base + MBOX_HEADER_BYTES + set * MBOX_SLOT_BYTES);
+    m.flag_out[r] = reinterpret_cast<uint32_t*>(base) + set * VKP_MAX_RANKS + st->rank;
+  }
+  m.flag_in = reinterpret_cast<uint32_t*>(st->mbox) + set * VKP_MAX_RANKS;
+  m.counter = reinterpret_cast<uint32_t*>(st->mbox) + 2 * VKP_MAX_RANKS;
+  m.epoch = st->mbox_epoch;
+  m.w = (uint32_t)st->nranks;
+  m.rank = (uint32_t)st->rank;
+  // 16 bytes per thread per pass; at most one CTA per SM (co-residency, see above)
+  size_t ctas = (total_floats / 4 + 255) / 256;
+  if (ctas < 1) ctas = 1;
+  if (ctas > (size_t)ctx->sms) ctas = ctx->sms;
+  const unsigned grid = (unsigned)ctas;
+  switch (op) {
+    case 0: peer_allreduce_kernel<0><<<grid, 256, 0, ctx->stream>>>(b, m, scale, staged); break;
+    case 1: peer_allreduce_kernel<1><<<grid, 256, 0, ctx->stream>>>(b, m, scale, staged); break;
+    case 2: peer_allreduce_kernel<2><<<grid, 256, 0, ctx->stream>>>(b, m, scale, staged); break;
+    default: peer_allreduce_kernel<3><<<grid, 256, 0, ctx->stream>>>(b, m, scale, staged); break;
+  }
+  return vkp_after_launch(ctx, "peer_allreduce");
+}
+
+float* mbox_next_slot(vkp_comm_state* st) {   // the slot the NEXT peer_launch will use
+  const uint32_t set = (st->mbox_epoch + 1) & 1u;
+  return reinterpret_cast<float*>(static_cast<char*>(st->mbox) + MBOX_HEADER_BYTES + set * MBOX_SLOT_BYTES);
+}
+
 }  // namespace
+
+// vkp_reduce.cu: local [prev, axis, post] -> [prev, post] reduction into any device pointer
+int vkp_reduce_axis_into(vkp_ctx* ctx, int op, const float* in, float* out, uint32_t prev, uint32_t axis, uint32_t post);
+
+static bool peer_ready(vkp_ctx* ctx, vkp_comm_state* st, size_t floats) {
+  if (st->mbox_off) return false;
+  if (st->mbox_state == 0 && mbox_reserve(ctx, st) != VKP_OK) return false;
+  return st->mbox_state == 1 && (floats + 4 * VKP_MAX_BUCKET) * sizeof(float) <= MBOX_SLOT_BYTES;
+}
+
+extern "C" int vkp_comm_allreduce(vkp_ctx* ctx, const float* send, float* recv, size_t count, int op,
+                                  vkp_job** job) {
+  VKP_CHECK(ctx && ctx->comm, "vkp_comm_allreduce: communicator not initialised");
+  VKP_CHECK(op >= 0 && op <= 3, "vkp_comm_allreduce: bad op %d", op);
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  void* bufs[2] = {(void*)send, (void*)recv};
+  VKP_TRY(vkp_prepare_buffers(ctx, bufs, 2));
+  vkp_comm_state* st = ctx->comm;
+  if (count && peer_ready(ctx, st, count)) {       // one kernel over NVLink peer memory
+    PeerBucket b;
+    memset(&b, 0, sizeof(b));
+    b.in[0] = send; b.out[0] = recv; b.count[0] = count; b.start[0] = 0; b.n = 1;
+    VKP_TRY(peer_launch(ctx, st, op, b, count, 1.0f, 0));
+  } else if (count) {
+    VKP_NCCL(g_nccl.AllReduce(send, recv, count, ncclFloat32, op, st->comm, ctx->stream));
+  }
+  return vkp_finish_op(ctx, job);
+}
+
+// One bucket for a set of small tensors (the data-parallel gradient exchange): ONE
+// mailbox kernel reduces all of them and applies the 1/world scale; buckets that do not fit a
+// mailbox slot (or without peer memory) go through one grouped NCCL launch + one scale kernel.
+namespace {
+struct ScaleMany {
+  float* ptr[VKP_MAX_BUCKET];
+  unsigned long long count[VKP_MAX_BUCKET];
+  int n;
+};
+__global__ void __launch_bounds__(256) scale_many_kernel(ScaleMany p, float scale) {
+  for (int t = 0; t < p.n; t++) {
+    float* x = p.ptr[t];
+    const size_t n = p.count[t];
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+      x[i] = x[i] * scale;
+  }
+}
+}  // namespace
+
+extern "C" int vkp_comm_allreduce_multi(vkp_ctx* ctx, float* const* bufs, const size_t* counts, int n, int op,
+                                        float scale, vkp_job** job) {
+  VKP_CHECK(ctx && ctx->comm, "vkp_comm_allreduce_multi: communicator not initialised");
+  VKP_CHECK(bufs && counts && n >= 1 && n <= VKP_MAX_BUCKET, "vkp_comm_allreduce_multi: 1..%d tensors", VKP_MAX_BUCKET);
+  VKP_CHECK(op >= 0 && op <= 3, "vkp_comm_allreduce_multi: bad op %d", op);
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  VKP_TRY(vkp_prepare_buffers(ctx, (void* const*)bufs, n));
+  vkp_comm_state* st = ctx->comm;
+  size_t total = 0, most = 0;
+  for (int t = 0; t < n; t++) {
+    total += (counts[t] + 3) & ~(size_t)3;
+    if (counts[t] > most) most = counts[t];
+  }
+  if (total && peer_ready(ctx, st, total)) {
+    PeerBucket b;
+    memset(&b, 0, sizeof(b));
+    size_t off = 0;
+    for (int t = 0; t < n; t++) {
+      b.in[t] = bufs[t]; b.out[t] = bufs[t]; b.count[t] = counts[t]; b.start[t] = off;
+      off += (counts[t] + 3) & ~(size_t)3;
+    }
+    b.n = n;
+    VKP_TRY(peer_launch(ctx, st, op, b, total, scale, 0));
+    return vkp_finish_op(ctx, job);
+  }
+  ScaleMany sm;
+  sm.n = n;
+  VKP_NCCL(g_nccl.GroupStart());
+  for (int t = 0; t < n; t++) {
+    sm.ptr[t] = bufs[t];
+    sm.count[t] = counts[t];
+    if (counts[t]) {
+      ncclResult_t r = g_nccl.AllReduce(bufs[t], bufs[t], counts[t], ncclFloat32, op, st->comm, ctx->stream);
+      if (r != 0) {
+        g_nccl.GroupEnd();
+        return vkp_set_error("ncclAllReduce (grouped) failed: %s", g_nccl.GetErrorString(r));
+      }
+    }
+  }
+  VKP_NCCL(g_nccl.GroupEnd());
+  if (scale != 1.0f && most) {
+    scale_many_kernel<<<vkp_grid_for(ctx, most, 256, 4), 256, 0, ctx->stream>>>(sm, scale);
+    VKP_TRY(vkp_after_launch(ctx, "scale_many"));
+  }
+  return vkp_finish_op(ctx, job);
+}
+
+// Sharded reduction with its exchange step fused (SURVEY 8(e) rows "full reduction" / "axis = 0"):
+// the local [prev, axis, post] -> [prev, post] reduction writes its result straight into this rank's
+// mailbox slot (no intermediate array, no copy), and the mailbox kernel folds the w slots into `out`.
+// Full reductions pass prev = 1, axis = n, post = 1.  Results that do not fit a slot (or ranks
+// without peer memory) reduce into `out` and all-reduce it in place with NCCL.
+extern "C" int vkp_comm_reduce_allreduce(vkp_ctx* ctx, int op, const float* in, float* out, uint32_t prev,
+                                         uint32_t axis, uint32_t post, vkp_job** job) {
+  VKP_CHECK(ctx && ctx->comm, "vkp_comm_reduce_allreduce: communicator not initialised");
+  VKP_CHECK(in && out && op >= 0 && op <= 3, "vkp_comm_reduce_allreduce: bad argument");
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  void* bufs[2] = {(void*)in, (void*)out};
+  VKP_TRY(vkp_prepare_buffers(ctx, bufs, 2));
+  vkp_comm_state* st = ctx->comm;
+  const size_t nout = (size_t)prev * post;
+  if (nout == 0) return vkp_finish_op(ctx, job);
+  VKP_CHECK(axis > 0, "vkp_comm_reduce_allreduce: empty axis");
+  if (peer_ready(ctx, st, nout)) {
+    VKP_TRY(vkp_reduce_axis_into(ctx, op, in, mbox_next_slot(st), prev, axis, post));
+    PeerBucket b;
+    memset(&b, 0, sizeof(b));
+    b.in[0] = nullptr; b.out[0] = out; b.count[0] = nout; b.start[0] = 0; b.n = 1;
+    VKP_TRY(peer_launch(ctx, st, op, b, nout, 1.0f, 1));
+  } else {
+    VKP_TRY(vkp_reduce_axis_into(ctx, op, in, out, prev, axis, post));
+    VKP_NCCL(g_nccl.AllReduce(out, out, nout, ncclFloat32, op, st->comm, ctx->stream));
+  }
+  return vkp_finish_op(ctx, job);
+}
+
+// Stream-ordered barrier across the ranks: mailbox flags when peer memory is mapped (one tiny
+// kernel), else a one-word NCCL all-reduce.
+static int comm_barrier_locked(vkp_ctx* ctx, vkp_comm_state* st) {
+  if (peer_ready(ctx, st, 0)) {
+    PeerBucket b;
+    memset(&b, 0, sizeof(b));
+    return peer_launch(ctx, st, 0, b, 0, 1.0f, 1);
+  }
+  VKP_TRY(ensure_words(ctx, st));
+  VKP_NCCL(g_nccl.AllReduce(st->barrier_word, st->barrier_word, 1, ncclFloat32, ncclSum, st->comm, ctx->stream));
+  return VKP_OK;
+}
+
+// mode 0: every later collective goes through NCCL; 1: peer mailbox where it applies (default);
+// -1: query only.  *active = 1 when the mailbox is mapped and selected.  Collective: all ranks must
+// switch at the same point of their streams.
+extern "C" int vkp_comm_peer_mode(vkp_ctx* ctx, int mode, int* active) {
+  VKP_CHECK(ctx && ctx->comm, "vkp_comm_peer_mode: communicator not initialised");
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  vkp_comm_state* st = ctx->comm;
+  if (mode == 0) st->mbox_off = true;
+  if (mode == 1) st->mbox_off = false;
+  if (active) *active = peer_ready(ctx, st, 0) ? 1 : 0;
+  return VKP_OK;
+}
+
+extern "C" int vkp_comm_barrier(vkp_ctx* ctx, vkp_job** job) {
+  VKP_CHECK(ctx && ctx->comm, "vkp_comm_barrier: communicator not initialised");
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  VKP_TRY(comm_barrier_locked(ctx, ctx->comm));
+  return vkp_finish_op(ctx, job);
+}
+
 
 extern "C" int vkp_comm_matmul_allgather(vkp_ctx* ctx, uint32_t M, uint32_t N, uint32_t K, const float* A,
                                          const float* B_shard, float* C, vkp_job** job) {
@@ -294,12 +645,7 @@ extern "C" int vkp_comm_matmul_allgather(vkp_ctx* ctx, uint32_t M, uint32_t N, u
   std::lock_guard<std::mutex> g(ctx->mu);
   void* bufs[3] = {(void*)A, (void*)B_shard, (void*)C};
   VKP_TRY(vkp_prepare_buffers(ctx, bufs, 3));
-  if (!st->flags) {
-    VKP_CUDA(cudaMalloc(&st->barrier_word, 256));
-    VKP_CUDA(cudaMemsetAsync(st->barrier_word, 0, 256, ctx->stream));
-    VKP_CUDA(cudaMalloc(&st->flags, sizeof(uint32_t) * 2 * VKP_MAX_RANKS));
-    VKP_CUDA(cudaMemsetAsync(st->flags, 0, sizeof(uint32_t) * 2 * VKP_MAX_RANKS, ctx->stream));
-  }
+  VKP_TRY(ensure_words(ctx, st));
   const size_t nk = (size_t)N * K, mk = (size_t)M * K;
   VKP_TRY(symm_reserve(ctx, st, nk * sizeof(float)));
   void* ws;
@@ -316,7 +662,7 @@ extern "C" int vkp_comm_matmul_allgather(vkp_ctx* ctx, uint32_t M, uint32_t N, u
   VKP_TRY(vkp_tc_split_lo(ctx, ctx->stream, A, a_lo, mk));
   VKP_TRY(vkp_tc_transpose_split(ctx, ctx->stream, B_shard, kc, N, bt_hi + (size_t)rank * kc, bt_lo + (size_t)rank * kc, K));
   // barrier: every rank's shard is staged (and every rank is done with the copy used two calls ago)
-  VKP_NCCL(g_nccl.AllReduce(st->barrier_word, st->barrier_word, 1, ncclFloat32, ncclSum, st->comm, ctx->stream));
+  VKP_TRY(comm_barrier_locked(ctx, st));
 
   // 2. one kernel: GEMM over all K ranges + the NVLink pulls of the ranges it does not have yet
   vkp_tc_chunks ch{st->flags, st->epoch, 0, rank, w};

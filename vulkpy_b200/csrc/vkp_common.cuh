@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -69,7 +70,9 @@ struct vkp_ctx {
   void* stage[3] = {nullptr, nullptr, nullptr};
   std::mutex mu;
   uint64_t seq = 0;        // number of operations enqueued so far
-  uint64_t done_seq = 0;   // all operations with sequence <= done_seq are known complete
+  // all operations with sequence <= done_seq are known complete; written under `mu`, read without it
+  // by vkp_job_wait / vkp_job_done (fast path of Array.wait())
+  std::atomic<uint64_t> done_seq{0};
   uint64_t kernel_launches = 0;
   bool debug_sync = false;
   int refcount = 1;

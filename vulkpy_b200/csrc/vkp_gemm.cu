@@ -36,7 +36,8 @@ gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, float
   __shared__ float Bs[TK][TN + 4];
   const uint32_t tid = threadIdx.x;
   const uint32_t tx = tid % 16, ty = tid / 16;
-  const uint32_t m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  // M tiles on grid.x (2^31 limit), N tiles on grid.y: tall matrices (M > 65535 * 64) stay legal
+  const uint32_t m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; i++)
@@ -247,11 +248,11 @@ int gemm_skinny(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, ui
   if (!aligned || (uint64_t)M * N * K < (1ull << 22)) return 0;       // small problems keep the tiled kernel
   if (!transA && transB && N <= 16 && K % 4 == 0 && K >= 128 && M >= 1024 && (size_t)N * K * 4 <= 96 * 1024) {
     const size_t smem = (size_t)N * K * 4;
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};      // the opt-in is per device (GPU(0) then GPU(1) in one process)
+    if (!attr[ctx->device & 63]) {
       if (cudaFuncSetAttribute(gemm_skinny_n_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess)
         return vkp_set_error("gemm_skinny: cannot raise the shared-memory limit") ? -1 : -1;
-      attr = true;
+      attr[ctx->device & 63] = true;
     }
     const unsigned grid = (unsigned)std::min<uint64_t>((M + 7) / 8, (uint64_t)ctx->sms * 2);
     gemm_skinny_n_kernel<16><<<grid, 256, smem, ctx->stream>>>(A, B, C, bias, M, N, K, accumulate);
@@ -285,8 +286,8 @@ int gemm_skinny(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, ui
 
 int gemm_simt(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
               const float* B, float* C, const float* bias, int accumulate) {
-  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, 1);
-  VKP_CHECK(grid.y <= 65535, "gemm_simt: M too large for the fallback kernel");
+  dim3 grid((M + TM - 1) / TM, (N + TN - 1) / TN, 1);
+  VKP_CHECK(grid.y <= 65535, "gemm_simt: N = %u is too wide for the fallback kernel (max %d columns)", N, 65535 * TN);
   // skinny problems (few output tiles, long K): split K over blockIdx.z so that every SM has work
   uint32_t splits = 1;
   const uint64_t tiles = (uint64_t)grid.x * grid.y;

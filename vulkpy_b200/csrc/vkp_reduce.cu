@@ -391,10 +391,10 @@ int reduce_axis(vkp_ctx* ctx, const float* in, float* out, uint32_t prev, uint32
         VKP_TRY(vkp_workspace(ctx, 0, (uint64_t)prev * nsplit * post * sizeof(float), &ws));
         dst = (float*)ws;
       }
-      static bool attr_set[4] = {false, false, false, false};
-      if (!attr_set[OP]) {
+      static bool attr_set[64] = {};       // per device: the opt-in does not carry over to GPU(1)
+      if (!attr_set[ctx->device & 63]) {
         VKP_CUDA(cudaFuncSetAttribute(reduce_cols_tma<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
-        attr_set[OP] = true;
+        attr_set[ctx->device & 63] = true;
       }
       reduce_cols_tma<OP><<<(unsigned)jobs, 256, CT_SMEM, ctx->stream>>>(tm, dst, prev, axis, post, nsplit, seg);
       VKP_TRY(vkp_after_launch(ctx, "reduce_cols_tma"));
@@ -501,6 +501,18 @@ int reduce_dispatch(vkp_ctx* ctx, int fam, void* const* bufs, int nbuf, const vo
 }
 
 }  // namespace
+
+// [prev, axis, post] -> [prev, post] into any 16-byte aligned device pointer (vkp_comm.cu reduces a
+// shard's partials straight into the peer mailbox slot the exchange kernel reads)
+int vkp_reduce_axis_into(vkp_ctx* ctx, int op, const float* in, float* out, uint32_t prev, uint32_t axis, uint32_t post) {
+  switch (op) {
+    case VKR_SUM: return reduce_axis<VKR_SUM>(ctx, in, out, prev, axis, post);
+    case VKR_PROD: return reduce_axis<VKR_PROD>(ctx, in, out, prev, axis, post);
+    case VKR_MAX: return reduce_axis<VKR_MAX>(ctx, in, out, prev, axis, post);
+    case VKR_MIN: return reduce_axis<VKR_MIN>(ctx, in, out, prev, axis, post);
+  }
+  return vkp_set_error("vkp_reduce_axis_into: unknown reduction %d", op);
+}
 
 int vkp_launch_reduce(vkp_ctx* ctx, int fam, int sub, void* const* bufs, int nbuf, const void* params,
                       size_t pbytes) {

@@ -507,9 +507,11 @@ extern "C" int vkp_host_view(vkp_ctx* ctx, void* ptr, void** out) {
   }
   void* np = nullptr;
   int rc = alloc_locked(ctx, b->bytes, &np, 0, 1);
-  if (rc != VKP_OK)
+  if (rc != VKP_OK) {
+    const std::string why(vkp_last_error());   // vkp_set_error formats into the buffer this points at
     return vkp_set_error("host view of a %zu-byte buffer: no managed memory left (%s); use vkp_download / "
-                         "Array.to_host() for bulk reads", b->bytes, vkp_last_error());
+                         "Array.to_host() for bulk reads", b->bytes, why.c_str());
+  }
   vkp_block* nb = ctx->blocks[np];
   void* bufs[2] = {ptr, np};
   VKP_TRY(vkp_prepare_buffers(ctx, bufs, 2));   // also orders the copy after copy-engine transfers

@@ -88,6 +88,36 @@ class NcclTransport:
                 a.job = j
         return arrs
 
+    def reduce_allreduce(self, arr, op: str, prev: int, axis: int, post: int, out_shape):
+        """Local ``[prev, axis, post] -> [prev, post]`` reduction of ``arr`` fused with its exchange
+        (``vkp_comm_reduce_allreduce``): the partials land in this rank's peer mailbox and one kernel
+        folds every rank's partials over NVLink.  Returns the replicated result (job attached)."""
+        import vulkpy_b200 as vk
+        b = self._b
+        out = vk.Array(self.gpu, shape=out_shape)
+        job = C.c_void_p()
+        b._check(b.lib.vkp_comm_reduce_allreduce(self.gpu.gpu._ctx, _OPS[op], arr.buffer.ptr, out.buffer.ptr,
+                                                 int(prev), int(axis), int(post), C.byref(job)))
+        out.job = b.Job(job.value)
+        out._keep = [arr]
+        return out
+
+    def barrier(self):
+        """Stream-ordered barrier over the ranks (mailbox flags over NVLink, else a one-word NCCL
+        all-reduce); returns the job."""
+        b = self._b
+        job = C.c_void_p()
+        b._check(b.lib.vkp_comm_barrier(self.gpu.gpu._ctx, C.byref(job)))
+        return b.Job(job.value)
+
+    def peer_mode(self, mode: int = -1) -> bool:
+        """0: route every later collective through NCCL, 1: peer mailbox where it applies (default),
+        -1: query.  Returns whether the mailbox path is mapped and selected.  Collective."""
+        b = self._b
+        active = C.c_int(0)
+        b._check(b.lib.vkp_comm_peer_mode(self.gpu.gpu._ctx, int(mode), C.byref(active)))
+        return bool(active.value)
+
     def allgather(self, arr, out):
         """``out`` (world * len(arr) elements) receives every rank's ``arr`` in rank order."""
         b = self._b
@@ -281,6 +311,17 @@ class ShardedArray:
         self.local.wait()
 
     # -- reductions --------------------------------------------------------------------------------
+    def _reduce0(self, name: str, local, keep_shape):
+        """Reduce ``local`` over its leading axis and over the ranks: replicated ``[1, ...]`` /
+        ``[...]`` array.  One fused call when the transport has it, else reduce + all-reduce."""
+        fused = getattr(self.group.t, "reduce_allreduce", None)
+        rest = tuple(local.shape[1:])
+        if fused is not None:
+            return fused(local, name, 1, int(local.shape[0]), int(np.prod(rest, dtype=np.int64)), keep_shape)
+        part = getattr(local, name)(axis=0)
+        part.reshape(keep_shape)
+        return self.group.t.allreduce(part, name)
+
     def _reduce(self, name: str, axis, keepdims: bool, rebroadcast: bool):
         nd = len(self.shape)
         if rebroadcast:
@@ -289,21 +330,30 @@ class ShardedArray:
             a = axis % nd
             if a != 0:
                 return self._like(getattr(self.local, name)(axis=a, rebroadcast=True))
-            part = getattr(self.local, name)(axis=0, keepdims=True)         # [1, ...] partial
-            self.group.t.allreduce(part, name)
+            part = self._reduce0(name, self.local, (1,) + tuple(self.local.shape[1:]))     # [1, ...]
             return self._like(part.broadcast_to(self.local.shape))
         if axis is None:
-            part = getattr(self.local, name)()                                # (1,) partial
-            self.group.t.allreduce(part, name)                                # one float
+            fused = getattr(self.group.t, "reduce_allreduce", None)
+            n_local = int(np.prod(self.local.shape, dtype=np.int64))
+            if fused is not None:
+                part = fused(self.local, name, 1, n_local, 1, (1,))               # one float per rank
+            else:
+                part = getattr(self.local, name)()                                # (1,) partial
+                self.group.t.allreduce(part, name)
             if keepdims:
                 part.reshape((1,) * nd)
             return part                                                        # replicated
         axes = sorted({int(a) % nd for a in np.asarray(axis).reshape(-1)})
-        local = getattr(self.local, name)(axis=axes, keepdims=keepdims)
         if 0 not in axes:
+            local = getattr(self.local, name)(axis=axes, keepdims=keepdims)
             return ShardedArray(self.group, local, (self.shape[0],) + tuple(local.shape[1:]))
-        self.group.t.allreduce(local, name)                                    # `post` floats
-        return local                                                           # replicated
+        inner = [a for a in axes if a != 0]
+        local = getattr(self.local, name)(axis=inner, keepdims=True) if inner else self.local
+        shape = [1 if a in axes else s for a, s in enumerate(self.shape)]          # keepdims form
+        out = self._reduce0(name, local, tuple(shape))                             # `post` floats
+        if not keepdims:
+            out.reshape(tuple(s for a, s in enumerate(shape) if a not in axes) or (1,))
+        return out                                                             # replicated
 
     def sum(self, axis=None, keepdims=False, rebroadcast=False): return self._reduce("sum", axis, keepdims, rebroadcast)
     def prod(self, axis=None, keepdims=False, rebroadcast=False): return self._reduce("prod", axis, keepdims, rebroadcast)

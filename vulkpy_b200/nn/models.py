@@ -39,14 +39,25 @@ class Sequence:
                 dx = layer.backward(dx)
 
     def _known_parameters(self):
-        """(parameters of the layers that expose them, the other layers)."""
-        params, rest = [], []
+        """(parameters the one-launch zero_grad / update may own, the other layers).
+
+        Only layers whose ``zero_grad`` / ``update`` / ``_parameters`` are the stock ``Dense`` ones are
+        taken over: a subclass that overrides them (frozen layer, clipping, a regularizer step) keeps
+        being called, as the reference's ``Sequence`` always does (models.py:46-78).  A parameter
+        shared by two layers (weight tying) is listed once."""
+        from .layers import Dense
+        params, rest, seen = [], [], set()
         for layer in self.L:
-            ps = getattr(layer, "_parameters", None)
-            if ps is None:
+            t = type(layer)
+            stock = (getattr(t, "_parameters", None) is Dense._parameters and t.update is Dense.update
+                     and t.zero_grad is Dense.zero_grad)
+            if not stock:
                 rest.append(layer)
-            else:
-                params.extend(p for p in ps() if p.grad is not None)
+                continue
+            for p in layer._parameters():
+                if p.grad is not None and id(p) not in seen:
+                    seen.add(id(p))
+                    params.append(p)
         return params, rest
 
     def _zero_grad(self):
