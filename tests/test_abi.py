@@ -119,3 +119,20 @@ def test_product_does_not_import_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("vulkpy_oracle", "oracle") or f == "__none__", \
                     f"{f} mentions the oracle"
+
+
+def test_compat_shim_exports_the_reference_extension_surface():
+    """vulkpy_b200/compat/_vkarray.py defines every name the reference's Python layer takes from its
+    pybind11 module (vkarray.py:26-44, random.py:26; _vkarray.cc:756-898) -- no device needed."""
+    import importlib
+    shim = importlib.import_module("vulkpy_b200.compat._vkarray")
+    for name in ("createGPU", "DataShape", "VectorParams", "MultiVector2Params", "VectorScalarParams",
+                 "VectorScalar2Params", "MatMulParams", "AxisReductionParams", "BroadcastParams",
+                 "Multi3BroadcastParams", "BatchAffineParams", "AxisGatherParams", "VectorRangeParams", "Job",
+                 "Buffer", "Shape", "GPU", "Xoshiro128pp"):
+        assert hasattr(shim, name), name
+    for meth in ("createBuffer", "createU32Buffer", "toBuffer", "toU32Buffer", "submit", "wait", "flush", "canSubgroupArithmetic"):
+        assert callable(getattr(shim.GPU, meth))
+    assert shim.VectorScalar2Params(7, 1.5, 2.5).scalar1 == 2.5 and shim.AxisGatherParams(1, 2, 3, 4).index_size == 4
+    assert shim._first_shape_binding("x/add_broadcast.spv") == 3 and shim._first_shape_binding("iadd_broadcast") == 2
+    assert shim._first_shape_binding("broadcast.spv") == 2 and shim._first_shape_binding("add.spv") is None

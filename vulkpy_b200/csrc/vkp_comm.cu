@@ -94,7 +94,7 @@ struct vkp_comm_state {
   void* peer[VKP_MAX_RANKS] = {};         // peer[r] = rank r's symm mapped here (peer[rank] = symm)
   uint64_t calls = 0;
   // ---- peer mailbox: small all-reduces / barriers as ONE kernel over NVLink peer memory ----
-  // block layout: [flags set 0: 16 words][flags set 1: 16 words][grid counter] ... pad to 4 KiB,
+  // block layout: flags[set 2][phase 2][16 ranks] (64 words), two grid counters ... pad to 4 KiB,
   // then two data slots (call parity) of MBOX_SLOT_BYTES each
   void* mbox = nullptr;
   void* mbox_peer[VKP_MAX_RANKS] = {};    // mbox_peer[r] = rank r's mailbox mapped here
@@ -300,11 +300,70 @@ struct PeerBucket {
 };
 struct PeerMbox {
   float* slot[VKP_MAX_RANKS];          // this call's data slot of every rank, as mapped here
-  uint32_t* flag_out[VKP_MAX_RANKS];   // &flags[set][my rank] inside rank r's mailbox
-  uint32_t* flag_in;                   // my flags[set][0..w)
-  uint32_t* counter;                   // grid arrival counter (local, zero between calls)
+  uint32_t* flag_out[VKP_MAX_RANKS];   // &flags[set][phase 0][my rank] inside rank r's mailbox (phase 1: + 16 words)
+  uint32_t* flag_in;                   // my flags[set][phase 0][0..w)                            (phase 1: + 16 words)
+  uint32_t* counter;                   // grid arrival counters (local, zero between calls), one per phase
   uint32_t epoch, w, rank;
 };
+
+// the last CTA to arrive at `counter` raises this rank's flag in every rank's mailbox
+__device__ __forceinline__ void mbox_publish(uint32_t* counter, uint32_t* const* flag_out, uint32_t phase,
+                                             uint32_t epoch, uint32_t w) {
+  __syncthreads();
+  __shared__ uint32_t s_last[2];
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last[phase] = (atomicAdd(counter + phase, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last[phase]) {
+    if (threadIdx.x == 0) counter[phase] = 0;             // ready for the next call (stream-ordered)
+    if (threadIdx.x < w) {
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag_out[threadIdx.x] + phase * VKP_MAX_RANKS), "r"(epoch)
+                   : "memory");
+    }
+  }
+}
+
+// every CTA waits until its own flags of this phase all carry `epoch`
+__device__ __forceinline__ void mbox_wait(const uint32_t* flag_in, uint32_t phase, uint32_t epoch, uint32_t w) {
+  if (threadIdx.x < w) {
+    // Ranks reach a collective at different times (first-use allocations, host work): wait up to a
+    // minute of wall clock, then trap -- a lost flag must fail the call, not hang the GPU.
+    uint32_t v;
+    unsigned long long t0 = 0;
+    for (uint32_t spin = 0;; spin++) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag_in + phase * VKP_MAX_RANKS + threadIdx.x) : "memory");
+      if (v == epoch) break;
+      __nanosleep(spin < 64 ? 20 : 200);
+      if ((spin & 1023u) == 1023u) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 60000000000ull) __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// local operands -> this rank's slot
+__device__ __forceinline__ void mbox_stage(const PeerBucket& b, float* mine, size_t gtid, size_t gstride) {
+  for (int t = 0; t < b.n; t++) {
+    const float* src = b.in[t];
+    float* dst = mine + b.start[t];
+    const size_t n = b.count[t];
+    if ((((uintptr_t)src) & 15) == 0) {
+      const size_t n4 = n >> 2;
+      for (size_t i = gtid; i < n4; i += gstride)
+        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+      for (size_t i = (n4 << 2) + gtid; i < n; i += gstride) dst[i] = src[i];
+    } else {
+      for (size_t i = gtid; i < n; i += gstride) dst[i] = src[i];
+    }
+  }
+}
 
 template <int OP> struct POp;
 template <> struct POp<0> { static __device__ __forceinline__ float f(float a, float b) { return a + b; } };
@@ -328,57 +387,11 @@ __global__ void __launch_bounds__(256)
 peer_allreduce_kernel(const __grid_constant__ PeerBucket b, const __grid_constant__ PeerMbox m, float scale, int staged) {
   const size_t gtid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const size_t gstride = (size_t)gridDim.x * blockDim.x;
-  float* mine = m.slot[m.rank];
-  // ---- 1. local operands -> my slot ----
-  if (!staged) {
-    for (int t = 0; t < b.n; t++) {
-      const float* src = b.in[t];
-      float* dst = mine + b.start[t];
-      const size_t n = b.count[t];
-      if ((((uintptr_t)src) & 15) == 0) {
-        const size_t n4 = n >> 2;
-        for (size_t i = gtid; i < n4; i += gstride)
-          reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
-        for (size_t i = (n4 << 2) + gtid; i < n; i += gstride) dst[i] = src[i];
-      } else {
-        for (size_t i = gtid; i < n; i += gstride) dst[i] = src[i];
-      }
-    }
-  }
-  // ---- publish: the last CTA to arrive raises my flag in every rank's mailbox ----
-  __syncthreads();
-  __shared__ uint32_t s_last;
-  if (threadIdx.x == 0) {
-    __threadfence();
-    s_last = (atomicAdd(m.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (s_last) {
-    if (threadIdx.x == 0) *m.counter = 0;                 // ready for the next call (stream-ordered)
-    if (threadIdx.x < m.w) {
-      __threadfence_system();
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(m.flag_out[threadIdx.x]), "r"(m.epoch) : "memory");
-    }
-  }
+  // ---- 1. local operands -> my slot; the last CTA raises my flag in every rank's mailbox ----
+  if (!staged) mbox_stage(b, m.slot[m.rank], gtid, gstride);
+  mbox_publish(m.counter, m.flag_out, 0, m.epoch, m.w);
   // ---- 2. wait for every rank's flag ----
-  if (threadIdx.x < m.w) {
-    // Ranks reach a collective at different times (first-use allocations, host work): wait up to a
-    // minute of wall clock, then trap -- a lost flag must fail the call, not hang the GPU.
-    uint32_t v;
-    unsigned long long t0 = 0;
-    for (uint32_t spin = 0;; spin++) {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(m.flag_in + threadIdx.x) : "memory");
-      if (v == m.epoch) break;
-      __nanosleep(spin < 64 ? 20 : 200);
-      if ((spin & 1023u) == 1023u) {
-        unsigned long long now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 60000000000ull) __trap();
-      }
-    }
-  }
-  __syncthreads();
+  mbox_wait(m.flag_in, 0, m.epoch, m.w);
   // ---- 3. fold the w slots in rank order ----
   for (int t = 0; t < b.n; t++) {
     float* dst = b.out[t];
@@ -413,6 +426,79 @@ peer_allreduce_kernel(const __grid_constant__ PeerBucket b, const __grid_constan
   }
 }
 
+// Two-shot form for buckets where NVLink traffic matters (the gradient bucket: a few MB on 4-8 ranks):
+// after the operands are staged (phase 0), rank q folds ONLY slice q of the concatenated bucket from
+// all w slots (reduce-scatter: (w-1)/w of the bucket crosses NVLink per rank instead of w-1 buckets),
+// writes it to its outputs and to a result region behind its data slot, raises the phase-1 flags, and
+// pulls the other w-1 reduced slices from their owners (all-gather).  Each slice is reduced once, by
+// its owner, in rank order: results are bit-identical on all ranks.
+__device__ __forceinline__ void mbox_store4(const PeerBucket& b, size_t o, float4 v) {
+  for (int t = 0; t < b.n; t++) {
+    const size_t st = b.start[t];
+    const size_t n = b.count[t];
+    if (o >= st && o < st + n) {
+      float* dst = b.out[t] + (o - st);
+      if (o - st + 4 <= n && (((uintptr_t)dst) & 15) == 0) {
+        *reinterpret_cast<float4*>(dst) = v;
+      } else {
+        const float e[4] = {v.x, v.y, v.z, v.w};
+        for (int k = 0; k < 4 && o - st + k < n; k++) dst[k] = e[k];
+      }
+      return;
+    }
+  }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256)
+peer_allreduce2_kernel(const __grid_constant__ PeerBucket b, const __grid_constant__ PeerMbox m, float scale,
+                       unsigned long long total, unsigned long long slice) {
+  const size_t gtid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t gstride = (size_t)gridDim.x * blockDim.x;
+  mbox_stage(b, m.slot[m.rank], gtid, gstride);
+  mbox_publish(m.counter, m.flag_out, 0, m.epoch, m.w);
+  mbox_wait(m.flag_in, 0, m.epoch, m.w);
+  // ---- reduce-scatter: my slice ----
+  {
+    const size_t lo = (size_t)m.rank * slice;
+    const size_t hi = lo + slice < total ? lo + slice : total;
+    float* res = m.slot[m.rank] + total;
+    const size_t n4 = hi > lo ? (hi - lo) >> 2 : 0;
+    for (size_t i = gtid; i < n4; i += gstride) {
+      const size_t o = lo + (i << 2);
+      float4 acc = ld_vol4(m.slot[0] + o);
+      for (uint32_t base = 1; base < m.w; base += 7) {
+        float4 v[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++)
+          if (base + j < m.w) v[j] = ld_vol4(m.slot[base + j] + o);
+#pragma unroll
+        for (int j = 0; j < 7; j++)
+          if (base + j < m.w) {
+            acc.x = POp<OP>::f(acc.x, v[j].x); acc.y = POp<OP>::f(acc.y, v[j].y);
+            acc.z = POp<OP>::f(acc.z, v[j].z); acc.w = POp<OP>::f(acc.w, v[j].w);
+          }
+      }
+      if (scale != 1.0f) { acc.x *= scale; acc.y *= scale; acc.z *= scale; acc.w *= scale; }
+      reinterpret_cast<float4*>(res)[i] = acc;
+      mbox_store4(b, o, acc);
+    }
+  }
+  mbox_publish(m.counter, m.flag_out, 1, m.epoch, m.w);
+  mbox_wait(m.flag_in, 1, m.epoch, m.w);
+  // ---- all-gather: the other ranks' reduced slices, ring order (every owner serves one reader at a time) ----
+  for (uint32_t j = 1; j < m.w; j++) {
+    uint32_t r = m.rank + j;
+    if (r >= m.w) r -= m.w;
+    const size_t lo = (size_t)r * slice;
+    if (lo >= total) continue;
+    const size_t hi = lo + slice < total ? lo + slice : total;
+    const float* res = m.slot[r] + total;
+    const size_t n4 = (hi - lo) >> 2;
+    for (size_t i = gtid; i < n4; i += gstride) mbox_store4(b, lo + (i << 2), ld_vol4(res + (i << 2)));
+  }
+}
+
 // collective, first use: allocate + map the mailboxes.  Returns with st->mbox_state = 1 or -1.
 int mbox_reserve(vkp_ctx* ctx, vkp_comm_state* st) {
   if (st->mbox_state != 0) return VKP_OK;
@@ -441,10 +527,10 @@ int peer_launch(vkp_ctx* ctx, vkp_comm_state* st, int op, PeerBucket& b, size_t 
   for (int r = 0; r < st->nranks; r++) {
     char* base = static_cast<char*>(st->mbox_peer[r]);
     m.slot[r] = reinterpret_cast<float*>(base + MBOX_HEADER_BYTES + set * MBOX_SLOT_BYTES);
-    m.flag_out[r] = reinterpret_cast<uint32_t*>(base) + set * VKP_MAX_RANKS + st->rank;
+    m.flag_out[r] = reinterpret_cast<uint32_t*>(base) + set * 2 * VKP_MAX_RANKS + st->rank;
   }
-  m.flag_in = reinterpret_cast<uint32_t*>(st->mbox) + set * VKP_MAX_RANKS;
-  m.counter = reinterpret_cast<uint32_t*>(st->mbox) + 2 * VKP_MAX_RANKS;
+  m.flag_in = reinterpret_cast<uint32_t*>(st->mbox) + set * 2 * VKP_MAX_RANKS;
+  m.counter = reinterpret_cast<uint32_t*>(st->mbox) + 4 * VKP_MAX_RANKS;
   m.epoch = st->mbox_epoch;
   m.w = (uint32_t)st->nranks;
   m.rank = (uint32_t)st->rank;
@@ -453,6 +539,21 @@ int peer_launch(vkp_ctx* ctx, vkp_comm_state* st, int op, PeerBucket& b, size_t 
   if (ctas < 1) ctas = 1;
   if (ctas > (size_t)ctx->sms) ctas = ctx->sms;
   const unsigned grid = (unsigned)ctas;
+  // two-shot (reduce-scatter + all-gather) once the bucket is big enough for NVLink bytes to matter
+  static const size_t two_shot_min = getenv("VKP_COMM_TWO_SHOT_MIN") ? (size_t)atoll(getenv("VKP_COMM_TWO_SHOT_MIN")) : 32768;
+  size_t slice = ((total_floats + st->nranks - 1) / st->nranks + 3) & ~(size_t)3;
+  const int two_shot_ranks = getenv("VKP_COMM_TWO_SHOT_MIN") ? 2 : 3;   // 2 ranks: same NVLink bytes either way
+  const bool two = !staged && st->nranks >= two_shot_ranks && total_floats >= two_shot_min &&
+                   (total_floats + slice) * sizeof(float) <= MBOX_SLOT_BYTES;
+  if (two) {
+    switch (op) {
+      case 0: peer_allreduce2_kernel<0><<<grid, 256, 0, ctx->stream>>>(b, m, scale, total_floats, slice); break;
+      case 1: peer_allreduce2_kernel<1><<<grid, 256, 0, ctx->stream>>>(b, m, scale, total_floats, slice); break;
+      case 2: peer_allreduce2_kernel<2><<<grid, 256, 0, ctx->stream>>>(b, m, scale, total_floats, slice); break;
+      default: peer_allreduce2_kernel<3><<<grid, 256, 0, ctx->stream>>>(b, m, scale, total_floats, slice); break;
+    }
+    return vkp_after_launch(ctx, "peer_allreduce(two-shot)");
+  }
   switch (op) {
     case 0: peer_allreduce_kernel<0><<<grid, 256, 0, ctx->stream>>>(b, m, scale, staged); break;
     case 1: peer_allreduce_kernel<1><<<grid, 256, 0, ctx->stream>>>(b, m, scale, staged); break;
@@ -491,7 +592,7 @@ extern "C" int vkp_comm_allreduce(vkp_ctx* ctx, const float* send, float* recv, 
     PeerBucket b;
     memset(&b, 0, sizeof(b));
     b.in[0] = send; b.out[0] = recv; b.count[0] = count; b.start[0] = 0; b.n = 1;
-    VKP_TRY(peer_launch(ctx, st, op, b, count, 1.0f, 0));
+    VKP_TRY(peer_launch(ctx, st, op, b, (count + 3) & ~(size_t)3, 1.0f, 0));
   } else if (count) {
     VKP_NCCL(g_nccl.AllReduce(send, recv, count, ncclFloat32, op, st->comm, ctx->stream));
   }

@@ -213,16 +213,29 @@ ew_tab_kernel(F f, const __grid_constant__ vkpm::MathCoef coef, const float* in0
   const float4* v1 = reinterpret_cast<const float4*>(in1);
   float4* vo = reinterpret_cast<float4*>(out);
   const size_t base = (size_t)blockIdx.x * EW_TILE_VEC + threadIdx.x;
-  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
   float4 a[EW_UNROLL], b[EW_UNROLL];
+  // Whole tile in range (every CTA but the last): all loads are issued before the first use and
+  // carry no predicate -- the predicated form below made the compiler load one vector, evaluate it,
+  // and only then fetch the other three (two exposed memory latencies per CTA:
+  // profiles/r02_pow_sass_notes.md).  The test is CTA-uniform, the shuffles stay warp-collective.
+  const bool full = (size_t)(blockIdx.x + 1) * EW_TILE_VEC <= nvec;
+  if (full) {
 #pragma unroll
-  for (int u = 0; u < EW_UNROLL; u++) {
-    const size_t i = base + (size_t)u * EW_BLOCK;
-    a[u] = one;
-    b[u] = one;
-    if (i < nvec) {
-      a[u] = v0[i];
-      if (NIN > 1) b[u] = v1[i];
+    for (int u = 0; u < EW_UNROLL; u++) {
+      a[u] = v0[base + (size_t)u * EW_BLOCK];
+      if (NIN > 1) b[u] = v1[base + (size_t)u * EW_BLOCK];
+    }
+  } else {
+    const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; u++) {
+      const size_t i = base + (size_t)u * EW_BLOCK;
+      a[u] = one;
+      b[u] = one;
+      if (i < nvec) {
+        a[u] = v0[i];
+        if (NIN > 1) b[u] = v1[i];
+      }
     }
   }
 #pragma unroll
@@ -235,7 +248,7 @@ ew_tab_kernel(F f, const __grid_constant__ vkpm::MathCoef coef, const float* in0
     r.z = f.fast(tab, a[u].z, b[u].z, sp);
     r.w = f.fast(tab, a[u].w, b[u].w, sp);
     if (sp) r = redo_slow(f, a[u], b[u]);   // rare: zero / negative / denormal / inf / nan / overflow
-    if (i < nvec) vo[i] = r;
+    if (full || i < nvec) vo[i] = r;
   }
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x < 32) {   // n % 4 tail, whole first warp participates
     const size_t i = (nvec << 2) + threadIdx.x;

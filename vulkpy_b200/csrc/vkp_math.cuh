@@ -82,9 +82,12 @@ VKP_HD float rcp_seed(float d) {
 // i.e. exp(-100) = 3.8e-44 must come out as 0: GPU Vulkan drivers flush float32 denormals.
 VKP_HD float d2f_ftz(double x) {
 #if defined(__CUDA_ARCH__)
-  float r;
-  asm("cvt.rn.ftz.f32.f64 %0, %1;" : "=f"(r) : "d"(x));
-  return r;
+  // cvt.rn.ftz.f32.f64 compiles to F2F + DSETP + a predicated FMUL; round first (subnormal results are
+  // correctly rounded subnormals), then let an FTZ add of -0 flush them: F2F + FADD, nothing on the FP64 pipe
+  float r, z;
+  asm("cvt.rn.f32.f64 %0, %1;" : "=f"(r) : "d"(x));
+  asm("add.ftz.f32 %0, %1, 0f80000000;" : "=f"(z) : "f"(r));
+  return z;
 #else
   const float r = (float)x;
   if (r < 1.17549435e-38f && r > -1.17549435e-38f) return std::copysign(0.0f, r);
@@ -209,8 +212,10 @@ VKP_HD float pow_f(float x, float y) {
 // =============================================================================================
 // Table-driven fast paths for exp / exp2 / pow (same binary64 accuracy, ~2.5x fewer instructions)
 //
-//   log2(x): x = 2^e * m with m in [2/3, 4/3), i = 5 bits of (bits(x) - bits(2/3)), rc_i = float(1 / centre_i):
-//            r = m * rc_i - 1 is exact in binary64 (|r| <= 2^-6), log2(m) = l2_i + log2(1 + r)
+//   log2(x): x = 2^e * m with m in [2/3, 4/3), i = 5 bits of (bits(x) - bits(2/3)), rc_i = 1 / centre_i rounded to
+//            21 significant bits (scripts/fit/gen_log_tables.py: its binary64 form has a zero low word, so the
+//            device shuffles ONE word per lookup and needs no float -> double conversion):
+//            r = m * rc_i - 1 is exact in binary64 (|r| <= 2^-5.6), log2(m) = l2_i + log2(1 + r)
 //            with l2_i = -log2(rc_i) and a degree-8 series (truncation < 2^-56 absolute).
 //   2^t    : k = rint(32 t), r = t - k/32 (|r| <= 1/64), 2^t = 2^(k>>5) * e2[k & 31] * 2^r with a
 //            degree-4 series for 2^r (truncation < 2^-39 relative).
@@ -219,27 +224,27 @@ VKP_HD float pow_f(float x, float y) {
 // conflicts); on the host (tests) the accessor indexes plain arrays.
 // =============================================================================================
 #define VKPM_TABLE_RC \
-  0x1.7b8d58p+0f, 0x1.72f560p+0f, 0x1.6abed2p+0f, 0x1.62e35ap+0f, \
-  0x1.5b5d2cp+0f, 0x1.5426fap+0f, 0x1.4d3be2p+0f, 0x1.469764p+0f, \
-  0x1.40355ep+0f, 0x1.3a11fep+0f, 0x1.3429bcp+0f, 0x1.2e794ep+0f, \
-  0x1.28fdaep+0f, 0x1.23b40ap+0f, 0x1.1e99c0p+0f, 0x1.19ac62p+0f, \
-  0x1.14e9a6p+0f, 0x1.104f6cp+0f, 0x1.0bdbbap+0f, 0x1.078cb2p+0f, \
-  0x1.036098p+0f, 0x1.000000p+0f, 0x1.edfd6ep-1f, 0x1.df881ep-1f, \
-  0x1.d1e550p-1f, 0x1.c5038ap-1f, 0x1.b8d33cp-1f, 0x1.ad466ep-1f, \
-  0x1.a2509ep-1f, 0x1.97e682p-1f, 0x1.8dfdeep-1f, 0x1.848daap-1f,
+  0x1.7b8d600000000p+0, 0x1.72f5600000000p+0, 0x1.6abed00000000p+0, 0x1.62e3600000000p+0, \
+  0x1.5b5d300000000p+0, 0x1.5427000000000p+0, 0x1.4d3be00000000p+0, 0x1.4697600000000p+0, \
+  0x1.4035600000000p+0, 0x1.3a12000000000p+0, 0x1.3429c00000000p+0, 0x1.2e79500000000p+0, \
+  0x1.28fdb00000000p+0, 0x1.23b4100000000p+0, 0x1.1e99c00000000p+0, 0x1.19ac600000000p+0, \
+  0x1.14e9a00000000p+0, 0x1.104f700000000p+0, 0x1.0bdbc00000000p+0, 0x1.078cb00000000p+0, \
+  0x1.0360900000000p+0, 0x1.0000000000000p+0, 0x1.edfd700000000p-1, 0x1.df88200000000p-1, \
+  0x1.d1e5500000000p-1, 0x1.c503900000000p-1, 0x1.b8d3400000000p-1, 0x1.ad46700000000p-1, \
+  0x1.a250a00000000p-1, 0x1.97e6800000000p-1, 0x1.8dfdf00000000p-1, 0x1.848db00000000p-1, \
 
 #define VKPM_TABLE_L2 \
-  -0x1.22e51bf786747p-1, -0x1.11fa756958969p-1, -0x1.0170c49dfb85ap-1, \
-  -0x1.e28796d387875p-2, -0x1.c2df1d2dc1369p-2, -0x1.a3e0b1f0c9c8dp-2, \
-  -0x1.8585554efb974p-2, -0x1.67c66c03c74fap-2, -0x1.4a9dd0855f1adp-2, \
-  -0x1.2e05b3d628a52p-2, -0x1.11f89dd8976b3p-2, -0x1.ece29b78e02d5p-3, \
-  -0x1.b6d5dc177eccep-3, -0x1.81c1ba1fe2fbfp-3, -0x1.4d9d55c042cb5p-3, \
-  -0x1.1a607f494729ep-3, -0x1.d00666c2559fcp-4, -0x1.6cfbea8d29ec0p-4, \
-  -0x1.0b9383ba4fae4p-4, -0x1.577eeeb48a61dp-5, -0x1.35cc168bceadfp-6, \
-  0x0.0p+0, 0x1.a73741c179688p-5, 0x1.8324e25e77944p-4, \
-  0x1.16cecdbed61d6p-3, 0x1.69a75a8aeaa41p-3, 0x1.ba3d595f5f453p-3, \
-  0x1.0457d271dfeebp-2, 0x1.2a8d3ba84259dp-2, 0x1.4fcc0beef0a7fp-2, \
-  0x1.74205c39d6788p-2, 0x1.97957155739efp-2,
+  -0x1.22e52b8935c71p-1, -0x1.11fa756958969p-1, -0x1.0170c08b65159p-1, \
+  -0x1.e287afcd8d8b6p-2, -0x1.c2df2e30c514dp-2, -0x1.a3e0cbffcf234p-2, \
+  -0x1.85854c712481bp-2, -0x1.67c659ebc3ee4p-2, -0x1.4a9dd9bf8b49fp-2, \
+  -0x1.2e05bd3e7f63dp-2, -0x1.11f8b10599dfep-2, -0x1.ece2af0237decp-3, \
+  -0x1.b6d5effd2b9bfp-3, -0x1.81c1f6e5e8252p-3, -0x1.4d9d55c042cb5p-3, \
+  -0x1.1a606a4e9af49p-3, -0x1.d005e6b84c9d8p-4, -0x1.6cfc415a83409p-4, \
+  -0x1.0b94081853b9ep-4, -0x1.577e950487283p-5, -0x1.35c93d810bd45p-6, \
+  0x0.0p+0, 0x1.a73711e8083d2p-5, 0x1.8324c9b914bc7p-4, \
+  0x1.16cecdbed61d6p-3, 0x1.69a73368d7dc5p-3, 0x1.ba3d3e8ffde41p-3, \
+  0x1.0457cb8fdd002p-2, 0x1.2a8d349814dfcp-2, 0x1.4fcc132d48bcbp-2, \
+  0x1.742054cd53df9p-2, 0x1.97955a856c4c6p-2, \
 
 #define VKPM_TABLE_E2 \
   0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, \
@@ -282,9 +287,10 @@ struct HostTables {
   double lc(int i) const { return c_.lc[i]; }
   double ec(int i) const { return c_.ec[i]; }
   double log2e() const { return c_.log2e; }
-  float rc(int i) const { static const float t[32] = {VKPM_TABLE_RC}; return t[i]; }
-  double l2(int i) const { static const double t[32] = {VKPM_TABLE_L2}; return t[i]; }
-  double e2(int i) const { static const double t[32] = {VKPM_TABLE_E2}; return t[i]; }
+  // like a warp shuffle, the accessors look at the low 5 bits of the index only
+  double rc(uint32_t i) const { static const double t[32] = {VKPM_TABLE_RC}; return t[i & 31u]; }
+  double l2(uint32_t i) const { static const double t[32] = {VKPM_TABLE_L2}; return t[i & 31u]; }
+  double e2(uint32_t i) const { static const double t[32] = {VKPM_TABLE_E2}; return t[i & 31u]; }
 };
 
 VKP_HD double hilo2d(uint32_t hi, uint32_t lo) {
@@ -309,6 +315,12 @@ VKP_HD uint32_t lo32(double x) {
 #endif
 }
 
+// (double)e for |e| < 2^31 without the conversion unit (I2F.F64 runs on the quarter-rate XU pipe): the
+// binary64 number with high word 0x43300000 and low word e + 2^31 is 2^52 + 2^31 + e exactly.
+VKP_HD double small_int_to_double(int e) {
+  return hilo2d(0x43300000u, (uint32_t)e ^ 0x80000000u) - 4503601774854144.0;
+}
+
 // log2 of the positive NORMAL float whose bits are u.  x = 2^e * m with m in [2/3, 4/3) so that
 // inputs near 1 have e = 0; interval 21 contains 1.0 and has rc = 1, l2 = 0 exactly, hence
 // log2(1) = 0, log2(2^n) = n and full RELATIVE accuracy around 1.  |r| <= 0.0209; truncation
@@ -317,17 +329,17 @@ template <class TA>
 VKP_HD double log2_tab(uint32_t u, const TA& ta) {
   const uint32_t d = u - 0x3f2aaaabu;                       // bits of 2/3
   const int e = (int)d >> 23;
-  const int i = (int)((d >> 18) & 31u);
-  const uint32_t mb = u - ((uint32_t)e << 23);              // float bits of m
-  const double md = hilo2d((mb >> 3) + 0x38000000u, mb << 29);
-  const double r = dfma(md, (double)ta.rc(i), -1.0);        // exact
+  const uint32_t mb = u - (d & 0xff800000u);                // float bits of m = x / 2^e
+  const double md = (double)bits2f(mb);                     // exact (one conversion; no bit assembly)
+  // interval index = bits 18..22 of d; the accessor uses only the low 5 bits of the index it is given
+  const double r = dfma(md, ta.rc(d >> 18), -1.0);          // exact
   double p = ta.lc(0);
   p = dfma(p, r, ta.lc(1));
   p = dfma(p, r, ta.lc(2));
   p = dfma(p, r, ta.lc(3));
   p = dfma(p, r, ta.lc(4));
   p = dfma(p, r, ta.lc(5));
-  return dfma(p, r, (double)e + ta.l2(i));
+  return dfma(p, r, small_int_to_double(e) + ta.l2(d >> 18));
 }
 
 // 2^t; meaningful for |t| <= 150 (other inputs give garbage but never trap)
@@ -342,8 +354,8 @@ VKP_HD double exp2_tab(double t, const TA& ta) {
   p = dfma(p, r, ta.ec(2));
   p = dfma(p, r, ta.ec(3));
   p = dfma(p, r, 1.0);
-  const double v = p * ta.e2(k & 31);        // in [0.98, 2.02]
-  return hilo2d(hi32(v) + (uint32_t)((k >> 5) << 20), lo32(v));
+  const double v = p * ta.e2(k);             // in [0.98, 2.02]; the accessor uses the low 5 bits of k
+  return hilo2d(hi32(v) + ((uint32_t)(k & ~31) << 15), lo32(v));   // += (k >> 5) in the exponent field
 }
 
 // Fast cores: every lane of a warp calls them together on the device (lookups are shuffles).
@@ -362,24 +374,23 @@ VKP_HD float exp2_core(float x, const TA& ta, bool& special) {
 template <class TA>
 VKP_HD float log2_core(float x, const TA& ta, bool& special) {
   const uint32_t ux = f2bits(x);
-  const bool ok = (ux - 0x00800000u) < 0x7f000000u;          // positive, normal, finite
-  special |= !ok;
-  return (float)log2_tab(ok ? ux : 0x3fc00000u, ta);
+  special |= !((ux - 0x00800000u) < 0x7f000000u);            // not (positive, normal, finite): value unused
+  return (float)log2_tab(ux, ta);
 }
 template <class TA>
 VKP_HD float log_core(float x, const TA& ta, bool& special) {
   const uint32_t ux = f2bits(x);
-  const bool ok = (ux - 0x00800000u) < 0x7f000000u;
-  special |= !ok;
-  return (float)(log2_tab(ok ? ux : 0x3fc00000u, ta) * 0.693147180559945309417232121458);
+  special |= !((ux - 0x00800000u) < 0x7f000000u);
+  return (float)(log2_tab(ux, ta) * 0.693147180559945309417232121458);
 }
 template <class TA>
 VKP_HD float pow_core(float x, float y, const TA& ta, bool& special) {
+  // x = 1 needs no special case: log2_tab(1) = 0 exactly, t = y * 0 is 0 (-> 1) or, for y = inf / nan,
+  // nan, which the |t| test sends to pow_f (C99: pow(1, anything) = 1)
   const uint32_t ux = f2bits(x);
-  const bool okx = (ux - 0x00800000u) < 0x7f000000u && ux != 0x3f800000u;   // positive, normal, != 1
-  const double t = (double)y * log2_tab(okx ? ux : 0x3fc00000u, ta);
-  special |= !(okx && (hi32(t) & 0x7fffffffu) < 0x4062c000u);               // or |t| >= 150 / nan
-  return d2f_ftz(exp2_tab(t, ta));
+  const double t = (double)y * log2_tab(ux, ta);
+  special |= !((ux - 0x00800000u) < 0x7f000000u) | !((hi32(t) & 0x7fffffffu) < 0x4062c000u);   // x not positive
+  return d2f_ftz(exp2_tab(t, ta));                                           // normal, or |t| >= 150 / nan
 }
 
 // convenience wrappers (host tests, single-element callers)

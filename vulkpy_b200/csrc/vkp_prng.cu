@@ -86,6 +86,29 @@ inline void matvec_host(const BitMat& m, const uint32_t (&v)[4], uint32_t (&out)
 std::once_flag g_jump_once;
 BitMat* g_jump_host = nullptr;  // [JUMP_LEVELS]
 
+// Byte-sliced form of the same matrices for the device: tab[k][j][v] = XOR of the columns 8j + b of
+// T^(2^k) over the set bits b of v, so that a mat-vec is 16 table look-ups (one per state byte)
+// instead of 128 masked column loads -- the jump-ahead of a segment drops from ~1000 to ~70
+// instructions per matrix, which matters for the reference's default of 64 lanes (thousands of
+// short segments per lane: profiles/r02_ncu_rows.md).  64 KiB per level, 2.2 MiB per device.
+struct ByteMat { uint32_t e[16][256][4]; };
+ByteMat* g_jump_bytes = nullptr;  // [JUMP_LEVELS]
+
+void build_byte_tables() {
+  g_jump_bytes = new ByteMat[JUMP_LEVELS];
+  for (int k = 0; k < JUMP_LEVELS; k++)
+    for (int j = 0; j < 16; j++) {
+      uint32_t (*t)[4] = g_jump_bytes[k].e[j];
+      t[0][0] = t[0][1] = t[0][2] = t[0][3] = 0;
+      for (int v = 1; v < 256; v++) {
+        const int low = __builtin_ctz(v);
+        const uint32_t* c = g_jump_host[k].col[8 * j + low];
+        const uint32_t* r = t[v & (v - 1)];
+        for (int w = 0; w < 4; w++) t[v][w] = r[w] ^ c[w];
+      }
+    }
+}
+
 void build_jump_tables() {
   g_jump_host = new BitMat[JUMP_LEVELS];
   for (int c = 0; c < 128; c++) {  // T itself
@@ -96,6 +119,7 @@ void build_jump_tables() {
   }
   for (int k = 1; k < JUMP_LEVELS; k++)  // squaring: (M*M) e_c = M (M e_c)
     for (int c = 0; c < 128; c++) matvec_host(g_jump_host[k - 1], g_jump_host[k - 1].col[c], g_jump_host[k].col[c]);
+  build_byte_tables();
 }
 
 // ---- device ---------------------------------------------------------------------------------
@@ -113,20 +137,22 @@ __device__ __forceinline__ uint32_t next_dev(uint4& s) {
   return result;
 }
 
+// m: one level of the byte-sliced tables, [16][256] uint4
 __device__ __forceinline__ uint4 matvec_dev(const uint4* __restrict__ m, uint4 v) {
   uint4 acc = make_uint4(0, 0, 0, 0);
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
   for (int i = 0; i < 4; i++) {
-#pragma unroll 8
-    for (int b = 0; b < 32; b++) {
-      const uint32_t mask = 0u - ((w[i] >> b) & 1u);
-      const uint4 c = __ldg(m + i * 32 + b);
-      acc.x ^= c.x & mask; acc.y ^= c.y & mask; acc.z ^= c.z & mask; acc.w ^= c.w & mask;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const uint4 c = __ldg(m + (i * 4 + b) * 256 + ((w[i] >> (8 * b)) & 255u));
+      acc.x ^= c.x; acc.y ^= c.y; acc.z ^= c.z; acc.w ^= c.w;
     }
   }
   return acc;
 }
+
+constexpr size_t LEVEL_STRIDE = 16 * 256;   // uint4 per level
 
 __device__ __forceinline__ float u2f01(uint32_t r) { return __uint_as_float((r >> 9) | 0x3f800000u) - 1.0f; }
 
@@ -165,7 +191,7 @@ xoshiro_stream_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ st
   // jump ahead by p * 2^log2L steps
   for (uint32_t b = 0; (p >> b) != 0; b++) {
     if ((p >> b) & 1u) {
-      const uint4* m = jump + (size_t)(log2L + b) * 128;
+      const uint4* m = jump + (size_t)(log2L + b) * LEVEL_STRIDE;
 #pragma unroll
       for (int q = 0; q < LPT; q++) s[q] = matvec_dev(m, s[q]);
     }
@@ -224,7 +250,7 @@ xoshiro_normal_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ st
   }
   for (uint32_t b = 0; (p >> b) != 0; b++) {
     if ((p >> b) & 1u) {
-      const uint4* m = jump + (size_t)(log2L + b) * 128;
+      const uint4* m = jump + (size_t)(log2L + b) * LEVEL_STRIDE;
       s0 = matvec_dev(m, s0);
       s1 = matvec_dev(m, s1);
     }
@@ -280,7 +306,7 @@ __global__ void xoshiro_advance_kernel(const uint4* __restrict__ state_in, uint4
   if (l >= size) return;
   uint4 s = state_in[l];
   for (uint32_t b = 0; (full >> b) != 0; b++)
-    if ((full >> b) & 1ull) s = matvec_dev(jump + (size_t)b * 128, s);
+    if ((full >> b) & 1ull) s = matvec_dev(jump + (size_t)b * LEVEL_STRIDE, s);
   if (l < rem) next_dev(s);
   state_out[l] = s;
 }
@@ -325,8 +351,8 @@ extern "C" int vkp_rng_create(vkp_ctx* ctx, uint32_t size, uint64_t seed, int ha
   {
     std::lock_guard<std::mutex> gj(g_jump_dev_mu);
     if (!g_jump_dev[ctx->device]) {
-      VKP_CUDA(cudaMalloc(&g_jump_dev[ctx->device], sizeof(BitMat) * JUMP_LEVELS));
-      VKP_CUDA(cudaMemcpyAsync(g_jump_dev[ctx->device], g_jump_host, sizeof(BitMat) * JUMP_LEVELS,
+      VKP_CUDA(cudaMalloc(&g_jump_dev[ctx->device], sizeof(ByteMat) * JUMP_LEVELS));
+      VKP_CUDA(cudaMemcpyAsync(g_jump_dev[ctx->device], g_jump_bytes, sizeof(ByteMat) * JUMP_LEVELS,
                                cudaMemcpyHostToDevice, ctx->stream));
     }
     r->jump = g_jump_dev[ctx->device];
@@ -374,11 +400,9 @@ static int rng_generate(vkp_rng* rng, void* out, uint64_t n_out, float mean, flo
     const uint32_t size = rng->size;
     const uint64_t n_draw = (MODE == MODE_NORMAL) ? ((n_out + 1) & ~1ull) : n_out;
     int lpt;
-    // lanes per thread: prefer whole warps per segment (uniform jump-ahead), then wider stores
+    // lanes per thread: the widest store the lane count allows (16 bytes for the default 64 lanes:
+    // half a warp per segment row; the byte-table jump-ahead makes mixed segments in a warp cheap)
     if (MODE == MODE_NORMAL) lpt = 2;  // caller guarantees an even size
-    else if (size % 128 == 0) lpt = 4;
-    else if (size % 64 == 0) lpt = 2;
-    else if (size % 32 == 0) lpt = 1;
     else lpt = (size % 4 == 0) ? 4 : ((size % 2 == 0) ? 2 : 1);
     const uint32_t groups = size / lpt;
     const uint64_t draws_per_lane = (n_draw + size - 1) / size;
