@@ -123,6 +123,29 @@ VKP_API int vkp_submit(vkp_ctx* ctx, int op, void* const* bufs, int nbuf,
 /* extra device-side utilities with no shader counterpart in the reference */
 VKP_API int vkp_fill_u32(vkp_ctx* ctx, void* dst, size_t count, uint32_t bits, vkp_job** job); /* `a[:] = v` host fills: vkarray.py:1540-1542, nn/parameters.py:81-86 */
 
+/* Fused chain of same-shape element-wise shaders (lazy element-wise fusion).  What the reference
+ * issues as n_steps dependent jobs over throw-away intermediates -- e.g. Sigmoid.forward, nn/layers.py:239-243:
+ * `y = 0.0 - x; y.exp(inplace); y += 1.0; y = 1.0 / y` -- is ONE launch that reads each input once and writes
+ * `out` once.  A running value starts as in[0]; step k applies the operation of ONE reference shader to it with
+ * exactly that shader's rounding (results are bit-identical to the op-by-op sequence).  srcs[k] names the second
+ * operand: 0 = scalars[k], 1..3 = in[1..3] (same element count), 4 = the copy saved by an earlier VKP_CHAIN_SAVE. */
+#define VKP_CHAIN_ADD   0   /* acc = acc + b   (add.comp / add_scalar.comp) */
+#define VKP_CHAIN_SUB   1
+#define VKP_CHAIN_MUL   2
+#define VKP_CHAIN_DIV   3
+#define VKP_CHAIN_MAX   4
+#define VKP_CHAIN_MIN   5
+#define VKP_CHAIN_POW   6
+#define VKP_CHAIN_RSUB  7   /* acc = b - acc   (rsub_scalar.comp) */
+#define VKP_CHAIN_RDIV  8
+#define VKP_CHAIN_RPOW  9
+#define VKP_CHAIN_UNARY 11  /* + index of the unary shader: abs sign sin cos tan asin acos atan sinh cosh tanh asinh
+                             *   acosh atanh exp log exp2 log2 sqrt invsqrt (0..19) */
+#define VKP_CHAIN_SAVE  31  /* tmp = acc */
+#define VKP_CHAIN_MAX_STEPS 16
+VKP_API int vkp_ew_chain(vkp_ctx* ctx, int n_in, const float* const* in, float* out, size_t count, int n_steps,
+                         const int* ops, const int* srcs, const float* scalars, vkp_job** job);
+
 /* General fp32 GEMM behind "matmul"/"batch_affine": C[M,N] = op(A)·op(B) (+ bias[N]).
  * transA=0: A is [M,K] row-major, 1: A is [K,M].  transB=0: B is [K,N], 1: B is [N,K].
  * Used for Dense.backward (nn/layers.py:104-141) where the reference materialises

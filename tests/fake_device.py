@@ -177,6 +177,28 @@ class FakeDevice:
         return self._done(name, len(infos))
 
     # -- entry points outside the shader list ------------------------------------------------------
+    def ew_chain(self, inputs, out, ops, srcs, scalars):
+        """vkp_ew_chain: the recorded chain evaluated step by step with the oracle's one-rounding ops."""
+        v = [b.arr for b in inputs]
+        acc, tmp = v[0].copy(), None
+        names = list(BIN) + ["rsub", "rdiv", "rpow"]
+        for op, src, s in zip(ops, srcs, scalars):
+            if op == 31:
+                tmp = acc.copy()
+                continue
+            if op >= 11:
+                acc = orc.unary(UN[op - 11], acc)
+                continue
+            rev = op >= 7
+            base = names[op][1:] if rev else names[op]
+            if src == 0:
+                acc = orc.scalar(base, acc, s, reverse=rev)
+            else:
+                b = tmp if src == 4 else v[src]
+                acc = orc.binary(base, b, acc) if rev else orc.binary(base, acc, b)
+        out.arr[:] = acc
+        return self._done("ew_chain", len(inputs) + 1)
+
     def fill(self, buf, bits):
         buf.arr.view(np.uint32)[:] = np.uint32(bits & 0xFFFFFFFF)
         return self._done("fill", 1)

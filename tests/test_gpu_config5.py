@@ -43,7 +43,13 @@ def test_config5_step_against_float64_model(gpu, batch):
     # ---- float64 model of the reference's step (diagonal softmax Jacobian: nn/layers.py:302-323) ----
     x64 = x.astype(np.float64)
     z1 = x64 @ W1.T + b1
-    h = np.maximum(z1, 0)
+    # ReLU mask taken from the device: float32 rounding flips the sign of a handful of the 8.4 M
+    # pre-activations that sit within ~1e-6 of zero, and each flip moves a gradient entry by one
+    # whole product term (~1e-5); everywhere else the float64 mask must agree
+    mask = np.asarray(net.L[1]._y) > 0
+    flips = mask != (z1 > 0)
+    assert flips.sum() < 100 and (np.abs(z1[flips]) < 1e-4).all(), (flips.sum(), np.abs(z1[flips]).max(initial=0))
+    h = np.where(mask, z1, 0.0)
     z2 = h @ W2.T + b2
     e = np.exp(z2 - z2.max(axis=1, keepdims=True))
     p = e / e.sum(axis=1, keepdims=True)
@@ -51,7 +57,7 @@ def test_config5_step_against_float64_model(gpu, batch):
     dp = -y / (p + 1e-8) / B
     dz2 = dp * p * (1 - p)
     gW2, gb2 = dz2.T @ h, dz2.sum(axis=0)
-    dz1 = (dz2 @ W2) * (z1 > 0)
+    dz1 = (dz2 @ W2) * mask
     gW1, gb1 = dz1.T @ x64, dz1.sum(axis=0)
     np.testing.assert_allclose(np.asarray(pred), p, rtol=2e-4, atol=1e-7)
     np.testing.assert_allclose(np.asarray(loss).reshape(-1)[0], L, rtol=2e-5)

@@ -501,3 +501,105 @@ def test_data_parallel_equals_full_batch_step(vk, gpu, world):
             np.testing.assert_allclose(np.asarray(ld.w.value), np.asarray(ls.w.value), rtol=2e-5, atol=1e-6)
             np.testing.assert_allclose(np.asarray(ld.b.value), np.asarray(ls.b.value), rtol=2e-5, atol=1e-6)
     np.testing.assert_allclose(float(np.asarray(losses[0]).reshape(-1)[0]), float(np.asarray(want_loss).reshape(-1)[0]), rtol=1e-5)
+
+
+# ---- lazy element-wise fusion (vk.fuse()): recording, hazards, launch counts ------------------------------------
+def test_fuse_records_chains_and_matches_eager(vk, gpu):
+    rs = np.random.default_rng(3)
+    x_h = rs.uniform(-2, 2, (7, 9)).astype(F)
+    b_h = rs.uniform(0.5, 2, (7, 9)).astype(F)
+
+    def sigmoid_chain(x):                     # nn/layers.py:239-243 of the reference
+        y = 0.0 - x
+        y.exp(inplace=True)
+        y += 1.0
+        return 1.0 / y
+
+    x, b = vk.Array(gpu, data=x_h), vk.Array(gpu, data=b_h)
+    eager = np.asarray(sigmoid_chain(x)).copy()
+    n0 = gpu.gpu.launch_count()
+    with vk.fuse():
+        y = sigmoid_chain(x)
+        assert gpu.gpu.launch_count() == n0                    # nothing launched yet
+        z = (y * b - 0.25).max(b) ** 2.0                       # continues the same chain, second input
+    assert gpu.gpu.launch_count() == n0
+    l0 = len(gpu.gpu.log)
+    got_y, got_z = np.asarray(y).copy(), np.asarray(z).copy()
+    assert gpu.gpu.log[l0:] == [("ew_chain", 2), ("ew_chain", 3)]      # 4 ops -> 1 launch; 8 ops, 2 inputs -> 1 launch
+    np.testing.assert_array_equal(got_y, eager)
+    want = np.asarray(((vk.Array(gpu, data=eager) * b - 0.25).max(b)) ** 2.0)
+    np.testing.assert_array_equal(got_z, want)
+    assert y.shape == (7, 9) and z.shape == (7, 9)
+
+
+def test_fuse_hazards(vk, gpu):
+    a_h = np.arange(12, dtype=F).reshape(3, 4) + 1
+    a = vk.Array(gpu, data=a_h)
+    with vk.fuse():
+        c = a + 1.0                 # recorded: reads a
+        a *= 2.0                    # overwrites a: c must be evaluated from the OLD a first
+        d = a + 0.5                 # reads the NEW a (extends a's in-place chain)
+        a -= 1.0                    # d must see 2a, not 2a - 1
+        e = a.sqrt()
+    np.testing.assert_array_equal(np.asarray(c), a_h + 1)
+    np.testing.assert_array_equal(np.asarray(d), a_h * 2 + F(0.5))
+    np.testing.assert_array_equal(np.asarray(a), a_h * 2 - 1)
+    np.testing.assert_array_equal(np.asarray(e), np.sqrt(a_h * 2 - 1))
+    # lazy operand on the right, later modified in place
+    p, q = vk.Array(gpu, data=a_h), vk.Array(gpu, data=a_h)
+    with vk.fuse():
+        r = q * 3.0                 # lazy
+        s = p + r                   # chain over p with the lazy r as second input
+        r += 100.0                  # s must have been evaluated with the old r
+    np.testing.assert_array_equal(np.asarray(s), a_h + a_h * 3)
+    np.testing.assert_array_equal(np.asarray(r), a_h * 3 + 100)
+    # a non-fusable consumer (reduction, broadcast) forces evaluation; host writes go to the evaluated array
+    with vk.fuse():
+        t = (p * 2.0).sum(axis=0)
+        u = p * 2.0
+        u[:] = 7.0
+        w = p + vk.Array(gpu, data=a_h[0])          # broadcast: eager path
+    np.testing.assert_array_equal(np.asarray(t), (a_h * 2).sum(axis=0))
+    np.testing.assert_array_equal(np.asarray(u), np.full_like(a_h, 7))
+    np.testing.assert_array_equal(np.asarray(w), a_h + a_h[0])
+
+
+def test_fuse_long_chains_split_and_dropped_results_cost_nothing(vk, gpu):
+    a_h = np.linspace(0.1, 1.0, 64, dtype=F)
+    a = vk.Array(gpu, data=a_h)
+    n0 = gpu.gpu.launch_count()
+    with vk.fuse():
+        y = a
+        for k in range(40):         # 40 steps: 16 per launch
+            y = y + 0.5
+        _ = a * 3.0                 # never looked at: never launched
+    got = np.asarray(y)
+    want = a_h.copy()
+    for k in range(40):
+        want = want + F(0.5)
+    np.testing.assert_array_equal(got, want)
+    assert gpu.gpu.launch_count() - n0 == 3
+    # five arrays in one expression: at most four inputs per chain
+    arrs = [vk.Array(gpu, data=a_h * (k + 1)) for k in range(6)]
+    with vk.fuse():
+        s = arrs[0]
+        for t in arrs[1:]:
+            s = s + t
+    np.testing.assert_array_equal(np.asarray(s), sum((a_h * (k + 1) for k in range(1, 6)), a_h * 1))
+
+
+def test_fuse_continues_the_lazy_operand_chain(vk, gpu):
+    a_h = np.linspace(0.5, 2.0, 30, dtype=F).reshape(5, 6)
+    g_h = np.linspace(-1.0, 1.0, 30, dtype=F).reshape(5, 6)
+    a, g = vk.Array(gpu, data=a_h), vk.Array(gpu, data=g_h)
+    l0 = len(gpu.gpu.log)
+    with vk.fuse():
+        root = a.sqrt()
+        root += 1e-3
+        d = g / root              # concrete / lazy: root's chain continues with a reversed divide
+        e = 2.0 - (g - root)      # concrete - lazy, then scalar - lazy
+    got_d, got_e = np.asarray(d).copy(), np.asarray(e).copy()
+    assert gpu.gpu.log[l0:] == [("ew_chain", 3), ("ew_chain", 3)]
+    r = np.sqrt(a_h) + F(1e-3)
+    np.testing.assert_array_equal(got_d, g_h / r)
+    np.testing.assert_array_equal(got_e, F(2.0) - (g_h - r))

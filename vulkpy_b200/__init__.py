@@ -14,7 +14,7 @@ hand-written sm_100a CUDA kernels behind a C ABI (``include/vulkpy_b200.h``).
 >>> print(a + b)
 [4. 5. 6.]
 """
-from .vkarray import GPU, U32Array, Shape, Array, zeros
+from .vkarray import GPU, U32Array, Shape, Array, zeros, fuse
 from . import random
 from . import nn
 from . import util

@@ -64,6 +64,8 @@ PROTOTYPES = {
     "vkp_op_count": (C.c_int, []),
     "vkp_submit": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.c_int, _vp, _sz, C.POINTER(_vp)]),
     "vkp_fill_u32": (C.c_int, [_vp, _vp, _sz, _u32, C.POINTER(_vp)]),
+    "vkp_ew_chain": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), _vp, _sz, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                               C.POINTER(C.c_float), C.POINTER(_vp)]),
     "vkp_gemm": (C.c_int, [_vp, C.c_int, C.c_int, _u32, _u32, _u32, _vp, _vp, _vp, _vp, C.c_int,
                            C.POINTER(_vp)]),
     "vkp_nn_adam": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz] + [C.c_float] * 8 + [C.POINTER(_vp)]),
@@ -329,6 +331,15 @@ class Device:
     def fill(self, buf: _BufferBase, bits: int) -> Job:
         job = _vp()
         _check(lib.vkp_fill_u32(self._ctx, buf.ptr, buf.size(), bits & 0xFFFFFFFF, C.byref(job)))
+        return Job(job.value)
+
+    def ew_chain(self, inputs, out: Buffer, ops, srcs, scalars) -> Job:
+        """One launch for a chain of same-shape element-wise operations (``vkp_ew_chain``)."""
+        n, k = len(inputs), len(ops)
+        ptrs = (_vp * n)(*[b.ptr for b in inputs])
+        job = _vp()
+        _check(lib.vkp_ew_chain(self._ctx, n, ptrs, out.ptr, out.size(), k, (C.c_int * k)(*ops), (C.c_int * k)(*srcs),
+                                (C.c_float * k)(*scalars), C.byref(job)))
         return Job(job.value)
 
     def gemm(self, transA: bool, transB: bool, M: int, N: int, K: int, A: Buffer, B: Buffer, Cbuf: Buffer,

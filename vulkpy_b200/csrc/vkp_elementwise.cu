@@ -272,6 +272,146 @@ int launch_ew_tab(vkp_ctx* ctx, const char* name, F f, const void* in0, const vo
   return vkp_after_launch(ctx, name);
 }
 
+// ---- fused element-wise chains (lazy element-wise fusion) -------------------
+// A chain is what the reference issues as a sequence of same-shape element-wise jobs whose
+// intermediate arrays nobody else reads, e.g. Sigmoid.forward (nn/layers.py:239-243):
+//     y = 0.0 - x;  y.exp(inplace);  y += 1.0;  y = 1.0 / y        4 jobs, 4 x 8 B per element
+// Here it is ONE launch that moves 8 B per element: a running value `acc` starts as input 0 and
+// every step applies one reference operation to it -- the very functor the stand-alone kernel of
+// that shader uses, so each step rounds exactly once like the job it replaces and the result is
+// bit-identical to the op-by-op sequence.  The second operand of a step is a scalar, another
+// input array (up to 3 more, same shape) or `tmp`, a copy of `acc` saved by an earlier step
+// (Huber: d.min(d ** 2.0)).  The program is a kernel parameter; all threads run the same step at
+// the same time, so the warp-collective table lookups of exp / log / pow stay legal.
+enum {
+  CH_ADD = 0, CH_SUB, CH_MUL, CH_DIV, CH_MAX, CH_MIN, CH_POW,      // acc = acc op b
+  CH_RSUB, CH_RDIV, CH_RPOW,                                      // acc = b op acc
+  CH_SQUARE,                                                      // pow(acc, 2.0) (see dispatch_scalar)
+  CH_UNARY0,                                                      // + VKU_* : acc = f(acc)
+  CH_SAVE = CH_UNARY0 + VKU_COUNT,                                // tmp = acc
+  CH_COUNT
+};
+enum { CH_SRC_SCALAR = 0, CH_SRC_IN1 = 1, CH_SRC_IN2 = 2, CH_SRC_IN3 = 3, CH_SRC_TMP = 4 };
+constexpr int CH_MAX_STEPS = 16;
+constexpr int CH_UNROLL = 2;
+constexpr int CH_TILE_VEC = EW_BLOCK * CH_UNROLL;
+
+struct ChainStep { uint8_t op, src, pad0, pad1; float s; };
+struct ChainProg { ChainStep st[CH_MAX_STEPS]; int n; int nin; };
+
+template <class B>
+__device__ __forceinline__ float4 ch_bin(float4 a, float4 b) {
+  return make_float4(B()(a.x, b.x), B()(a.y, b.y), B()(a.z, b.z), B()(a.w, b.w));
+}
+template <class U>
+__device__ __forceinline__ float4 ch_un(float4 a) {
+  return make_float4(U()(a.x), U()(a.y), U()(a.z), U()(a.w));
+}
+template <class T>
+__device__ __forceinline__ float4 ch_tab(const LaneTables& tab, const T f, float4 a, float4 b) {
+  bool sp = false;
+  float4 r;
+  r.x = f.fast(tab, a.x, b.x, sp);
+  r.y = f.fast(tab, a.y, b.y, sp);
+  r.z = f.fast(tab, a.z, b.z, sp);
+  r.w = f.fast(tab, a.w, b.w, sp);
+  if (sp) r = redo_slow(f, a, b);
+  return r;
+}
+
+template <int NV>   // NV float4 per thread, all in registers
+__device__ __forceinline__ void ch_step(const LaneTables& tab, const ChainStep st, float4 (&acc)[NV], float4 (&tmp)[NV],
+                                        const float4 (&i1)[NV], const float4 (&i2)[NV], const float4 (&i3)[NV]) {
+  float4 b[NV];
+#pragma unroll
+  for (int u = 0; u < NV; u++) {
+    switch (st.src) {
+      case CH_SRC_IN1: b[u] = i1[u]; break;
+      case CH_SRC_IN2: b[u] = i2[u]; break;
+      case CH_SRC_IN3: b[u] = i3[u]; break;
+      case CH_SRC_TMP: b[u] = tmp[u]; break;
+      default: b[u] = make_float4(st.s, st.s, st.s, st.s);
+    }
+  }
+#define CH_EACH(EXPR)                  \
+  _Pragma("unroll") for (int u = 0; u < NV; u++) acc[u] = (EXPR); \
+  break
+  switch (st.op) {
+    case CH_ADD: CH_EACH(ch_bin<FAdd>(acc[u], b[u]));
+    case CH_SUB: CH_EACH(ch_bin<FSub>(acc[u], b[u]));
+    case CH_MUL: CH_EACH(ch_bin<FMul>(acc[u], b[u]));
+    case CH_DIV: CH_EACH(ch_bin<FDiv>(acc[u], b[u]));
+    case CH_MAX: CH_EACH(ch_bin<FMax>(acc[u], b[u]));
+    case CH_MIN: CH_EACH(ch_bin<FMin>(acc[u], b[u]));
+    case CH_POW: CH_EACH(ch_tab(tab, TPow(), acc[u], b[u]));
+    case CH_RSUB: CH_EACH(ch_bin<FSub>(b[u], acc[u]));
+    case CH_RDIV: CH_EACH(ch_bin<FDiv>(b[u], acc[u]));
+    case CH_RPOW: CH_EACH(ch_tab(tab, TPow(), b[u], acc[u]));
+    case CH_SQUARE: CH_EACH(ch_un<USquare>(acc[u]));
+    case CH_UNARY0 + VKU_ABS: CH_EACH(ch_un<UAbs>(acc[u]));
+    case CH_UNARY0 + VKU_SIGN: CH_EACH(ch_un<USign>(acc[u]));
+    case CH_UNARY0 + VKU_SIN: CH_EACH(ch_un<USin>(acc[u]));
+    case CH_UNARY0 + VKU_COS: CH_EACH(ch_un<UCos>(acc[u]));
+    case CH_UNARY0 + VKU_TAN: CH_EACH(ch_un<UTan>(acc[u]));
+    case CH_UNARY0 + VKU_ASIN: CH_EACH(ch_un<UAsin>(acc[u]));
+    case CH_UNARY0 + VKU_ACOS: CH_EACH(ch_un<UAcos>(acc[u]));
+    case CH_UNARY0 + VKU_ATAN: CH_EACH(ch_un<UAtan>(acc[u]));
+    case CH_UNARY0 + VKU_SINH: CH_EACH(ch_un<USinh>(acc[u]));
+    case CH_UNARY0 + VKU_COSH: CH_EACH(ch_un<UCosh>(acc[u]));
+    case CH_UNARY0 + VKU_TANH: CH_EACH(ch_un<UTanh>(acc[u]));
+    case CH_UNARY0 + VKU_ASINH: CH_EACH(ch_un<UAsinh>(acc[u]));
+    case CH_UNARY0 + VKU_ACOSH: CH_EACH(ch_un<UAcosh>(acc[u]));
+    case CH_UNARY0 + VKU_ATANH: CH_EACH(ch_un<UAtanh>(acc[u]));
+    case CH_UNARY0 + VKU_EXP: CH_EACH(ch_tab(tab, TExp(), acc[u], b[u]));
+    case CH_UNARY0 + VKU_LOG: CH_EACH(ch_tab(tab, TLog(), acc[u], b[u]));
+    case CH_UNARY0 + VKU_EXP2: CH_EACH(ch_tab(tab, TExp2(), acc[u], b[u]));
+    case CH_UNARY0 + VKU_LOG2: CH_EACH(ch_tab(tab, TLog2(), acc[u], b[u]));
+    case CH_UNARY0 + VKU_SQRT: CH_EACH(ch_un<USqrt>(acc[u]));
+    case CH_UNARY0 + VKU_INVSQRT: CH_EACH(ch_un<UInvSqrt>(acc[u]));
+    case CH_SAVE:
+#pragma unroll
+      for (int u = 0; u < NV; u++) tmp[u] = acc[u];
+      break;
+  }
+#undef CH_EACH
+}
+
+__global__ void __launch_bounds__(EW_BLOCK)
+ew_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__ vkpm::MathCoef coef, const float* in0,
+                const float* in1, const float* in2, const float* in3, float* out, size_t n) {
+  const LaneTables tab(coef);
+  const size_t nvec = n >> 2;
+  const size_t base = (size_t)blockIdx.x * CH_TILE_VEC + threadIdx.x;
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+  float4 acc[CH_UNROLL], tmp[CH_UNROLL], i1[CH_UNROLL], i2[CH_UNROLL], i3[CH_UNROLL];
+#pragma unroll
+  for (int u = 0; u < CH_UNROLL; u++) {
+    const size_t i = base + (size_t)u * EW_BLOCK;
+    const bool ok = i < nvec;
+    acc[u] = ok ? reinterpret_cast<const float4*>(in0)[i] : one;
+    i1[u] = (ok && prog.nin > 1) ? reinterpret_cast<const float4*>(in1)[i] : one;
+    i2[u] = (ok && prog.nin > 2) ? reinterpret_cast<const float4*>(in2)[i] : one;
+    i3[u] = (ok && prog.nin > 3) ? reinterpret_cast<const float4*>(in3)[i] : one;
+    tmp[u] = one;
+  }
+  for (int k = 0; k < prog.n; k++) ch_step<CH_UNROLL>(tab, prog.st[k], acc, tmp, i1, i2, i3);
+#pragma unroll
+  for (int u = 0; u < CH_UNROLL; u++) {
+    const size_t i = base + (size_t)u * EW_BLOCK;
+    if (i < nvec) reinterpret_cast<float4*>(out)[i] = acc[u];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x < 32) {   // n % 4 tail: the whole first warp walks the program
+    const size_t i = (nvec << 2) + threadIdx.x;
+    const bool ok = i < n;
+    float4 a1[1] = {make_float4(ok ? in0[i] : 1.f, 1.f, 1.f, 1.f)}, t1[1] = {one};
+    const float4 b1[1] = {make_float4((ok && prog.nin > 1) ? in1[i] : 1.f, 1.f, 1.f, 1.f)};
+    const float4 b2[1] = {make_float4((ok && prog.nin > 2) ? in2[i] : 1.f, 1.f, 1.f, 1.f)};
+    const float4 b3[1] = {make_float4((ok && prog.nin > 3) ? in3[i] : 1.f, 1.f, 1.f, 1.f)};
+    for (int k = 0; k < prog.n; k++) ch_step<1>(tab, prog.st[k], a1, t1, b1, b2, b3);
+    if (ok) out[i] = a1[0].x;
+  }
+}
+
 // ---- Box-Muller (prng_box_muller.comp:19-32, prng_ibox_muller.comp:16-27) -----------------
 // One thread per pair.  Unlike the reference dispatch (floor(n/2) invocations rounded up to a
 // workgroup, random.py:106-121) the last element of an odd-length output is always written.
@@ -504,6 +644,46 @@ extern "C" int vkp_fill_u32(vkp_ctx* ctx, void* dst, size_t count, uint32_t bits
     const unsigned grid = vkp_grid_for(ctx, (count + 3) / 4, 256, 8);
     fill_u32_kernel<<<grid, 256, 0, ctx->stream>>>((uint32_t*)dst, count, bits);
     VKP_TRY(vkp_after_launch(ctx, "fill"));
+  }
+  return vkp_finish_op(ctx, job);
+}
+
+// One launch for a chain of same-shape element-wise operations (see ew_chain_kernel).  ops[k] is a
+// VKP_CHAIN_* code, srcs[k] selects the second operand (0 scalar, 1..3 input k, 4 the saved copy),
+// scalars[k] its value when it is a scalar.  `out` may alias any input.
+extern "C" int vkp_ew_chain(vkp_ctx* ctx, int n_in, const float* const* in, float* out, size_t count, int n_steps,
+                            const int* ops, const int* srcs, const float* scalars, vkp_job** job) {
+  VKP_CHECK(ctx && in && out && ops && srcs && scalars, "vkp_ew_chain: null argument");
+  VKP_CHECK(n_in >= 1 && n_in <= 4, "vkp_ew_chain: 1..4 inputs, got %d", n_in);
+  VKP_CHECK(n_steps >= 1 && n_steps <= CH_MAX_STEPS, "vkp_ew_chain: 1..%d steps, got %d", CH_MAX_STEPS, n_steps);
+  ChainProg prog;
+  memset(&prog, 0, sizeof(prog));
+  prog.n = n_steps;
+  prog.nin = n_in;
+  for (int k = 0; k < n_steps; k++) {
+    int op = ops[k];
+    const int src = srcs[k];
+    VKP_CHECK(op >= 0 && op < CH_COUNT && op != CH_SQUARE, "vkp_ew_chain: bad op %d at step %d", op, k);
+    VKP_CHECK(src >= 0 && src <= CH_SRC_TMP && (src == CH_SRC_SCALAR || src == CH_SRC_TMP || src < n_in),
+              "vkp_ew_chain: step %d reads input %d of %d", k, src, n_in);
+    if (op == CH_POW && src == CH_SRC_SCALAR && scalars[k] == 2.0f) op = CH_SQUARE;   // as dispatch_scalar does
+    prog.st[k].op = (uint8_t)op;
+    prog.st[k].src = (uint8_t)src;
+    prog.st[k].s = scalars[k];
+  }
+  for (int i = 0; i < n_in; i++) VKP_CHECK(in[i] && ((uintptr_t)in[i] & 15) == 0, "vkp_ew_chain: input %d is null or unaligned", i);
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  void* bufs[5] = {(void*)in[0], n_in > 1 ? (void*)in[1] : nullptr, n_in > 2 ? (void*)in[2] : nullptr,
+                   n_in > 3 ? (void*)in[3] : nullptr, (void*)out};
+  VKP_TRY(vkp_prepare_buffers(ctx, bufs, 5));
+  if (count) {
+    const size_t nvec = count >> 2;
+    const size_t tiles = (nvec + CH_TILE_VEC - 1) / CH_TILE_VEC;
+    const unsigned grid = (unsigned)(tiles ? tiles : 1);
+    ew_chain_kernel<<<grid, EW_BLOCK, 0, ctx->stream>>>(prog, vkpt::host_coef(), in[0], n_in > 1 ? in[1] : in[0],
+                                                        n_in > 2 ? in[2] : in[0], n_in > 3 ? in[3] : in[0], out, count);
+    VKP_TRY(vkp_after_launch(ctx, "ew_chain"));
   }
   return vkp_finish_op(ctx, job);
 }

@@ -23,6 +23,7 @@
 #include "vkp_math.cuh"
 #include "vkp_tables.cuh"
 
+#include <cstdlib>
 #include <random>
 
 namespace {
@@ -158,17 +159,21 @@ __device__ __forceinline__ float u2f01(uint32_t r) { return __uint_as_float((r >
 
 enum { MODE_U32 = 0, MODE_F32 = 1, MODE_NORMAL = 2 };
 
+// The stream is written once and read by a later kernel: streaming (evict-first) stores keep the
+// thousands of concurrent segment streams from ageing in L2 and reaching DRAM as scattered lines.
 template <int LPT> struct VecStore;
-template <> struct VecStore<1> { static __device__ void st(uint32_t* p, const uint32_t* v) { p[0] = v[0]; } };
-template <> struct VecStore<2> { static __device__ void st(uint32_t* p, const uint32_t* v) { *reinterpret_cast<uint2*>(p) = make_uint2(v[0], v[1]); } };
-template <> struct VecStore<4> { static __device__ void st(uint32_t* p, const uint32_t* v) { *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]); } };
+template <> struct VecStore<1> { static __device__ void st(uint32_t* p, const uint32_t* v, bool cs) { if (cs) __stcs(p, v[0]); else p[0] = v[0]; } };
+template <> struct VecStore<2> { static __device__ void st(uint32_t* p, const uint32_t* v, bool cs) {
+  if (cs) __stcs(reinterpret_cast<uint2*>(p), make_uint2(v[0], v[1])); else *reinterpret_cast<uint2*>(p) = make_uint2(v[0], v[1]); } };
+template <> struct VecStore<4> { static __device__ void st(uint32_t* p, const uint32_t* v, bool cs) {
+  if (cs) __stcs(reinterpret_cast<uint4*>(p), make_uint4(v[0], v[1], v[2], v[3])); else *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]); } };
 
 // uniform streams (MODE_U32 / MODE_F32): n numbers, out[c*size + lane]
 template <int LPT, int MODE>
 __global__ void __launch_bounds__(128)
 xoshiro_stream_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ state_out,
                       uint32_t* __restrict__ out, const uint4* __restrict__ jump, uint32_t size,
-                      uint64_t n_draw, uint32_t log2L, uint32_t nseg) {
+                      uint64_t n_draw, uint32_t log2L, uint32_t nseg, bool cs) {
   const uint32_t groups = size / LPT;
   const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (t >= (uint64_t)groups * nseg) return;
@@ -206,7 +211,7 @@ xoshiro_stream_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ st
 #pragma unroll
       for (int q = 0; q < LPT; q++) r[q] = __float_as_uint(u2f01(r[q]));
     }
-    VecStore<LPT>::st(out + c * size + l0, r);
+    VecStore<LPT>::st(out + c * size + l0, r, cs);
   }
   // tail chunk: draw index `full`, lanes < rem only
   if (rem != 0 && full >= start && full < seg_end) {
@@ -406,8 +411,10 @@ static int rng_generate(vkp_rng* rng, void* out, uint64_t n_out, float mean, flo
     else lpt = (size % 4 == 0) ? 4 : ((size % 2 == 0) ? 2 : 1);
     const uint32_t groups = size / lpt;
     const uint64_t draws_per_lane = (n_draw + size - 1) / size;
-    // segment length: power of two, >= 256 draws, giving about sms*1024 threads
-    uint64_t want_seg = ((uint64_t)ctx->sms * 1024 + groups - 1) / groups;
+    // segment length: power of two, >= 256 draws, giving about sms * 1024 threads (VKP_PRNG_THREADS_PER_SM)
+    static const uint64_t tps = getenv("VKP_PRNG_THREADS_PER_SM") ? (uint64_t)atoll(getenv("VKP_PRNG_THREADS_PER_SM")) : 1024;
+    static const bool cs = getenv("VKP_PRNG_STCS") && getenv("VKP_PRNG_STCS")[0] == '1';
+    uint64_t want_seg = ((uint64_t)ctx->sms * tps + groups - 1) / groups;
     if (want_seg < 1) want_seg = 1;
     uint64_t L = (draws_per_lane + want_seg - 1) / want_seg;
     uint32_t log2L = 8;
@@ -426,7 +433,7 @@ static int rng_generate(vkp_rng* rng, void* out, uint64_t n_out, float mean, flo
     uint4* sout = rng->state[rng->cur ^ 1];
 #define LAUNCH(LPT)                                                                                  \
   xoshiro_stream_kernel<LPT, (MODE == MODE_NORMAL ? MODE_F32 : MODE)><<<grid, 128, 0, ctx->stream>>>(     \
-      sin_, sout, (uint32_t*)out, rng->jump, size, n_draw, log2L, nseg)
+      sin_, sout, (uint32_t*)out, rng->jump, size, n_draw, log2L, nseg, cs)
     if (MODE == MODE_NORMAL) {
       xoshiro_normal_kernel<<<grid, 128, 0, ctx->stream>>>(sin_, sout, (float*)out, rng->jump, size, n_draw, n_out,
                                                            log2L, nseg, mean, stddev);

@@ -5,7 +5,7 @@ from __future__ import annotations
 
 from typing import Callable, Iterable, Optional
 
-from ..vkarray import GPU, Array, DataShape, BatchAffineParams
+from ..vkarray import GPU, Array, DataShape, BatchAffineParams, fuse
 from .core import Module, Optimizer, Regularizer
 from .parameters import Parameter
 from .initializers import HeNormal
@@ -111,6 +111,14 @@ class Sigmoid(Module):
     """1 / (1 + exp(-x)) (reference: layers.py:213-267)."""
 
     def forward(self, x: Array) -> Array:
+        if not _opt.UNFUSED:
+            # the reference's four jobs (layers.py:239-243) recorded and issued as ONE chain launch
+            # (vkp_ew_chain): same operations, same roundings, 8 B per element instead of 32
+            with fuse():
+                y = 0.0 - x
+                y.exp(inplace=True)
+                y += 1.0
+                return 1.0 / y
         y = 0.0 - x
         y.exp(inplace=True)
         y += 1.0

@@ -5,11 +5,20 @@ from __future__ import annotations
 
 from typing import Callable, Iterable, Optional, Tuple
 
-from ..vkarray import Array, DataShape, VectorParams
+import contextlib
+
+from ..vkarray import Array, DataShape, VectorParams, fuse
+from . import optimizers as _opt
 from .core import Loss
 from .layers import Softmax
 
 __all__ = ["CrossEntropyLoss", "SoftmaxCrossEntropyLoss", "MSELoss", "HuberLoss", "MixLoss"]
+
+
+def _chains():
+    """Element-wise chains of a loss (`L = y - x; L **= 2`, `dx = x - y; dx *= 2; dx *= 1/B` ...) are recorded
+    and issued as one launch each unless the op-by-op reference order is requested (VULKPY_NN_UNFUSED=1)."""
+    return contextlib.nullcontext() if _opt.UNFUSED else fuse()
 
 
 class ReduceLoss(Loss):
@@ -28,13 +37,15 @@ class ReduceLoss(Loss):
 
     def __call__(self, x: Array, y: Array) -> Array:
         self._x, self._y = x, y
-        return self.reduce(self.forward(x, y))
+        with _chains():
+            return self.reduce(self.forward(x, y))
 
     def grad(self) -> Array:
-        dx = self.backward()
-        if self.scale_backward is not None:
-            dx *= self.scale_backward(dx)
-        return dx
+        with _chains():
+            dx = self.backward()
+            if self.scale_backward is not None:
+                dx *= self.scale_backward(dx)
+            return dx
 
     def forward(self, x: Array, y: Array) -> Array:
         raise NotImplementedError

@@ -10,7 +10,7 @@ import logging
 import os
 from typing import Iterable
 
-from ..vkarray import GPU, Array, zeros
+from ..vkarray import GPU, Array, zeros, fuse
 from .core import Optimizer, OptimizerState
 
 __all__ = ["SGD", "SGDState", "AdaGrad", "AdaGradState", "Adam", "AdamState", "Optimizer", "OptimizerState"]
@@ -49,6 +49,15 @@ class AdaGradState(OptimizerState):
         self.h[:] = tau
 
     def grad2diff(self, grad: Array) -> Array:
+        if not UNFUSED:
+            with fuse():     # h += g^2 and diff = g / (sqrt(h) + eps) * -lr: two chain launches instead of five jobs
+                self.h += grad ** 2
+                self.h.wait()
+                root = self.h.sqrt()
+                root += self.opt.eps
+                diff = grad / root
+                diff *= -self.opt.lr
+                return diff
         self.h += grad ** 2
         root = self.h.sqrt()
         root += self.opt.eps

@@ -14,9 +14,12 @@ fill instead of a host loop (Q17).
 """
 from __future__ import annotations
 
+import contextlib
 import logging
 import math
 import operator
+import os
+import weakref
 from typing import Iterable, List, Optional, Tuple, Union
 
 import numpy as np
@@ -30,7 +33,7 @@ from ._backend import (  # re-exported: nn code imports these from here (nn/laye
 )
 from .vktyping import Resource
 
-__all__ = ["GPU", "U32Array", "Shape", "Array", "zeros"]
+__all__ = ["GPU", "U32Array", "Shape", "Array", "zeros", "fuse"]
 
 logger = logging.getLogger("vulkpy")
 
@@ -46,6 +49,63 @@ for _name, _id in list(_b.OPS.items()):
         _SHAPE_BINDING[_id] = 2
     elif _name.endswith("_broadcast"):
         _SHAPE_BINDING[_id] = 3
+
+
+# ---- lazy element-wise fusion -------------------------------------------------
+# Inside `with vk.fuse():` (or with VULKPY_FUSE=1) same-shape / scalar element-wise operators do not
+# launch: the result carries a recorded chain over its concrete inputs and ONE `vkp_ew_chain` launch
+# evaluates it when something needs the values (any other operation, wait(), a host view).  Every
+# step is the reference shader's own operation with its own rounding, so results are bit-identical
+# to the op-by-op sequence; intermediates nobody looks at are never written to memory.
+_CHAIN_BIN = {"add": 0, "sub": 1, "mul": 2, "div": 3, "max": 4, "min": 5, "pow": 6, "rsub": 7, "rdiv": 8, "rpow": 9}
+_CHAIN_FLIP = {0: 0, 2: 2, 4: 4, 5: 5, 1: 7, 3: 8, 6: 9}     # concrete (op) lazy == lazy (flipped op) concrete
+_CHAIN_UNARY0 = 11
+_CHAIN_SAVE = 31
+_CHAIN_MAX_STEPS = 16
+_CHAIN_MAX_INPUTS = 4
+_fuse_depth = 1 if os.environ.get("VULKPY_FUSE", "0") == "1" else 0
+
+
+@contextlib.contextmanager
+def fuse():
+    """Record same-shape element-wise operators instead of launching them one by one; chains are
+    evaluated by one kernel each on first use.  Additive (the reference has no counterpart); do not
+    write through a NumPy view obtained BEFORE an operation was recorded on that array."""
+    global _fuse_depth
+    _fuse_depth += 1
+    try:
+        yield
+    finally:
+        _fuse_depth -= 1
+
+
+class _Lazy:
+    """Recorded chain: inputs[0] is the running value's source, steps = (op, src, scalar)."""
+    __slots__ = ("inputs", "steps")
+
+    def __init__(self, inputs, steps):
+        self.inputs, self.steps = inputs, steps
+
+    def extended(self, op: int, other):
+        """New chain = this one + (op, other); None when it would not fit one launch."""
+        if len(self.steps) >= _CHAIN_MAX_STEPS:
+            return None
+        inputs = self.inputs
+        if other is None:
+            step = (op, 0, 0.0)
+        elif isinstance(other, _GPUArray):
+            for k, a in enumerate(inputs):
+                if a is other and k > 0:
+                    break
+            else:
+                if len(inputs) >= _CHAIN_MAX_INPUTS:
+                    return None
+                inputs = inputs + [other]
+                k = len(inputs) - 1
+            step = (op, k, 0.0)
+        else:
+            step = (op, 0, float(other))
+        return _Lazy(inputs, self.steps + [step])
 
 
 def _full_slice(key) -> bool:
@@ -139,6 +199,61 @@ class _GPUArray(Resource):
         self.job: Optional[Job] = None
         self._keep: List[Resource] = []
         self._view: Optional[np.ndarray] = None
+        self._buffer = None
+        self._lazy: Optional[_Lazy] = None        # recorded, not yet launched chain (vk.fuse())
+        self._consumers = None                    # weak set of lazy arrays that read this one
+
+    # The device buffer.  Reading it is what "needs the values": a recorded chain is launched first,
+    # and recorded chains that READ this array are launched before anyone can overwrite it.
+    @property
+    def buffer(self):
+        if self._consumers:
+            self._flush_consumers()
+        if self._lazy is not None:
+            self._materialize()
+        return self._buffer
+
+    @buffer.setter
+    def buffer(self, b):
+        self._buffer = b
+
+    def _flush_consumers(self):
+        cons, self._consumers = self._consumers, None
+        for c in list(cons):
+            if c._lazy is not None:
+                c._materialize()
+
+    def _materialize(self):
+        lz, self._lazy = self._lazy, None
+        dev = self._gpu.gpu
+        src0 = lz.inputs[0]
+        for a in lz.inputs:
+            if a._lazy is not None:
+                a._materialize()
+        # an in-place chain (`a += 1; a.exp(inplace=True)`) writes back into its own source buffer;
+        # chains recorded from the value it is about to overwrite go first
+        if src0 is self._inplace_src and src0._consumers:
+            src0._flush_consumers()
+        out = src0._buffer if src0 is self._inplace_src else self._create(dev, _prod(self.shape))
+        self.job = dev.ew_chain([a._buffer for a in lz.inputs], out, [st[0] for st in lz.steps],
+                                [st[1] for st in lz.steps], [st[2] for st in lz.steps])
+        self._buffer = out
+        self._keep = [a for a in lz.inputs if a is not self._inplace_src]
+        self._inplace_src = None
+        for a in lz.inputs:
+            if a._consumers is not None:
+                a._consumers.discard(self)
+
+    _inplace_src = None
+
+    def _watch(self, lz: _Lazy):
+        """Register this (lazy) array with the inputs of its chain."""
+        for a in lz.inputs:
+            if a is self._inplace_src:
+                continue
+            if a._consumers is None:
+                a._consumers = weakref.WeakSet()
+            a._consumers.add(self)
 
     def _alloc(self, data, shape):
         dev = self._gpu.gpu
@@ -157,6 +272,8 @@ class _GPUArray(Resource):
 
     def wait(self):
         """Wait for the job that writes this array."""
+        if self._lazy is not None:
+            self._materialize()
         job = self.job
         if job is not None:
             job.wait()
@@ -253,7 +370,7 @@ class _GPUArray(Resource):
 
     def _set_shape(self, shape):
         shape = tuple(int(s) for s in (shape if np.ndim(shape) else (shape,)))
-        n = self.buffer.size()
+        n = _prod(self.shape) if self._lazy is not None else self.buffer.size()
         if shape.count(-1) == 1:
             rest = -_prod(shape)
             if rest > 0 and n % rest == 0:
@@ -325,8 +442,59 @@ class Array(_GPUArray):
         ret._keep = keep
         return ret
 
+    # -- lazy element-wise fusion ---------------------------------------------------------------------
+    def _shell(self) -> "Array":
+        """A second handle on this array's current buffer (the source of an in-place chain)."""
+        sh = Array.__new__(Array)
+        _GPUArray.__init__(sh, self._gpu)
+        sh.shape = self.shape
+        sh._buffer, sh.job, sh._keep = self._buffer, self.job, self._keep
+        return sh
+
+    def _record(self, op: int, other, inplace: bool) -> Optional["Array"]:
+        """Record `self (op) other` instead of launching it; None when it cannot join a chain."""
+        if isinstance(other, _GPUArray):
+            if type(other) is not Array or tuple(other.shape) != tuple(self.shape) or other._gpu is not self._gpu:
+                return None
+            if other is self and inplace:
+                return None
+        if _prod(self.shape) == 0:
+            return None
+        if (not inplace and self._lazy is None and isinstance(other, Array) and other._lazy is not None
+                and op in _CHAIN_FLIP and other is not self):
+            return other._record(_CHAIN_FLIP[op], self, False)      # continue the other operand's chain
+        if inplace and self._consumers:          # recorded readers of the OLD value go first
+            self._flush_consumers()
+        if self._lazy is not None:
+            lz = self._lazy.extended(op, other)
+            if lz is None:                       # chain full: launch it, start a new one on its result
+                self._materialize()
+        if self._lazy is None:
+            if inplace:
+                src = self._shell()
+                lz = _Lazy([src], []).extended(op, other)
+            else:
+                lz = _Lazy([self], []).extended(op, other)
+        if inplace:
+            if self._lazy is None:
+                self._inplace_src = src
+                self._buffer, self.job, self._keep, self._view = None, None, [], None
+            self._lazy = lz
+            self._watch(lz)
+            return self
+        ret = Array.__new__(Array)
+        _GPUArray.__init__(ret, self._gpu)
+        ret.shape = tuple(self.shape)
+        ret._lazy = lz
+        ret._watch(lz)
+        return ret
+
     def _op(self, other, name: str) -> "Array":
         """Out-of-place binary op: same shape, scalar or broadcast (reference: vkarray.py:492-519)."""
+        if _fuse_depth > 0:
+            r = self._record(_CHAIN_BIN[name], other, False)
+            if r is not None:
+                return r
         n = self.buffer.size()
         if not isinstance(other, Array):
             ret = self._new()
@@ -346,6 +514,10 @@ class Array(_GPUArray):
 
     def _iop(self, other, name: str) -> "Array":
         """In-place binary op (reference: vkarray.py:533-559; NumPy rules for any rank, Q1)."""
+        if _fuse_depth > 0:
+            r = self._record(_CHAIN_BIN[name], other, True)
+            if r is not None:
+                return r
         n = self.buffer.size()
         if not isinstance(other, Array):
             return self._run(self, "i" + name + "_scalar", [self], VectorScalarParams(n, float(other)), [])
@@ -363,11 +535,19 @@ class Array(_GPUArray):
         return self._run(self, "i" + name + "_broadcast", [self, other, sh], p, [other])
 
     def _rop(self, other: Scalar, name: str) -> "Array":
+        if _fuse_depth > 0:
+            r = self._record(_CHAIN_BIN[name], other, False)
+            if r is not None:
+                return r
         ret = self._new()
         return self._run(ret, name + "_scalar", [self, ret], VectorScalarParams(self.buffer.size(), float(other)),
                          [self])
 
     def _unary(self, name: str, inplace: bool) -> "Array":
+        if _fuse_depth > 0:
+            r = self._record(_CHAIN_UNARY0 + _UNARY.index(name), None, inplace)
+            if r is not None:
+                return r
         p = VectorParams(self.buffer.size())
         if inplace:
             return self._run(self, "i" + name, [self], p, [])
