@@ -19,8 +19,13 @@
 //   warp 2      TMEM allocator (2 x BN fp32 columns: double-buffered accumulators)
 //   warps 4-7   epilogue: tcgen05.ld 32 lanes x 32 columns per warp, + bias / + C, 128-byte
 //               row segments stored straight to global memory
-// Inputs that are not K-major (A given as [K,M], B given as [K,N]) are transposed once into a
-// device workspace by a tiled transpose kernel (<2% of the GEMM time at 8192^3).
+// Operands that are not K-major (A given as [K,M], B given as [K,N]: the B of every `a @ b`, both
+// operands of Dense.backward's dW = dy^T x) are read as they lie: their tiles are MN-major in
+// shared memory (tcgen05 takes MN-major TF32 operands), fetched by one 3-D TMA per tile that
+// views the [K, MN] matrix as {32 floats of MN, K, MN/32} so that every 32-wide chunk lands as
+// its own 128-byte-swizzled slab -- the canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) layout with
+// LBO = BK*128 B, SBO = 1024 B.  Only leading dimensions that are not a multiple of 32 still go
+// through the tiled transpose kernel (VKP_TC_MN=0 forces it: A/B measurements).
 //
 // PRESPLIT variant (large problems): the converter warps saturate the shared-memory pipe (they read
 // and write every tile once more: profiles/r01_ncu_gemm_tc_notes.md), so for problems where an
@@ -68,6 +73,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
@@ -170,6 +181,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand, 128-byte swizzle: 32-float chunks of MN, each a slab of BK rows x 128 B
+// (8-row groups = one k-step of kind::tf32, 1024 B apart); consecutive chunks BK*128 B apart
+template <int BK>
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((BK * 128) >> 4) << 16;            // leading byte offset: next 32-wide chunk of MN
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: next group of 8 k
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -229,7 +253,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
                float* __restrict__ C, const float* __restrict__ bias, uint32_t M, uint32_t N, uint32_t K,
                int accumulate, uint32_t splits, uint32_t kb_per_split, vkp_tc_chunks ch,
-               const __grid_constant__ vkp_tc_pull pl) {
+               const __grid_constant__ vkp_tc_pull pl, int a_mn, int b_mn) {
+  // a_mn / b_mn: the operand lies as [K, MN] in memory (MN contiguous): 3-D tensor map, MN-major tiles
   // ch.n_chunks > 1 (row-sharded matmul, vkp_comm.cu): K is cut into n_chunks ranges that become
   // valid one after the other while this kernel runs -- the peers' shards of B, fetched over NVLink
   // by this kernel's own spare warps (pull_ranges); the producer walks them starting at ch.first
@@ -329,11 +354,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* st = smem + stage * cfg::STAGE_BYTES;
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_arrive_expect_tx(fb, PRESPLIT ? cfg::STAGE_BYTES : A_TILE_BYTES + cfg::B_TILE_BYTES);
-          tma_load_2d(smem_u32(st), &tmA, fb, (int)(kb * BK), (int)(mb * BM));
-          tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES), &tmB, fb, (int)(kb * BK), (int)(nb * BN));
+          auto load_a = [&](uint32_t dst, const CUtensorMap* m) {
+            if (a_mn) tma_load_3d(dst, m, fb, 0, (int)(kb * BK), (int)(mb * (BM / 32)));
+            else tma_load_2d(dst, m, fb, (int)(kb * BK), (int)(mb * BM));
+          };
+          auto load_b = [&](uint32_t dst, const CUtensorMap* m) {
+            if (b_mn) tma_load_3d(dst, m, fb, 0, (int)(kb * BK), (int)(nb * (BN / 32)));
+            else tma_load_2d(dst, m, fb, (int)(kb * BK), (int)(nb * BN));
+          };
+          load_a(smem_u32(st), &tmA);
+          load_b(smem_u32(st + 2 * A_TILE_BYTES), &tmB);
           if (PRESPLIT) {
-            tma_load_2d(smem_u32(st + A_TILE_BYTES), &tmAlo, fb, (int)(kb * BK), (int)(mb * BM));
-            tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + cfg::B_TILE_BYTES), &tmBlo, fb, (int)(kb * BK), (int)(nb * BN));
+            load_a(smem_u32(st + A_TILE_BYTES), &tmAlo);
+            load_b(smem_u32(st + 2 * A_TILE_BYTES + cfg::B_TILE_BYTES), &tmBlo);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -343,7 +376,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================== MMA issuer =======================================
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // (bit 15 / 16: A / B is MN-major)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24) |
+                             (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
@@ -356,16 +391,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (!PRESPLIT) mbar_wait(smem_u32(&conv_bar[stage]), phase);
           tcgen05_fence_after();
           uint8_t* st = smem + stage * cfg::STAGE_BYTES;
-          const uint64_t a_hi = make_desc<BK>(smem_u32(st));
-          const uint64_t a_lo = make_desc<BK>(smem_u32(st + A_TILE_BYTES));
-          const uint64_t b_hi = make_desc<BK>(smem_u32(st + 2 * A_TILE_BYTES));
-          const uint64_t b_lo = make_desc<BK>(smem_u32(st + 2 * A_TILE_BYTES + cfg::B_TILE_BYTES));
+          const uint32_t sa = smem_u32(st), sb = smem_u32(st + 2 * A_TILE_BYTES);
+          const uint64_t a_hi = a_mn ? make_desc_mn<BK>(sa) : make_desc<BK>(sa);
+          const uint64_t a_lo = a_mn ? make_desc_mn<BK>(sa + A_TILE_BYTES) : make_desc<BK>(sa + A_TILE_BYTES);
+          const uint64_t b_hi = b_mn ? make_desc_mn<BK>(sb) : make_desc<BK>(sb);
+          const uint64_t b_lo = b_mn ? make_desc_mn<BK>(sb + cfg::B_TILE_BYTES) : make_desc<BK>(sb + cfg::B_TILE_BYTES);
+          // one k-step (8 k): 32 bytes along a K-major swizzle row, one 1024-byte row group of an MN-major slab
+          const uint64_t step_a = a_mn ? (1024 >> 4) : ((UMMA_K * 4) >> 4);
+          const uint64_t step_b = b_mn ? (1024 >> 4) : ((UMMA_K * 4) >> 4);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; k++) {
-            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);   // 32 bytes per k-step
-            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, ((kb - kb0) | k) != 0);
-            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
-            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+            const uint64_t adv_a = k * step_a, adv_b = k * step_b;
+            umma_tf32(d_tmem, a_lo + adv_a, b_hi + adv_b, idesc, ((kb - kb0) | k) != 0);
+            umma_tf32(d_tmem, a_hi + adv_a, b_lo + adv_b, idesc, 1);
+            umma_tf32(d_tmem, a_hi + adv_a, b_hi + adv_b, idesc, 1);
           }
           tcgen05_commit(smem_u32(&empty_bar[stage]));
           if (kb == kb1 - 1) tcgen05_commit(smem_u32(&tfull_bar[acc]));
@@ -577,18 +616,46 @@ int make_map(CUtensorMap* map, const float* ptr, uint32_t rows, uint32_t K, uint
   return VKP_OK;
 }
 
+// [K, MN] fp32 matrix (MN contiguous, MN % 32 == 0) seen as {32 floats of MN, K, MN / 32}: one box brings
+// `chunks` 128-byte-swizzled slabs of bk rows, i.e. an MN-major tile of 32 * chunks x bk
+int make_map_mn(CUtensorMap* map, const float* ptr, uint32_t MN, uint32_t K, uint32_t chunks, uint32_t bk) {
+  EncodeTiledFn enc = get_encode();
+  VKP_CHECK(enc, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[3] = {32, K, MN / 32};
+  cuuint64_t strides[2] = {(cuuint64_t)MN * 4, 128};
+  cuuint32_t box[3] = {32, bk, chunks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VKP_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(MN-major) failed with %d", (int)r);
+  return VKP_OK;
+}
+
 // Alo / Btlo: pre-split low parts (MODE_PRESPLIT) or nullptr (converter warps split in shared memory)
+// a_mn / b_mn: that operand (and its low part) lies as [K, MN], not [MN, K]
 template <int BN, int BK>
 int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, const float* Alo, const float* Btlo, float* C,
               const float* bias, uint32_t M, uint32_t N, uint32_t K, int accumulate,
-              vkp_tc_chunks ch = vkp_tc_chunks{nullptr, 0, 0, 0, 1}, const vkp_tc_pull* pull = nullptr) {
+              vkp_tc_chunks ch = vkp_tc_chunks{nullptr, 0, 0, 0, 1}, const vkp_tc_pull* pull = nullptr,
+              bool a_mn = false, bool b_mn = false) {
   using cfg = Cfg<BN, BK>;
   const bool presplit = Alo != nullptr;
   CUtensorMap tmA, tmB, tmAlo, tmBlo;
-  VKP_TRY(make_map(&tmA, A, M, K, BM, BK));
-  VKP_TRY(make_map(&tmB, Bt, N, K, BN, BK));
-  VKP_TRY(make_map(&tmAlo, presplit ? Alo : A, M, K, BM, BK));
-  VKP_TRY(make_map(&tmBlo, presplit ? Btlo : Bt, N, K, BN, BK));
+  if (a_mn) {
+    VKP_TRY(make_map_mn(&tmA, A, M, K, BM / 32, BK));
+    VKP_TRY(make_map_mn(&tmAlo, presplit ? Alo : A, M, K, BM / 32, BK));
+  } else {
+    VKP_TRY(make_map(&tmA, A, M, K, BM, BK));
+    VKP_TRY(make_map(&tmAlo, presplit ? Alo : A, M, K, BM, BK));
+  }
+  if (b_mn) {
+    VKP_TRY(make_map_mn(&tmB, Bt, N, K, BN / 32, BK));
+    VKP_TRY(make_map_mn(&tmBlo, presplit ? Btlo : Bt, N, K, BN / 32, BK));
+  } else {
+    VKP_TRY(make_map(&tmB, Bt, N, K, BN, BK));
+    VKP_TRY(make_map(&tmBlo, presplit ? Btlo : Bt, N, K, BN, BK));
+  }
   static const bool rewrite_hi = getenv("VKP_TC_REWRITE_HI") != nullptr;
   auto kernel = presplit ? gemm_tc_kernel<BN, BK, MODE_PRESPLIT>
                          : (rewrite_hi ? gemm_tc_kernel<BN, BK, MODE_CONVERT_REWRITE_HI> : gemm_tc_kernel<BN, BK, MODE_CONVERT>);
@@ -618,7 +685,8 @@ int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, const float* Alo, c
   const uint32_t work = tiles * splits;
   const unsigned grid = work < (uint32_t)ctx->sms ? work : (unsigned)ctx->sms;
   kernel<<<grid, NUM_THREADS, cfg::SMEM_BYTES, ctx->stream>>>(
-      tmA, tmB, tmAlo, tmBlo, dst, splits > 1 ? nullptr : bias, M, N, K, splits > 1 ? 0 : accumulate, splits, kb_per, ch, pl);
+      tmA, tmB, tmAlo, tmBlo, dst, splits > 1 ? nullptr : bias, M, N, K, splits > 1 ? 0 : accumulate, splits, kb_per, ch, pl,
+      a_mn ? 1 : 0, b_mn ? 1 : 0);
   VKP_TRY(vkp_after_launch(ctx, "gemm_tc(tcgen05 3xTF32)"));
   if (splits > 1) {
     const unsigned rgrid = vkp_grid_for(ctx, ((size_t)M * N + 3) / 4, 256, 8);
@@ -644,71 +712,83 @@ int vkp_gemm_tc_supported(int transA, int transB, uint32_t M, uint32_t N, uint32
   return 1;
 }
 
-// The pre-split variant pays one extra pass over the operands (8 B per element, 12 with the
-// transpose) to take the converter warps off the shared-memory pipe; worth it once the contraction
-// is long next to that pass.  VKP_TC_PRESPLIT=0/1 forces the choice.
+// The pre-split variant pays one extra pass over the operands (8 B per element) to take the
+// converter warps off the shared-memory pipe; worth it once the contraction is long next to that
+// pass.  VKP_TC_PRESPLIT=0/1 forces the choice.
 static bool use_presplit(uint32_t M, uint32_t N, uint32_t K) {
   static const char* env = getenv("VKP_TC_PRESPLIT");
   if (env) return env[0] == '1';
   (void)K;
-  return M >= 2048 && N >= 2048;
+  // pre-pass ~ (M + N) K bytes against a contraction ~ M N K: config 5's Dense GEMMs (8192 x 1024 x 1024 forward,
+  // 1024 x 1024 x 8192 weight gradient) gain 30-40 us each over the converter variant (52-57 % tensor pipe)
+  return M >= 512 && N >= 512 && (uint64_t)M * N >= 512ull * ((uint64_t)M + N);
 }
 
 int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
                 const float* B, float* C, const float* bias, int accumulate) {
-  // bring both operands to K-major: A as [M,K], B as [N,K]
+  // A as [M,K] and B as [N,K] are K-major; the other two storage orders are taken as MN-major tiles
+  // when their leading dimension allows the 3-D tensor map, else transposed once into the workspace
+  static bool mn_ok = !(getenv("VKP_TC_MN") && getenv("VKP_TC_MN")[0] == '0');
   const bool presplit = use_presplit(M, N, K);
-  const float* Ak = A;
-  const float* Bk = B;
-  const float* Alo = nullptr;
-  const float* Blo = nullptr;
-  const size_t a_elems = (size_t)M * K, b_elems = (size_t)N * K;
-  size_t need = 0;
-  if (transA) need += a_elems * 4;
-  if (!transB) need += b_elems * 4;
-  if (presplit) need += (a_elems + b_elems) * 4;
-  if (need) {
-    void* ws;
-    VKP_TRY(vkp_workspace(ctx, 1, need, &ws));
-    float* w = static_cast<float*>(ws);
-    float* alo = nullptr;
-    float* blo = nullptr;
-    if (presplit) {
-      alo = w; w += a_elems;
-      blo = w; w += b_elems;
-      Alo = alo; Blo = blo;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    const bool a_mn = transA && mn_ok && M % 32 == 0;
+    const bool b_mn = !transB && mn_ok && N % 32 == 0;
+    const bool a_tr = transA && !a_mn, b_tr = !transB && !b_mn;
+    const float* Ak = A;
+    const float* Bk = B;
+    const float* Alo = nullptr;
+    const float* Blo = nullptr;
+    const size_t a_elems = (size_t)M * K, b_elems = (size_t)N * K;
+    size_t need = 0;
+    if (a_tr) need += a_elems * 4;
+    if (b_tr) need += b_elems * 4;
+    if (presplit) need += (a_elems + b_elems) * 4;
+    if (need) {
+      void* ws;
+      VKP_TRY(vkp_workspace(ctx, 1, need, &ws));
+      float* w = static_cast<float*>(ws);
+      float* alo = nullptr;
+      float* blo = nullptr;
+      if (presplit) {
+        alo = w; w += a_elems;
+        blo = w; w += b_elems;
+        Alo = alo; Blo = blo;
+      }
+      if (a_tr) {     // A stored [K, M] -> [M, K]
+        launch_transpose(ctx->stream, A, w, alo, K, M, K);
+        VKP_TRY(vkp_after_launch(ctx, "transpose(A)"));
+        Ak = w;
+        w += a_elems;
+      } else if (presplit) {   // low parts in the operand's own layout (element-wise)
+        split_lo_kernel<<<vkp_grid_for(ctx, a_elems / 4, 256, 8), 256, 0, ctx->stream>>>(
+            reinterpret_cast<const float4*>(A), reinterpret_cast<float4*>(alo), a_elems / 4);
+        VKP_TRY(vkp_after_launch(ctx, "split_lo(A)"));
+      }
+      if (b_tr) {     // B stored [K, N] -> [N, K]
+        launch_transpose(ctx->stream, B, w, blo, K, N, K);
+        VKP_TRY(vkp_after_launch(ctx, "transpose(B)"));
+        Bk = w;
+      } else if (presplit) {
+        split_lo_kernel<<<vkp_grid_for(ctx, b_elems / 4, 256, 8), 256, 0, ctx->stream>>>(
+            reinterpret_cast<const float4*>(B), reinterpret_cast<float4*>(blo), b_elems / 4);
+        VKP_TRY(vkp_after_launch(ctx, "split_lo(B)"));
+      }
     }
-    if (transA) {   // A stored [K, M] -> [M, K]
-      launch_transpose(ctx->stream, A, w, alo, K, M, K);
-      VKP_TRY(vkp_after_launch(ctx, "transpose(A)"));
-      Ak = w;
-      w += a_elems;
-    } else if (presplit) {
-      split_lo_kernel<<<vkp_grid_for(ctx, a_elems / 4, 256, 8), 256, 0, ctx->stream>>>(
-          reinterpret_cast<const float4*>(A), reinterpret_cast<float4*>(alo), a_elems / 4);
-      VKP_TRY(vkp_after_launch(ctx, "split_lo(A)"));
-    }
-    if (!transB) {  // B stored [K, N] -> [N, K]
-      launch_transpose(ctx->stream, B, w, blo, K, N, K);
-      VKP_TRY(vkp_after_launch(ctx, "transpose(B)"));
-      Bk = w;
-    } else if (presplit) {
-      split_lo_kernel<<<vkp_grid_for(ctx, b_elems / 4, 256, 8), 256, 0, ctx->stream>>>(
-          reinterpret_cast<const float4*>(B), reinterpret_cast<float4*>(blo), b_elems / 4);
-      VKP_TRY(vkp_after_launch(ctx, "split_lo(B)"));
-    }
+    if (bias && (((uintptr_t)bias) & 15)) return vkp_set_error("vkp_gemm_tc: bias must be 16-byte aligned");
+    const bool wide = getenv("VKP_TC_BN128") == nullptr && (N % 256 == 0 || N >= 1024);
+    // pre-split tiles need no converter pass, so shorter k-blocks (64-byte swizzle rows) buy a 4-deep
+    // ring in the same shared memory: 8192^3 4.46 -> 4.27 ms; with converters BK=32 stays ahead
+    static const char* bk_env = getenv("VKP_TC_BK16");
+    const bool bk16 = bk_env ? bk_env[0] == '1' : presplit;
+    const vkp_tc_chunks no_chunks{nullptr, 0, 0, 0, 1};
+    int rc;
+    if (wide && bk16) rc = launch_tc<256, 16>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, a_mn, b_mn);
+    else if (wide) rc = launch_tc<256, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, a_mn, b_mn);
+    else rc = launch_tc<128, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, a_mn, b_mn);
+    if (rc == VKP_OK || !(a_mn || b_mn) || !strstr(vkp_last_error(), "MN-major")) return rc;
+    mn_ok = false;      // this driver refuses the 3-D map: transposes from now on
   }
-  if (bias && (((uintptr_t)bias) & 15)) return vkp_set_error("vkp_gemm_tc: bias must be 16-byte aligned");
-  const bool wide = getenv("VKP_TC_BN128") == nullptr && (N % 256 == 0 || N >= 1024);
-  // pre-split tiles need no converter pass, so shorter k-blocks (64-byte swizzle rows) buy a 4-deep
-  // ring in the same shared memory: 8192^3 4.46 -> 4.27 ms; with converters BK=32 stays ahead
-  static const char* bk_env = getenv("VKP_TC_BK16");
-  const bool bk16 = bk_env ? bk_env[0] == '1' : presplit;
-  if (wide) {
-    if (bk16) return launch_tc<256, 16>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate);
-    return launch_tc<256, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate);
-  }
-  return launch_tc<128, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate);
+  return VKP_ERR;
 }
 
 // ---- pieces of the row-sharded matmul (vkp_comm.cu): operands pre-split, K arriving in ranges ----

@@ -278,7 +278,7 @@ xoshiro_normal_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ st
     for (uint32_t i = 0; i < batch; i++) {
       float o0, o1;
       VKP_BM_PAIR(o0, o1);
-      *reinterpret_cast<float2*>(o) = make_float2(o0, o1);
+      __stcs(reinterpret_cast<float2*>(o), make_float2(o0, o1));
       o += size;
     }
     iters -= batch;
@@ -413,7 +413,8 @@ static int rng_generate(vkp_rng* rng, void* out, uint64_t n_out, float mean, flo
     const uint64_t draws_per_lane = (n_draw + size - 1) / size;
     // segment length: power of two, >= 256 draws, giving about sms * 1024 threads (VKP_PRNG_THREADS_PER_SM)
     static const uint64_t tps = getenv("VKP_PRNG_THREADS_PER_SM") ? (uint64_t)atoll(getenv("VKP_PRNG_THREADS_PER_SM")) : 1024;
-    static const bool cs = getenv("VKP_PRNG_STCS") && getenv("VKP_PRNG_STCS")[0] == '1';
+    // streaming stores: +3-4 % at both lane counts (profiles/r02_prng_variants.txt); VKP_PRNG_STCS=0 for A/B
+    static const bool cs = !(getenv("VKP_PRNG_STCS") && getenv("VKP_PRNG_STCS")[0] == '0');
     uint64_t want_seg = ((uint64_t)ctx->sms * tps + groups - 1) / groups;
     if (want_seg < 1) want_seg = 1;
     uint64_t L = (draws_per_lane + want_seg - 1) / want_seg;
