@@ -23,8 +23,8 @@
 // operands of Dense.backward's dW = dy^T x) are read as they lie: their tiles are MN-major in
 // shared memory (tcgen05 takes MN-major TF32 operands), fetched by one 3-D TMA per tile that
 // views the [K, MN] matrix as {32 floats of MN, K, MN/32} so that every 32-wide chunk lands as
-// its own 128-byte-swizzled slab -- the canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) layout with
-// LBO = BK*128 B, SBO = 1024 B.  Only leading dimensions that are not a multiple of 32 still go
+// its own slab of BK rows x 128 B, swizzled in 32-byte atoms (the only MN-major form tcgen05 takes
+// for 32-bit data: SWIZZLE_128B_BASE32B, LBO = BK*128 B between chunks, SBO = 512 B between 4-row groups).  Only leading dimensions that are not a multiple of 32 still go
 // through the tiled transpose kernel (VKP_TC_MN=0 forces it: A/B measurements).
 //
 // PRESPLIT variant (large problems): the converter warps saturate the shared-memory pipe (they read
@@ -181,16 +181,19 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return d;
 }
 
-// MN-major operand, 128-byte swizzle: 32-float chunks of MN, each a slab of BK rows x 128 B
-// (8-row groups = one k-step of kind::tf32, 1024 B apart); consecutive chunks BK*128 B apart
+// MN-major operand.  For 32-bit (TF32) data tcgen05 takes only the 128-byte swizzle with 32-byte atoms
+// (layout type 1, SWIZZLE_128B_BASE32B; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 32-float chunks of
+// MN, each a slab of BK rows x 128 B in which the four 32-byte pieces of row r sit at piece ^ (r & 3).
+// Canonical form ((8,n),(4,k)):((1,LBO),(8,SBO)) in 16-byte units: groups of 4 k-rows are 512 B
+// apart (SBO), consecutive chunks BK*128 B apart (LBO); one k-step of kind::tf32 (8 k) = 1024 B.
 template <int BK>
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
   d |= (uint64_t)((BK * 128) >> 4) << 16;            // leading byte offset: next 32-wide chunk of MN
-  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: next group of 8 k
+  d |= (uint64_t)(512 >> 4) << 32;                   // stride byte offset: next group of 4 k
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  d |= (uint64_t)1 << 61;                            // SWIZZLE_128B_BASE32B
   return d;
 }
 
@@ -354,13 +357,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* st = smem + stage * cfg::STAGE_BYTES;
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_arrive_expect_tx(fb, PRESPLIT ? cfg::STAGE_BYTES : A_TILE_BYTES + cfg::B_TILE_BYTES);
+          // MN-major operand: mode 1 = one 3-D box {32, BK, chunks}; mode 2 = one 2-D box {32, BK} per
+          // 32-wide chunk of the [K, MN] matrix, each landing as its own BK x 128 B slab
           auto load_a = [&](uint32_t dst, const CUtensorMap* m) {
-            if (a_mn) tma_load_3d(dst, m, fb, 0, (int)(kb * BK), (int)(mb * (BM / 32)));
-            else tma_load_2d(dst, m, fb, (int)(kb * BK), (int)(mb * BM));
+            if (a_mn == 1) tma_load_3d(dst, m, fb, 0, (int)(kb * BK), (int)(mb * (BM / 32)));
+            else if (a_mn == 2) {
+              for (int c = 0; c < BM / 32; c++) tma_load_2d(dst + c * BK * 128, m, fb, (int)(mb * BM + c * 32), (int)(kb * BK));
+            } else tma_load_2d(dst, m, fb, (int)(kb * BK), (int)(mb * BM));
           };
           auto load_b = [&](uint32_t dst, const CUtensorMap* m) {
-            if (b_mn) tma_load_3d(dst, m, fb, 0, (int)(kb * BK), (int)(nb * (BN / 32)));
-            else tma_load_2d(dst, m, fb, (int)(kb * BK), (int)(nb * BN));
+            if (b_mn == 1) tma_load_3d(dst, m, fb, 0, (int)(kb * BK), (int)(nb * (BN / 32)));
+            else if (b_mn == 2) {
+              for (int c = 0; c < BN / 32; c++) tma_load_2d(dst + c * BK * 128, m, fb, (int)(nb * BN + c * 32), (int)(kb * BK));
+            } else tma_load_2d(dst, m, fb, (int)(kb * BK), (int)(nb * BN));
           };
           load_a(smem_u32(st), &tmA);
           load_b(smem_u32(st + 2 * A_TILE_BYTES), &tmB);
@@ -618,15 +627,26 @@ int make_map(CUtensorMap* map, const float* ptr, uint32_t rows, uint32_t K, uint
 
 // [K, MN] fp32 matrix (MN contiguous, MN % 32 == 0) seen as {32 floats of MN, K, MN / 32}: one box brings
 // `chunks` 128-byte-swizzled slabs of bk rows, i.e. an MN-major tile of 32 * chunks x bk
-int make_map_mn(CUtensorMap* map, const float* ptr, uint32_t MN, uint32_t K, uint32_t chunks, uint32_t bk) {
+int make_map_mn(CUtensorMap* map, const float* ptr, uint32_t MN, uint32_t K, uint32_t chunks, uint32_t bk, int mode) {
   EncodeTiledFn enc = get_encode();
   VKP_CHECK(enc, "cuTensorMapEncodeTiled is not available from this driver");
+  if (mode == 2) {   // plain 2-D view of the [K, MN] matrix, one 32-wide chunk per box
+    cuuint64_t dims2[2] = {MN, K};
+    cuuint64_t strides2[1] = {(cuuint64_t)MN * 4};
+    cuuint32_t box2[2] = {32, bk};
+    cuuint32_t estr2[2] = {1, 1};
+    CUresult r2 = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims2, strides2, box2, estr2,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VKP_CHECK(r2 == CUDA_SUCCESS, "cuTensorMapEncodeTiled(MN-major, 2-D) failed with %d", (int)r2);
+    return VKP_OK;
+  }
   cuuint64_t dims[3] = {32, K, MN / 32};
   cuuint64_t strides[2] = {(cuuint64_t)MN * 4, 128};
   cuuint32_t box[3] = {32, bk, chunks};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VKP_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(MN-major) failed with %d", (int)r);
   return VKP_OK;
@@ -638,20 +658,20 @@ template <int BN, int BK>
 int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, const float* Alo, const float* Btlo, float* C,
               const float* bias, uint32_t M, uint32_t N, uint32_t K, int accumulate,
               vkp_tc_chunks ch = vkp_tc_chunks{nullptr, 0, 0, 0, 1}, const vkp_tc_pull* pull = nullptr,
-              bool a_mn = false, bool b_mn = false) {
+              int a_mn = 0, int b_mn = 0) {
   using cfg = Cfg<BN, BK>;
   const bool presplit = Alo != nullptr;
   CUtensorMap tmA, tmB, tmAlo, tmBlo;
   if (a_mn) {
-    VKP_TRY(make_map_mn(&tmA, A, M, K, BM / 32, BK));
-    VKP_TRY(make_map_mn(&tmAlo, presplit ? Alo : A, M, K, BM / 32, BK));
+    VKP_TRY(make_map_mn(&tmA, A, M, K, BM / 32, BK, a_mn));
+    VKP_TRY(make_map_mn(&tmAlo, presplit ? Alo : A, M, K, BM / 32, BK, a_mn));
   } else {
     VKP_TRY(make_map(&tmA, A, M, K, BM, BK));
     VKP_TRY(make_map(&tmAlo, presplit ? Alo : A, M, K, BM, BK));
   }
   if (b_mn) {
-    VKP_TRY(make_map_mn(&tmB, Bt, N, K, BN / 32, BK));
-    VKP_TRY(make_map_mn(&tmBlo, presplit ? Btlo : Bt, N, K, BN / 32, BK));
+    VKP_TRY(make_map_mn(&tmB, Bt, N, K, BN / 32, BK, b_mn));
+    VKP_TRY(make_map_mn(&tmBlo, presplit ? Btlo : Bt, N, K, BN / 32, BK, b_mn));
   } else {
     VKP_TRY(make_map(&tmB, Bt, N, K, BN, BK));
     VKP_TRY(make_map(&tmBlo, presplit ? Btlo : Bt, N, K, BN, BK));
@@ -686,7 +706,7 @@ int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, const float* Alo, c
   const unsigned grid = work < (uint32_t)ctx->sms ? work : (unsigned)ctx->sms;
   kernel<<<grid, NUM_THREADS, cfg::SMEM_BYTES, ctx->stream>>>(
       tmA, tmB, tmAlo, tmBlo, dst, splits > 1 ? nullptr : bias, M, N, K, splits > 1 ? 0 : accumulate, splits, kb_per, ch, pl,
-      a_mn ? 1 : 0, b_mn ? 1 : 0);
+      a_mn, b_mn);
   VKP_TRY(vkp_after_launch(ctx, "gemm_tc(tcgen05 3xTF32)"));
   if (splits > 1) {
     const unsigned rgrid = vkp_grid_for(ctx, ((size_t)M * N + 3) / 4, 256, 8);
@@ -731,6 +751,7 @@ int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, ui
   static bool mn_ok = !(getenv("VKP_TC_MN") && getenv("VKP_TC_MN")[0] == '0');
   const bool presplit = use_presplit(M, N, K);
   for (int attempt = 0; attempt < 2; attempt++) {
+    static const int mn_mode = getenv("VKP_TC_MN_TMA") ? atoi(getenv("VKP_TC_MN_TMA")) : 1;   // 1: one 3-D box per tile (default), 2: one 2-D box per 32-wide chunk
     const bool a_mn = transA && mn_ok && M % 32 == 0;
     const bool b_mn = !transB && mn_ok && N % 32 == 0;
     const bool a_tr = transA && !a_mn, b_tr = !transB && !b_mn;
@@ -782,9 +803,10 @@ int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, ui
     const bool bk16 = bk_env ? bk_env[0] == '1' : presplit;
     const vkp_tc_chunks no_chunks{nullptr, 0, 0, 0, 1};
     int rc;
-    if (wide && bk16) rc = launch_tc<256, 16>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, a_mn, b_mn);
-    else if (wide) rc = launch_tc<256, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, a_mn, b_mn);
-    else rc = launch_tc<128, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, a_mn, b_mn);
+    const int am = a_mn ? mn_mode : 0, bm = b_mn ? mn_mode : 0;
+    if (wide && bk16) rc = launch_tc<256, 16>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm);
+    else if (wide) rc = launch_tc<256, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm);
+    else rc = launch_tc<128, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm);
     if (rc == VKP_OK || !(a_mn || b_mn) || !strstr(vkp_last_error(), "MN-major")) return rc;
     mn_ok = false;      // this driver refuses the 3-D map: transposes from now on
   }
