@@ -489,6 +489,8 @@ def sharded_block(B):
     a_f = rs.uniform(0.5, 2, (R, Cc)).astype(F)
     b_f = rs.uniform(0.5, 2, (R, Cc)).astype(F)
     a, b = g.shard(a_f), g.shard(b_f)
+    p_f = rs.uniform(0.97, 1.03, (R, Cc)).astype(F)          # products over 64 * world rows stay inside float32
+    pa = g.shard(p_f)
     for mode in (1, 0):                        # peer mailbox, then plain NCCL
         peer = g.t.peer_mode(mode)
         np.testing.assert_array_equal((a + b).to_numpy(), a_f + b_f)
@@ -496,7 +498,7 @@ def sharded_block(B):
         np.testing.assert_array_equal(np.asarray(a.maximum()), [a_f.max()])
         np.testing.assert_array_equal(np.asarray(a.minimum(axis=0)), a_f.min(axis=0))
         np.testing.assert_allclose(np.asarray(a.sum(axis=0)), a_f.astype(np.float64).sum(axis=0), rtol=2e-6)
-        np.testing.assert_allclose(np.asarray(a.prod(axis=0)), a_f.astype(np.float64).prod(axis=0), rtol=2e-5)
+        np.testing.assert_allclose(np.asarray(pa.prod(axis=0)), p_f.astype(np.float64).prod(axis=0), rtol=2e-5)
         np.testing.assert_allclose(a.sum(axis=1).to_numpy(), a_f.astype(np.float64).sum(axis=1), rtol=2e-6)
         np.testing.assert_allclose(np.asarray(a.mean()), [a_f.astype(np.float64).mean()], rtol=2e-6)
         np.testing.assert_allclose(a.maximum(axis=0, rebroadcast=True).to_numpy(),

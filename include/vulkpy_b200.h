@@ -154,9 +154,18 @@ VKP_API int vkp_ew_chain(vkp_ctx* ctx, int n_in, const float* const* in, float* 
 #define VKP_GEMM_FORCE_SIMT 1
 #define VKP_GEMM_FORCE_TC   2
 #define VKP_GEMM_ACCUMULATE 4  /* C += instead of C = */
+#define VKP_GEMM_RELU       8  /* C = max(C, 0) after bias: Dense.forward followed by ReLU.forward (x.max(0.0),
+                                * nn/layers.py:186) in the GEMM epilogue, same float32 operation */
 VKP_API int vkp_gemm(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K,
              const float* A, const float* B, float* C, const float* bias, int flags,
              vkp_job** job);
+
+/* vkp_gemm with an activation gradient folded into the epilogue: relu_mask ([M, N] like C, or NULL) is the OUTPUT y of
+ * the ReLU in front of this layer and every C element becomes max(sign(y), 0) * C -- ReLU.backward (nn/layers.py:207-210)
+ * applied to the dx = dy W contraction of Dense.backward, bit-identical to the separate job. */
+VKP_API int vkp_gemm_fused(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K,
+                           const float* A, const float* B, float* C, const float* bias, const float* relu_mask,
+                           int flags, vkp_job** job);
 
 /* ---- fused vulkpy.nn steps: same float32 operations, order and roundings as the
  * reference's op-by-op compositions, one kernel each ------------------------------------------- */

@@ -68,6 +68,8 @@ PROTOTYPES = {
                                C.POINTER(C.c_float), C.POINTER(_vp)]),
     "vkp_gemm": (C.c_int, [_vp, C.c_int, C.c_int, _u32, _u32, _u32, _vp, _vp, _vp, _vp, C.c_int,
                            C.POINTER(_vp)]),
+    "vkp_gemm_fused": (C.c_int, [_vp, C.c_int, C.c_int, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, C.c_int,
+                                 C.POINTER(_vp)]),
     "vkp_nn_adam": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz] + [C.c_float] * 8 + [C.POINTER(_vp)]),
     "vkp_nn_activation_backward": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz, C.POINTER(_vp)]),
     "vkp_nn_softmax_forward": (C.c_int, [_vp, _vp, _vp, _u32, _u32, C.POINTER(_vp)]),
@@ -343,10 +345,11 @@ class Device:
         return Job(job.value)
 
     def gemm(self, transA: bool, transB: bool, M: int, N: int, K: int, A: Buffer, B: Buffer, Cbuf: Buffer,
-             bias: Optional[Buffer] = None, flags: int = 0) -> Job:
+             bias: Optional[Buffer] = None, flags: int = 0, relu_mask: Optional[Buffer] = None) -> Job:
         job = _vp()
-        _check(lib.vkp_gemm(self._ctx, int(transA), int(transB), M, N, K, A.ptr, B.ptr, Cbuf.ptr,
-                            bias.ptr if bias is not None else None, flags, C.byref(job)))
+        _check(lib.vkp_gemm_fused(self._ctx, int(transA), int(transB), M, N, K, A.ptr, B.ptr, Cbuf.ptr,
+                                  bias.ptr if bias is not None else None,
+                                  relu_mask.ptr if relu_mask is not None else None, flags, C.byref(job)))
         return Job(job.value)
 
     def argreduce(self, op: int, src: Buffer, dst: "Shape", prev: int, axis: int, post: int) -> Job:

@@ -307,6 +307,7 @@ __global__ void iota_kernel(uint32_t* out, uint32_t n) {
 
 extern "C" int vkp_argreduce(vkp_ctx* ctx, int op, const float* in, uint32_t* out, uint32_t prev, uint32_t axis,
                              uint32_t post, vkp_job** job) {
+  VKP_RANGE(__func__);
   VKP_CHECK(ctx && in && out, "vkp_argreduce: null argument");
   VKP_CHECK(op == 0 || op == 1, "vkp_argreduce: op must be 0 (max) or 1 (min)");
   VKP_CHECK(prev >= 1 && axis >= 1 && post >= 1, "attempt to get argmax of an empty sequence");
@@ -320,6 +321,7 @@ extern "C" int vkp_argreduce(vkp_ctx* ctx, int op, const float* in, uint32_t* ou
 
 // out[0..n) = indices 0..n-1 stably sorted by keys[0..n)  (keys are left untouched)
 extern "C" int vkp_argsort_u32(vkp_ctx* ctx, const uint32_t* keys, uint32_t* out, uint32_t n, vkp_job** job) {
+  VKP_RANGE(__func__);
   VKP_CHECK(ctx && (n == 0 || (keys && out)), "vkp_argsort_u32: null argument");
   VKP_TRY(vkp_make_current(ctx));
   std::lock_guard<std::mutex> g(ctx->mu);

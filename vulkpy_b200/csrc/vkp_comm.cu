@@ -156,6 +156,7 @@ extern "C" int vkp_comm_destroy(vkp_ctx* ctx) {
 
 extern "C" int vkp_comm_allgather(vkp_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank,
                                   vkp_job** job) {
+  VKP_RANGE("vkp_comm_allgather");
   VKP_CHECK(ctx && ctx->comm, "vkp_comm_allgather: communicator not initialised");
   VKP_TRY(vkp_make_current(ctx));
   std::lock_guard<std::mutex> g(ctx->mu);
@@ -581,6 +582,7 @@ static bool peer_ready(vkp_ctx* ctx, vkp_comm_state* st, size_t floats) {
 
 extern "C" int vkp_comm_allreduce(vkp_ctx* ctx, const float* send, float* recv, size_t count, int op,
                                   vkp_job** job) {
+  VKP_RANGE("vkp_comm_allreduce");
   VKP_CHECK(ctx && ctx->comm, "vkp_comm_allreduce: communicator not initialised");
   VKP_CHECK(op >= 0 && op <= 3, "vkp_comm_allreduce: bad op %d", op);
   VKP_TRY(vkp_make_current(ctx));
@@ -620,6 +622,7 @@ __global__ void __launch_bounds__(256) scale_many_kernel(ScaleMany p, float scal
 
 extern "C" int vkp_comm_allreduce_multi(vkp_ctx* ctx, float* const* bufs, const size_t* counts, int n, int op,
                                         float scale, vkp_job** job) {
+  VKP_RANGE("vkp_comm_allreduce_multi");
   VKP_CHECK(ctx && ctx->comm, "vkp_comm_allreduce_multi: communicator not initialised");
   VKP_CHECK(bufs && counts && n >= 1 && n <= VKP_MAX_BUCKET, "vkp_comm_allreduce_multi: 1..%d tensors", VKP_MAX_BUCKET);
   VKP_CHECK(op >= 0 && op <= 3, "vkp_comm_allreduce_multi: bad op %d", op);
@@ -673,6 +676,7 @@ extern "C" int vkp_comm_allreduce_multi(vkp_ctx* ctx, float* const* bufs, const 
 // without peer memory) reduce into `out` and all-reduce it in place with NCCL.
 extern "C" int vkp_comm_reduce_allreduce(vkp_ctx* ctx, int op, const float* in, float* out, uint32_t prev,
                                          uint32_t axis, uint32_t post, vkp_job** job) {
+  VKP_RANGE("vkp_comm_reduce_allreduce");
   VKP_CHECK(ctx && ctx->comm, "vkp_comm_reduce_allreduce: communicator not initialised");
   VKP_CHECK(in && out && op >= 0 && op <= 3, "vkp_comm_reduce_allreduce: bad argument");
   VKP_TRY(vkp_make_current(ctx));
@@ -724,6 +728,7 @@ extern "C" int vkp_comm_peer_mode(vkp_ctx* ctx, int mode, int* active) {
 }
 
 extern "C" int vkp_comm_barrier(vkp_ctx* ctx, vkp_job** job) {
+  VKP_RANGE("vkp_comm_barrier");
   VKP_CHECK(ctx && ctx->comm, "vkp_comm_barrier: communicator not initialised");
   VKP_TRY(vkp_make_current(ctx));
   std::lock_guard<std::mutex> g(ctx->mu);
@@ -734,6 +739,7 @@ extern "C" int vkp_comm_barrier(vkp_ctx* ctx, vkp_job** job) {
 
 extern "C" int vkp_comm_matmul_allgather(vkp_ctx* ctx, uint32_t M, uint32_t N, uint32_t K, const float* A,
                                          const float* B_shard, float* C, vkp_job** job) {
+  VKP_RANGE("vkp_comm_matmul_allgather");
   VKP_CHECK(ctx && ctx->comm, "vkp_comm_matmul_allgather: communicator not initialised");
   VKP_CHECK(A && B_shard && C, "vkp_comm_matmul_allgather: null argument");
   vkp_comm_state* st = ctx->comm;

@@ -12,6 +12,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: no-ops unless a tool (Nsight Systems / Compute) is attached
+
 #include "../../include/vulkpy_b200.h"
 
 #define VKP_OK 0
@@ -38,6 +40,17 @@ int vkp_set_error(const char* fmt, ...);
     int _r = (expr);           \
     if (_r != VKP_OK) return _r; \
   } while (0)
+
+// NVTX range around one public entry point (named like the reference shader / C-ABI call it serves):
+// the timeline of a profiler shows `add`, `sum_axis`, `vkp_gemm`, `vkp_comm_allreduce` ... as ranges with
+// their kernels inside.  The reference's analogue is util.enable_debug's API dump (vulkpy/util.py:19-55).
+struct vkp_nvtx_range {
+  explicit vkp_nvtx_range(const char* name) { nvtxRangePushA(name); }
+  ~vkp_nvtx_range() { nvtxRangePop(); }
+  vkp_nvtx_range(const vkp_nvtx_range&) = delete;
+  vkp_nvtx_range& operator=(const vkp_nvtx_range&) = delete;
+};
+#define VKP_RANGE(name) vkp_nvtx_range _vkp_range(name)
 
 struct vkp_block {
   void* ptr = nullptr;
@@ -148,8 +161,16 @@ int vkp_launch_reduce(vkp_ctx* ctx, int fam, int sub, void* const* bufs, int nbu
                       const void* params, size_t pbytes);
 int vkp_launch_gather(vkp_ctx* ctx, int fam, int sub, void* const* bufs, int nbuf,
                       const void* params, size_t pbytes);
+// Element-wise step applied to every output of a GEMM after bias / accumulate (fused activation):
+//   relu : C = max(C, 0)                      ReLU.forward = x.max(0.0)       (nn/layers.py:186)
+//   mask : C = max(sign(mask), 0) * C         ReLU.backward on the dx GEMM    (nn/layers.py:207-210)
+struct vkp_gemm_post {
+  int relu;
+  const float* mask;   // [M, N] like C, or nullptr
+};
 int vkp_launch_gemm(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K,
-                    const float* A, const float* B, float* C, const float* bias, int flags);
+                    const float* A, const float* B, float* C, const float* bias, int flags,
+                    vkp_gemm_post post = vkp_gemm_post{0, nullptr});
 
 // op families
 enum {

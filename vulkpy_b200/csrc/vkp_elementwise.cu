@@ -635,6 +635,7 @@ int vkp_launch_elementwise(vkp_ctx* ctx, int fam, int sub, void* const* bufs, in
 }
 
 extern "C" int vkp_fill_u32(vkp_ctx* ctx, void* dst, size_t count, uint32_t bits, vkp_job** job) {
+  VKP_RANGE("vkp_fill_u32");
   VKP_CHECK(ctx && (dst || count == 0), "vkp_fill_u32: null argument");
   VKP_TRY(vkp_make_current(ctx));
   std::lock_guard<std::mutex> g(ctx->mu);
@@ -653,6 +654,7 @@ extern "C" int vkp_fill_u32(vkp_ctx* ctx, void* dst, size_t count, uint32_t bits
 // scalars[k] its value when it is a scalar.  `out` may alias any input.
 extern "C" int vkp_ew_chain(vkp_ctx* ctx, int n_in, const float* const* in, float* out, size_t count, int n_steps,
                             const int* ops, const int* srcs, const float* scalars, vkp_job** job) {
+  VKP_RANGE("vkp_ew_chain");
   VKP_CHECK(ctx && in && out && ops && srcs && scalars, "vkp_ew_chain: null argument");
   VKP_CHECK(n_in >= 1 && n_in <= 4, "vkp_ew_chain: 1..4 inputs, got %d", n_in);
   VKP_CHECK(n_steps >= 1 && n_steps <= CH_MAX_STEPS, "vkp_ew_chain: 1..%d steps, got %d", CH_MAX_STEPS, n_steps);

@@ -18,18 +18,26 @@
 int vkp_gemm_tc_supported(int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
                           const float* B, float* C, int forced);
 int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
-                const float* B, float* C, const float* bias, int accumulate);
+                const float* B, float* C, const float* bias, int accumulate, vkp_gemm_post post);
+
+#include "vkp_math.cuh"
 
 namespace {
 
 constexpr int TM = 64, TN = 64, TK = 16;
+
+__device__ __forceinline__ float post1(float v, const vkp_gemm_post& p, size_t idx) {
+  if (p.relu) v = fmaxf(v, 0.0f);
+  if (p.mask) v = fmaxf(vkpm::sign_f(p.mask[idx]), 0.0f) * v;
+  return v;
+}
 
 // C[m,n] (+)= sum_k a(m,k) b(k,n) + bias[n]
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
                  const float* __restrict__ bias, uint32_t M, uint32_t N, uint32_t K, int accumulate,
-                 uint32_t k_per_split) {
+                 uint32_t k_per_split, vkp_gemm_post post) {
   // blockIdx.z selects a K slice (split-K for skinny problems); with more than one slice C is a
   // [splits][M][N] partial buffer and bias / accumulate are applied by simt_splitk_reduce.
   __shared__ float As[TK][TM + 4];
@@ -96,20 +104,22 @@ gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, float
       float v = acc[i][j];
       if (bias) v += bias[gn];
       float* c = C + (size_t)gm * N + gn;
-      *c = accumulate ? (*c + v) : v;
+      if (accumulate) v = *c + v;
+      *c = post1(v, post, (size_t)gm * N + gn);
     }
   }
 }
 
 __global__ void __launch_bounds__(256)
 simt_splitk_reduce(const float* __restrict__ part, float* __restrict__ C, const float* __restrict__ bias, uint32_t M,
-                   uint32_t N, uint32_t splits, int accumulate) {
+                   uint32_t N, uint32_t splits, int accumulate, vkp_gemm_post post) {
   const size_t mn = (size_t)M * N;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < mn; i += (size_t)gridDim.x * blockDim.x) {
     float acc = part[i];
     for (uint32_t s = 1; s < splits; s++) acc += part[s * mn + i];   // fixed order: deterministic
     if (bias) acc += bias[i % N];
-    C[i] = accumulate ? (C[i] + acc) : acc;
+    if (accumulate) acc = C[i] + acc;
+    C[i] = post1(acc, post, i);
   }
 }
 
@@ -125,7 +135,8 @@ simt_splitk_reduce(const float* __restrict__ part, float* __restrict__ C, const 
 template <int NMAX>
 __global__ void __launch_bounds__(256)
 gemm_skinny_n_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
-                     const float* __restrict__ bias, uint32_t M, uint32_t N, uint32_t K, int accumulate) {
+                     const float* __restrict__ bias, uint32_t M, uint32_t N, uint32_t K, int accumulate,
+                     vkp_gemm_post post) {
   extern __shared__ float4 sk_b[];                  // [N][K/4]
   const uint32_t k4 = K / 4;
   for (uint32_t i = threadIdx.x; i < N * k4; i += 256) sk_b[i] = reinterpret_cast<const float4*>(B)[i];
@@ -163,7 +174,8 @@ gemm_skinny_n_kernel(const float* __restrict__ A, const float* __restrict__ B, f
     if (lane < N) {
       if (bias) v += bias[lane];
       float* c = C + (size_t)m * N + lane;
-      *c = accumulate ? (*c + v) : v;
+      if (accumulate) v = *c + v;
+      *c = post1(v, post, (size_t)m * N + lane);
     }
   }
 }
@@ -208,7 +220,7 @@ gemm_skinny_m_kernel(const float* __restrict__ A, const float* __restrict__ B, f
 template <int KMAX>
 __global__ void __launch_bounds__(256)
 gemm_skinny_k_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C,
-                     uint32_t M, uint32_t N, uint32_t K, int accumulate, uint32_t rows_per_block) {
+                     uint32_t M, uint32_t N, uint32_t K, int accumulate, uint32_t rows_per_block, vkp_gemm_post post) {
   const uint32_t n4 = blockIdx.x * 256 + threadIdx.x;
   if (n4 * 4 >= N) return;
   float4 b[KMAX];
@@ -235,16 +247,22 @@ gemm_skinny_k_kernel(const float* __restrict__ A, const float* __restrict__ B, f
       const float4 o = *c;
       acc.x = o.x + acc.x; acc.y = o.y + acc.y; acc.z = o.z + acc.z; acc.w = o.w + acc.w;
     }
+    if (post.relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+    if (post.mask) {    // N % 4 == 0 and 16-byte aligned like C
+      const float4 y = *reinterpret_cast<const float4*>(post.mask + (size_t)m * N + n4 * 4);
+      acc.x = fmaxf(vkpm::sign_f(y.x), 0.f) * acc.x; acc.y = fmaxf(vkpm::sign_f(y.y), 0.f) * acc.y;
+      acc.z = fmaxf(vkpm::sign_f(y.z), 0.f) * acc.z; acc.w = fmaxf(vkpm::sign_f(y.w), 0.f) * acc.w;
+    }
     *c = acc;
   }
 }
 
 // returns 1 and launches when one of the skinny kernels takes the problem, 0 otherwise, < 0 on error
 int gemm_skinny(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
-                const float* B, float* C, const float* bias, int accumulate) {
+                const float* B, float* C, const float* bias, int accumulate, vkp_gemm_post post) {
   static const bool off = getenv("VKP_DISABLE_SKINNY") != nullptr;
   if (off) return 0;
-  const bool aligned = ((((uintptr_t)A) | ((uintptr_t)B) | ((uintptr_t)C)) & 15) == 0;
+  const bool aligned = ((((uintptr_t)A) | ((uintptr_t)B) | ((uintptr_t)C) | ((uintptr_t)post.mask)) & 15) == 0;
   if (!aligned || (uint64_t)M * N * K < (1ull << 22)) return 0;       // small problems keep the tiled kernel
   if (!transA && transB && N <= 16 && K % 4 == 0 && K >= 128 && M >= 1024 && (size_t)N * K * 4 <= 96 * 1024) {
     const size_t smem = (size_t)N * K * 4;
@@ -255,7 +273,7 @@ int gemm_skinny(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, ui
       attr[ctx->device & 63] = true;
     }
     const unsigned grid = (unsigned)std::min<uint64_t>((M + 7) / 8, (uint64_t)ctx->sms * 2);
-    gemm_skinny_n_kernel<16><<<grid, 256, smem, ctx->stream>>>(A, B, C, bias, M, N, K, accumulate);
+    gemm_skinny_n_kernel<16><<<grid, 256, smem, ctx->stream>>>(A, B, C, bias, M, N, K, accumulate, post);
     return vkp_after_launch(ctx, "gemm_skinny_n") == VKP_OK ? 1 : -1;
   }
   if (transA && !transB && M <= 16 && N % 4 == 0 && N >= 256 && K >= 1024) {
@@ -269,7 +287,7 @@ int gemm_skinny(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, ui
     float* part = static_cast<float*>(ws);
     gemm_skinny_m_kernel<16><<<dim3(nblk, splits), 256, 0, ctx->stream>>>(A, B, part, M, N, K, k_per);
     if (vkp_after_launch(ctx, "gemm_skinny_m") != VKP_OK) return -1;
-    simt_splitk_reduce<<<vkp_grid_for(ctx, (size_t)M * N, 256, 8), 256, 0, ctx->stream>>>(part, C, bias, M, N, splits, accumulate);
+    simt_splitk_reduce<<<vkp_grid_for(ctx, (size_t)M * N, 256, 8), 256, 0, ctx->stream>>>(part, C, bias, M, N, splits, accumulate, post);
     return vkp_after_launch(ctx, "gemm_skinny_m_reduce") == VKP_OK ? 1 : -1;
   }
   if (!transA && !transB && K <= 16 && N % 4 == 0 && N >= 256 && M >= 1024 && !bias) {
@@ -278,14 +296,14 @@ int gemm_skinny(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, ui
     uint32_t rows_per = (M + yb - 1) / yb;
     if (rows_per < 8) rows_per = 8;
     yb = (M + rows_per - 1) / rows_per;
-    gemm_skinny_k_kernel<16><<<dim3(nblk, yb), 256, 0, ctx->stream>>>(A, B, C, M, N, K, accumulate, rows_per);
+    gemm_skinny_k_kernel<16><<<dim3(nblk, yb), 256, 0, ctx->stream>>>(A, B, C, M, N, K, accumulate, rows_per, post);
     return vkp_after_launch(ctx, "gemm_skinny_k") == VKP_OK ? 1 : -1;
   }
   return 0;
 }
 
 int gemm_simt(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
-              const float* B, float* C, const float* bias, int accumulate) {
+              const float* B, float* C, const float* bias, int accumulate, vkp_gemm_post post) {
   dim3 grid((M + TM - 1) / TM, (N + TN - 1) / TN, 1);
   VKP_CHECK(grid.y <= 65535, "gemm_simt: N = %u is too wide for the fallback kernel (max %d columns)", N, 65535 * TN);
   // skinny problems (few output tiles, long K): split K over blockIdx.z so that every SM has work
@@ -310,14 +328,15 @@ int gemm_simt(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint
   }
   const float* kb = splits > 1 ? nullptr : bias;
   const int ka = splits > 1 ? 0 : accumulate;
-  if (!transA && !transB) gemm_simt_kernel<false, false><<<grid, 256, 0, ctx->stream>>>(A, B, dst, kb, M, N, K, ka, k_per);
-  else if (!transA && transB) gemm_simt_kernel<false, true><<<grid, 256, 0, ctx->stream>>>(A, B, dst, kb, M, N, K, ka, k_per);
-  else if (transA && !transB) gemm_simt_kernel<true, false><<<grid, 256, 0, ctx->stream>>>(A, B, dst, kb, M, N, K, ka, k_per);
-  else gemm_simt_kernel<true, true><<<grid, 256, 0, ctx->stream>>>(A, B, dst, kb, M, N, K, ka, k_per);
+  const vkp_gemm_post kp = splits > 1 ? vkp_gemm_post{0, nullptr} : post;
+  if (!transA && !transB) gemm_simt_kernel<false, false><<<grid, 256, 0, ctx->stream>>>(A, B, dst, kb, M, N, K, ka, k_per, kp);
+  else if (!transA && transB) gemm_simt_kernel<false, true><<<grid, 256, 0, ctx->stream>>>(A, B, dst, kb, M, N, K, ka, k_per, kp);
+  else if (transA && !transB) gemm_simt_kernel<true, false><<<grid, 256, 0, ctx->stream>>>(A, B, dst, kb, M, N, K, ka, k_per, kp);
+  else gemm_simt_kernel<true, true><<<grid, 256, 0, ctx->stream>>>(A, B, dst, kb, M, N, K, ka, k_per, kp);
   VKP_TRY(vkp_after_launch(ctx, "gemm_simt"));
   if (splits > 1) {
     simt_splitk_reduce<<<vkp_grid_for(ctx, (size_t)M * N, 256, 8), 256, 0, ctx->stream>>>(dst, C, bias, M, N, splits,
-                                                                                        accumulate);
+                                                                                        accumulate, post);
     VKP_TRY(vkp_after_launch(ctx, "gemm_simt_splitk_reduce"));
   }
   return VKP_OK;
@@ -326,29 +345,38 @@ int gemm_simt(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint
 }  // namespace
 
 int vkp_launch_gemm(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K,
-                    const float* A, const float* B, float* C, const float* bias, int flags) {
+                    const float* A, const float* B, float* C, const float* bias, int flags, vkp_gemm_post post) {
   if (M == 0 || N == 0) return VKP_OK;
   const int accumulate = (flags & VKP_GEMM_ACCUMULATE) ? 1 : 0;
   const bool force_simt = flags & VKP_GEMM_FORCE_SIMT, force_tc = flags & VKP_GEMM_FORCE_TC;
   const bool tc_ok = !force_simt && vkp_gemm_tc_supported(transA, transB, M, N, K, A, B, C, force_tc);
   VKP_CHECK(!(force_tc && !tc_ok), "vkp_gemm: tensor-core path forced but the shape (%u,%u,%u) is not supported", M, N, K);
-  if (tc_ok) return vkp_gemm_tc(ctx, transA, transB, M, N, K, A, B, C, bias, accumulate);
+  if (flags & VKP_GEMM_RELU) post.relu = 1;
+  if (tc_ok) return vkp_gemm_tc(ctx, transA, transB, M, N, K, A, B, C, bias, accumulate, post);
   if (!force_simt) {
-    const int r = gemm_skinny(ctx, transA, transB, M, N, K, A, B, C, bias, accumulate);
+    const int r = gemm_skinny(ctx, transA, transB, M, N, K, A, B, C, bias, accumulate, post);
     if (r < 0) return VKP_ERR;
     if (r > 0) return VKP_OK;
   }
-  return gemm_simt(ctx, transA, transB, M, N, K, A, B, C, bias, accumulate);
+  return gemm_simt(ctx, transA, transB, M, N, K, A, B, C, bias, accumulate, post);
+}
+
+extern "C" int vkp_gemm_fused(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K,
+                              const float* A, const float* B, float* C, const float* bias, const float* relu_mask,
+                              int flags, vkp_job** job) {
+  VKP_RANGE("vkp_gemm");
+  VKP_CHECK(ctx && A && B && C, "vkp_gemm: null argument");
+  VKP_CHECK(!relu_mask || (N % 4 == 0 && (((uintptr_t)relu_mask) & 15) == 0), "vkp_gemm_fused: mask needs N %% 4 == 0 and 16-byte alignment");
+  VKP_TRY(vkp_make_current(ctx));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  void* bufs[5] = {(void*)A, (void*)B, (void*)C, (void*)bias, (void*)relu_mask};
+  VKP_TRY(vkp_prepare_buffers(ctx, bufs, 5));
+  VKP_TRY(vkp_launch_gemm(ctx, transA, transB, M, N, K, A, B, C, bias, flags, vkp_gemm_post{0, relu_mask}));
+  return vkp_finish_op(ctx, job);
 }
 
 extern "C" int vkp_gemm(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K,
                         const float* A, const float* B, float* C, const float* bias, int flags,
                         vkp_job** job) {
-  VKP_CHECK(ctx && A && B && C, "vkp_gemm: null argument");
-  VKP_TRY(vkp_make_current(ctx));
-  std::lock_guard<std::mutex> g(ctx->mu);
-  void* bufs[4] = {(void*)A, (void*)B, (void*)C, (void*)bias};
-  VKP_TRY(vkp_prepare_buffers(ctx, bufs, 4));
-  VKP_TRY(vkp_launch_gemm(ctx, transA, transB, M, N, K, A, B, C, bias, flags));
-  return vkp_finish_op(ctx, job);
+  return vkp_gemm_fused(ctx, transA, transB, M, N, K, A, B, C, bias, nullptr, flags, job);
 }

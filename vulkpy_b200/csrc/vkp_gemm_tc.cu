@@ -34,6 +34,7 @@
 // stage (A, A_lo, Bt, Bt_lo); the converter warps retire immediately.  Measured at 8192^3
 // (profiles/r01_gemm_variants.txt): 5.07 ms -> 4.27 ms including the pre-pass.
 #include "vkp_common.cuh"
+#include "vkp_math.cuh"
 
 #include <cuda.h>
 #include <cstdlib>
@@ -41,6 +42,16 @@
 namespace {
 
 constexpr int BM = 128;
+
+__device__ __forceinline__ float4 post4(float4 o, const vkp_gemm_post& p, size_t idx) {
+  if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+  if (p.mask) {
+    const float4 y = *reinterpret_cast<const float4*>(p.mask + idx);
+    o.x = fmaxf(vkpm::sign_f(y.x), 0.f) * o.x; o.y = fmaxf(vkpm::sign_f(y.y), 0.f) * o.y;
+    o.z = fmaxf(vkpm::sign_f(y.z), 0.f) * o.z; o.w = fmaxf(vkpm::sign_f(y.w), 0.f) * o.w;
+  }
+  return o;
+}
 constexpr int UMMA_K = 8;         // kind::tf32
 constexpr int NUM_THREADS = 384;
 
@@ -256,7 +267,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
                float* __restrict__ C, const float* __restrict__ bias, uint32_t M, uint32_t N, uint32_t K,
                int accumulate, uint32_t splits, uint32_t kb_per_split, vkp_tc_chunks ch,
-               const __grid_constant__ vkp_tc_pull pl, int a_mn, int b_mn) {
+               const __grid_constant__ vkp_tc_pull pl, int a_mn, int b_mn, vkp_gemm_post post) {
   // a_mn / b_mn: the operand lies as [K, MN] in memory (MN contiguous): 3-D tensor map, MN-major tiles
   // ch.n_chunks > 1 (row-sharded matmul, vkp_comm.cu): K is cut into n_chunks ranges that become
   // valid one after the other while this kernel runs -- the peers' shards of B, fetched over NVLink
@@ -476,7 +487,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float4 cv = *reinterpret_cast<const float4*>(dst + j);
                 o.x += cv.x; o.y += cv.y; o.z += cv.z; o.w += cv.w;
               }
-              *reinterpret_cast<float4*>(dst + j) = o;
+              *reinterpret_cast<float4*>(dst + j) = post4(o, post, (size_t)row * N + col0 + j);
             }
           }
         }
@@ -501,7 +512,7 @@ teardown:
 // C = (accumulate ? C : 0) + bias + sum_s part[s]   (fixed order: deterministic)
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ C, const float* __restrict__ bias,
-                     uint32_t M, uint32_t N, uint32_t splits, int accumulate) {
+                     uint32_t M, uint32_t N, uint32_t splits, int accumulate, vkp_gemm_post post) {
   const size_t mn = (size_t)M * N;
   for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4; i < mn; i += (size_t)gridDim.x * blockDim.x * 4) {
     float4 acc = *reinterpret_cast<const float4*>(part + i);
@@ -517,7 +528,7 @@ splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ C, cons
       const float4 cv = *reinterpret_cast<const float4*>(C + i);
       acc.x += cv.x; acc.y += cv.y; acc.z += cv.z; acc.w += cv.w;
     }
-    *reinterpret_cast<float4*>(C + i) = acc;
+    *reinterpret_cast<float4*>(C + i) = post4(acc, post, i);
   }
 }
 
@@ -658,7 +669,7 @@ template <int BN, int BK>
 int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, const float* Alo, const float* Btlo, float* C,
               const float* bias, uint32_t M, uint32_t N, uint32_t K, int accumulate,
               vkp_tc_chunks ch = vkp_tc_chunks{nullptr, 0, 0, 0, 1}, const vkp_tc_pull* pull = nullptr,
-              int a_mn = 0, int b_mn = 0) {
+              int a_mn = 0, int b_mn = 0, vkp_gemm_post post = vkp_gemm_post{0, nullptr}) {
   using cfg = Cfg<BN, BK>;
   const bool presplit = Alo != nullptr;
   CUtensorMap tmA, tmB, tmAlo, tmBlo;
@@ -706,11 +717,11 @@ int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, const float* Alo, c
   const unsigned grid = work < (uint32_t)ctx->sms ? work : (unsigned)ctx->sms;
   kernel<<<grid, NUM_THREADS, cfg::SMEM_BYTES, ctx->stream>>>(
       tmA, tmB, tmAlo, tmBlo, dst, splits > 1 ? nullptr : bias, M, N, K, splits > 1 ? 0 : accumulate, splits, kb_per, ch, pl,
-      a_mn, b_mn);
+      a_mn, b_mn, splits > 1 ? vkp_gemm_post{0, nullptr} : post);
   VKP_TRY(vkp_after_launch(ctx, "gemm_tc(tcgen05 3xTF32)"));
   if (splits > 1) {
     const unsigned rgrid = vkp_grid_for(ctx, ((size_t)M * N + 3) / 4, 256, 8);
-    splitk_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(dst, C, bias, M, N, splits, accumulate);
+    splitk_reduce_kernel<<<rgrid, 256, 0, ctx->stream>>>(dst, C, bias, M, N, splits, accumulate, post);
     VKP_TRY(vkp_after_launch(ctx, "gemm_splitk_reduce"));
   }
   return VKP_OK;
@@ -745,7 +756,7 @@ static bool use_presplit(uint32_t M, uint32_t N, uint32_t K) {
 }
 
 int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
-                const float* B, float* C, const float* bias, int accumulate) {
+                const float* B, float* C, const float* bias, int accumulate, vkp_gemm_post post) {
   // A as [M,K] and B as [N,K] are K-major; the other two storage orders are taken as MN-major tiles
   // when their leading dimension allows the 3-D tensor map, else transposed once into the workspace
   static bool mn_ok = !(getenv("VKP_TC_MN") && getenv("VKP_TC_MN")[0] == '0');
@@ -804,9 +815,9 @@ int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, ui
     const vkp_tc_chunks no_chunks{nullptr, 0, 0, 0, 1};
     int rc;
     const int am = a_mn ? mn_mode : 0, bm = b_mn ? mn_mode : 0;
-    if (wide && bk16) rc = launch_tc<256, 16>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm);
-    else if (wide) rc = launch_tc<256, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm);
-    else rc = launch_tc<128, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm);
+    if (wide && bk16) rc = launch_tc<256, 16>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm, post);
+    else if (wide) rc = launch_tc<256, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm, post);
+    else rc = launch_tc<128, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm, post);
     if (rc == VKP_OK || !(a_mn || b_mn) || !strstr(vkp_last_error(), "MN-major")) return rc;
     mn_ok = false;      // this driver refuses the 3-D map: transposes from now on
   }

@@ -159,6 +159,7 @@ extern "C" int vkp_nn_adam(vkp_ctx* ctx, const float* grad, float* m, float* v, 
                            float beta1, float one_minus_beta1, float beta2, float one_minus_beta2,
                            float one_minus_beta1t, float one_minus_beta2t, float eps, float neg_lr,
                            vkp_job** job) {
+  VKP_RANGE(__func__);
   NN_PROLOGUE((void*)grad, m, v, diff);
   if (n) {
     adam_kernel<<<vkp_grid_for(ctx, n, NB, 16), NB, 0, ctx->stream>>>(grad, m, v, diff, n, beta1, one_minus_beta1, beta2,
@@ -172,6 +173,7 @@ extern "C" int vkp_nn_adam(vkp_ctx* ctx, const float* grad, float* m, float* v, 
 extern "C" int vkp_nn_adam_apply_many(vkp_ctx* ctx, int n_tensors, const float* const* grad, float* const* m,
                                       float* const* v, float* const* value, const size_t* count,
                                       const float* scalars /* [n_tensors][8] */, vkp_job** job) {
+  VKP_RANGE(__func__);
   VKP_CHECK(ctx && grad && m && v && value && count && scalars, "vkp_nn_adam_apply_many: null argument");
   VKP_CHECK(n_tensors >= 1 && n_tensors <= VKP_NN_MAX_TENSORS, "vkp_nn_adam_apply_many: 1..%d tensors", VKP_NN_MAX_TENSORS);
   VKP_TRY(vkp_make_current(ctx));
@@ -218,6 +220,7 @@ extern "C" int vkp_fill_many_u32(vkp_ctx* ctx, int n_tensors, void* const* ptr, 
 
 extern "C" int vkp_nn_activation_backward(vkp_ctx* ctx, int kind, const float* y, const float* dy, float* dx,
                                           size_t n, vkp_job** job) {
+  VKP_RANGE(__func__);
   NN_PROLOGUE((void*)y, (void*)dy, dx);
   VKP_CHECK(kind == 0 || kind == 1, "vkp_nn_activation_backward: kind must be 0 (relu) or 1 (y(1-y))");
   if (n) {
@@ -231,6 +234,7 @@ extern "C" int vkp_nn_activation_backward(vkp_ctx* ctx, int kind, const float* y
 
 extern "C" int vkp_nn_softmax_forward(vkp_ctx* ctx, const float* x, float* y, uint32_t rows, uint32_t cols,
                                       vkp_job** job) {
+  VKP_RANGE(__func__);
   NN_PROLOGUE((void*)x, y);
   if (rows && cols) {
     const unsigned grid = vkp_grid_for(ctx, rows, NB / 32, 16);

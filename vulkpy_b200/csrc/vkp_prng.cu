@@ -395,6 +395,7 @@ extern "C" int vkp_rng_state(vkp_rng* rng, uint32_t* host_out) {
 
 template <int MODE>
 static int rng_generate(vkp_rng* rng, void* out, uint64_t n_out, float mean, float stddev, vkp_job** job) {
+  VKP_RANGE(MODE == MODE_NORMAL ? "vkp_rng_normal" : (MODE == MODE_F32 ? "vkp_rng_float" : "vkp_rng_uint32"));
   VKP_CHECK(rng && (out || n_out == 0), "vkp_rng: null argument");
   vkp_ctx* ctx = rng->ctx;
   VKP_TRY(vkp_make_current(ctx));

@@ -374,6 +374,7 @@ static bool wants_bounce(vkp_ctx* ctx, const void* dev_ptr, size_t bytes) {
 }
 
 extern "C" int vkp_upload(vkp_ctx* ctx, void* dst, const void* src_host, size_t bytes) {
+  VKP_RANGE("vkp_upload");
   VKP_CHECK(ctx && (bytes == 0 || (dst && src_host)), "vkp_upload: null argument");
   if (bytes == 0) return VKP_OK;
   VKP_TRY(vkp_make_current(ctx));
@@ -398,6 +399,7 @@ extern "C" int vkp_upload(vkp_ctx* ctx, void* dst, const void* src_host, size_t 
 }
 
 extern "C" int vkp_download(vkp_ctx* ctx, void* dst_host, const void* src, size_t bytes) {
+  VKP_RANGE("vkp_download");
   VKP_CHECK(ctx && (bytes == 0 || (dst_host && src)), "vkp_download: null argument");
   if (bytes == 0) return VKP_OK;
   VKP_TRY(vkp_make_current(ctx));
@@ -430,6 +432,7 @@ static int order_after_compute(vkp_ctx* ctx, cudaStream_t side) {
 }
 
 extern "C" int vkp_upload_async(vkp_ctx* ctx, void* dst, const void* src_pinned, size_t bytes, vkp_job** job) {
+  VKP_RANGE("vkp_upload_async");
   VKP_CHECK(ctx && dst && src_pinned && job, "vkp_upload_async: null argument");
   VKP_TRY(vkp_make_current(ctx));
   VKP_CHECK(is_page_locked(src_pinned), "vkp_upload_async: the source must be page-locked (vkp_host_alloc)");
@@ -465,6 +468,7 @@ extern "C" int vkp_upload_async(vkp_ctx* ctx, void* dst, const void* src_pinned,
 }
 
 extern "C" int vkp_download_async(vkp_ctx* ctx, void* dst_pinned, const void* src, size_t bytes, vkp_job** job) {
+  VKP_RANGE("vkp_download_async");
   VKP_CHECK(ctx && dst_pinned && src && job, "vkp_download_async: null argument");
   VKP_TRY(vkp_make_current(ctx));
   VKP_CHECK(is_page_locked(dst_pinned), "vkp_download_async: the destination must be page-locked (vkp_host_alloc)");

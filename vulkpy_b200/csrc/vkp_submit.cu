@@ -94,6 +94,7 @@ extern "C" int vkp_submit(vkp_ctx* ctx, int op, void* const* bufs, int nbuf, con
                           size_t params_bytes, vkp_job** job) {
   VKP_CHECK(ctx, "vkp_submit: null context");
   VKP_CHECK(op >= 0 && op < g_nops, "Unknown Operation");  // _vkarray.cc:752
+  VKP_RANGE(g_ops[op].name);
   VKP_CHECK(bufs && params && nbuf >= 1 && nbuf <= 4, "vkp_submit: bad buffer list");
   for (int i = 0; i < nbuf; i++) VKP_CHECK(bufs[i], "vkp_submit(%s): binding %d is null", g_ops[op].name, i);
   VKP_TRY(vkp_make_current(ctx));
