@@ -208,7 +208,7 @@ class FakeDevice:
             b.arr.view(np.uint32)[:] = np.uint32(bits & 0xFFFFFFFF)
         return self._done("fill_many", len(bufs))
 
-    def gemm(self, transA, transB, M, N, K, A, B, Cbuf, bias=None, flags=0):
+    def gemm(self, transA, transB, M, N, K, A, B, Cbuf, bias=None, flags=0, relu_mask=None):
         a = A.arr.reshape((K, M) if transA else (M, K)).astype(np.float64)
         b = B.arr.reshape((N, K) if transB else (K, N)).astype(np.float64)
         c = (a.T if transA else a) @ (b.T if transB else b)
@@ -217,6 +217,10 @@ class FakeDevice:
             c = (c + bias.arr[None, :]).astype(F)
         if flags & 4:
             c = (Cbuf.arr.reshape(M, N) + c).astype(F)
+        if flags & 8:                       # VKP_GEMM_RELU: x.max(0.0)
+            c = orc.scalar("max", c, 0.0)
+        if relu_mask is not None:           # ReLU.backward: max(sign(y), 0) * dx
+            c = (np.maximum(np.sign(relu_mask.arr.reshape(M, N)), F(0)) * c).astype(F)
         Cbuf.arr[:] = c.reshape(-1)
         return self._done("gemm", 3)
 

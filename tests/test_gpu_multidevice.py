@@ -12,8 +12,9 @@ pytestmark = pytest.mark.gpu
 F = np.float32
 
 
-@pytest.mark.skipif(device_count() < 2, reason="needs two GPUs")
 def test_opt_in_kernels_on_second_device_after_first():
+    if device_count() < 2:       # asked at run time: on a box without a driver the query itself raises
+        pytest.skip("needs two GPUs")
     rs = np.random.default_rng(0)
     x_h = rs.uniform(0, 1, (1024, 384)).astype(F)            # TMA-staged column reduction (96 KiB shared memory)
     a_h = rs.normal(size=(2048, 1024)).astype(F)             # skinny-N Dense forward (64 KiB shared memory)

@@ -110,6 +110,29 @@ gemm_simt_kernel(const float* __restrict__ A, const float* __restrict__ B, float
   }
 }
 
+// many partials, few outputs (the skinny weight gradient: ~148 partials of a [16, 1024] result): 8 lanes per
+// output element, lane g folds partials g, g + 8, ... in order, then the 8 lanes are folded in a fixed xor tree
+__global__ void __launch_bounds__(256)
+simt_splitk_reduce_wide(const float* __restrict__ part, float* __restrict__ C, const float* __restrict__ bias, uint32_t M,
+                        uint32_t N, uint32_t splits, int accumulate, vkp_gemm_post post) {
+  const size_t mn = (size_t)M * N;
+  const uint32_t g = threadIdx.x & 7;
+  for (size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 3; i < ((mn + 31) & ~(size_t)31);
+       i += ((size_t)gridDim.x * blockDim.x) >> 3) {
+    float acc = 0.f;
+    if (i < mn)
+      for (uint32_t s = g; s < splits; s += 8) acc += part[s * mn + i];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (g == 0 && i < mn) {
+      if (bias) acc += bias[i % N];
+      if (accumulate) acc = C[i] + acc;
+      C[i] = post1(acc, post, i);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 simt_splitk_reduce(const float* __restrict__ part, float* __restrict__ C, const float* __restrict__ bias, uint32_t M,
                    uint32_t N, uint32_t splits, int accumulate, vkp_gemm_post post) {
@@ -181,38 +204,64 @@ gemm_skinny_n_kernel(const float* __restrict__ A, const float* __restrict__ B, f
 }
 
 // weight gradient:  part[split][M, N] = sum_{k in split} A[k, M]^T B[k, N],  M <= 16, N % 4 == 0.
-// Thread = 4 neighbouring columns of B x all M rows of the result (M x 4 accumulators); the K range
-// is cut over blockIdx.y; simt_splitk_reduce folds the partials (fixed order) and applies
+// Block = 256 column threads (4 neighbouring columns of B each) x 2 k-groups; the block's slice of A
+// ([k_per_split, M], a few KB) is staged in shared memory once and read back as broadcast float4s
+// (the first version issued M scalar loads per k and thread: LSU-bound, 32 us for a 32 MB pass), B
+// streams through 16-byte loads, the two k-groups are folded through shared memory, and one partial
+// per block goes to the workspace; simt_splitk_reduce folds the partials (fixed order) and applies
 // bias / accumulate.
 template <int MMAX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 gemm_skinny_m_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ part,
                      uint32_t M, uint32_t N, uint32_t K, uint32_t k_per_split) {
-  const uint32_t n4 = blockIdx.x * 256 + threadIdx.x;          // float4 column index
+  extern __shared__ float sk_a[];                              // [k_per_split][MMAX], then 256 float4 of scratch
+  const uint32_t tx = threadIdx.x & 255, ty = threadIdx.x >> 8;
+  const uint32_t n4 = blockIdx.x * 256 + tx;                   // float4 column index
   const uint32_t k0 = blockIdx.y * k_per_split;
   const uint32_t k1 = (k0 + k_per_split < K) ? k0 + k_per_split : K;
-  if (n4 * 4 >= N) return;
+  for (uint32_t i = threadIdx.x; i < (k1 - k0) * MMAX; i += 512) {
+    const uint32_t r = i / MMAX, m = i % MMAX;
+    sk_a[i] = m < M ? A[(size_t)(k0 + r) * M + m] : 0.f;
+  }
+  __syncthreads();
   float4 acc[MMAX];
 #pragma unroll
   for (int m = 0; m < MMAX; m++) acc[m] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (uint32_t k = k0; k < k1; k++) {
-    const float4 b = *reinterpret_cast<const float4*>(B + (size_t)k * N + n4 * 4);
-    const float* a = A + (size_t)k * M;                          // same address for the whole warp: broadcast
+  const bool live = n4 * 4 < N;
+  if (live) {
+    for (uint32_t k = k0 + ty; k < k1; k += 2) {
+      const float4 b = *reinterpret_cast<const float4*>(B + (size_t)k * N + n4 * 4);
+      const float4* a4 = reinterpret_cast<const float4*>(sk_a + (size_t)(k - k0) * MMAX);
 #pragma unroll
-    for (int m = 0; m < MMAX; m++) {
-      if (m < (int)M) {
-        const float am = __ldg(a + m);
-        acc[m].x = fmaf(am, b.x, acc[m].x);
-        acc[m].y = fmaf(am, b.y, acc[m].y);
-        acc[m].z = fmaf(am, b.z, acc[m].z);
-        acc[m].w = fmaf(am, b.w, acc[m].w);
+      for (int q = 0; q < MMAX / 4; q++) {
+        const float4 a = a4[q];                                // same address for the whole warp: broadcast
+        const float am[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float4& c = acc[4 * q + j];
+          c.x = fmaf(am[j], b.x, c.x);
+          c.y = fmaf(am[j], b.y, c.y);
+          c.z = fmaf(am[j], b.z, c.z);
+          c.w = fmaf(am[j], b.w, c.w);
+        }
       }
     }
   }
+  float4* red = reinterpret_cast<float4*>(sk_a + (size_t)k_per_split * MMAX);
   float* out = part + (size_t)blockIdx.y * M * N;
 #pragma unroll
-  for (int m = 0; m < MMAX; m++)
-    if (m < (int)M) *reinterpret_cast<float4*>(out + (size_t)m * N + n4 * 4) = acc[m];
+  for (int m = 0; m < MMAX; m++) {
+    if (m < (int)M) {                                          // M is uniform: every thread takes the same path
+      if (ty == 1) red[tx] = acc[m];
+      __syncthreads();
+      if (ty == 0 && live) {
+        const float4 o = red[tx];
+        *reinterpret_cast<float4*>(out + (size_t)m * N + n4 * 4) =
+            make_float4(acc[m].x + o.x, acc[m].y + o.y, acc[m].z + o.z, acc[m].w + o.w);
+      }
+      __syncthreads();
+    }
+  }
 }
 
 // input gradient:  C[M, N] (+)= A[M, K] B[K, N],  K <= 16, N % 4 == 0.  Thread = 4 neighbouring
@@ -229,13 +278,25 @@ gemm_skinny_k_kernel(const float* __restrict__ A, const float* __restrict__ B, f
     b[k] = (k < (int)K) ? *reinterpret_cast<const float4*>(B + (size_t)k * N + n4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   const uint32_t m0 = blockIdx.y * rows_per_block;
   const uint32_t m1 = (m0 + rows_per_block < M) ? m0 + rows_per_block : M;
+  const bool avec = (K % 4 == 0) && ((((uintptr_t)A) & 15) == 0);
   for (uint32_t m = m0; m < m1; m++) {
     const float* a = A + (size_t)m * K;                          // warp-uniform address: broadcast
+    float ar[KMAX];
+    if (avec) {                                                  // K / 4 16-byte loads instead of K scalar ones
+#pragma unroll
+      for (int q = 0; q < KMAX / 4; q++) {
+        const float4 v = (4 * q < (int)K) ? __ldg(reinterpret_cast<const float4*>(a) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ar[4 * q] = v.x; ar[4 * q + 1] = v.y; ar[4 * q + 2] = v.z; ar[4 * q + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < KMAX; k++) ar[k] = (k < (int)K) ? __ldg(a + k) : 0.f;
+    }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < KMAX; k++) {
       if (k < (int)K) {
-        const float ak = __ldg(a + k);
+        const float ak = ar[k];
         acc.x = fmaf(ak, b[k].x, acc.x);
         acc.y = fmaf(ak, b[k].y, acc.y);
         acc.z = fmaf(ak, b[k].z, acc.z);
@@ -278,16 +339,21 @@ int gemm_skinny(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, ui
   }
   if (transA && !transB && M <= 16 && N % 4 == 0 && N >= 256 && K >= 1024) {
     const uint32_t nblk = (N / 4 + 255) / 256;
-    uint32_t splits = (uint32_t)std::max<uint64_t>(1, (uint64_t)ctx->sms * 2 / nblk);
+    uint32_t splits = (uint32_t)std::max<uint64_t>(1, (uint64_t)ctx->sms / nblk);   // one 512-thread block per SM
     if (splits > K / 16) splits = K / 16;
     uint32_t k_per = (K + splits - 1) / splits;
+    if (k_per > 512) k_per = 512;                      // A slice of at most 32 KiB in shared memory
     splits = (K + k_per - 1) / k_per;
     void* ws;
     if (vkp_workspace(ctx, 0, (size_t)splits * M * N * sizeof(float), &ws) != VKP_OK) return -1;
     float* part = static_cast<float*>(ws);
-    gemm_skinny_m_kernel<16><<<dim3(nblk, splits), 256, 0, ctx->stream>>>(A, B, part, M, N, K, k_per);
+    const size_t smem_m = (size_t)k_per * 16 * sizeof(float) + 256 * sizeof(float4);
+    gemm_skinny_m_kernel<16><<<dim3(nblk, splits), 512, smem_m, ctx->stream>>>(A, B, part, M, N, K, k_per);
     if (vkp_after_launch(ctx, "gemm_skinny_m") != VKP_OK) return -1;
-    simt_splitk_reduce<<<vkp_grid_for(ctx, (size_t)M * N, 256, 8), 256, 0, ctx->stream>>>(part, C, bias, M, N, splits, accumulate, post);
+    if (splits >= 16)
+      simt_splitk_reduce_wide<<<vkp_grid_for(ctx, (size_t)M * N * 8, 256, 8), 256, 0, ctx->stream>>>(part, C, bias, M, N, splits, accumulate, post);
+    else
+      simt_splitk_reduce<<<vkp_grid_for(ctx, (size_t)M * N, 256, 8), 256, 0, ctx->stream>>>(part, C, bias, M, N, splits, accumulate, post);
     return vkp_after_launch(ctx, "gemm_skinny_m_reduce") == VKP_OK ? 1 : -1;
   }
   if (!transA && !transB && K <= 16 && N % 4 == 0 && N >= 256 && M >= 1024 && !bias) {

@@ -731,10 +731,12 @@ int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, const float* Alo, c
 
 int vkp_gemm_tc_supported(int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
                           const float* B, float* C, int forced) {
-  (void)transA; (void)transB;
   if (!forced) {
     if (getenv("VKP_DISABLE_TC")) return 0;
-    if (M < 128 || N < 128 || K < 32) return 0;               // small problems: SIMT kernel
+    // narrow outputs (nn.Dense with a handful of classes: forward X W^T + b, N <= 32): one 128 x 32 tile per
+    // 128 rows, the pass over X is the cost; both operands must be K-major as they lie
+    const bool narrow = !transA && transB && N >= 8 && N <= 32 && M >= 1024 && K >= 256 && !getenv("VKP_TC_NO_NARROW");
+    if (!narrow && (M < 128 || N < 128 || K < 32)) return 0;  // small problems: SIMT kernel
     if ((uint64_t)M * N * K < (1ull << 22)) return 0;
   }
   if (K == 0) return 0;
@@ -815,7 +817,8 @@ int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, ui
     const vkp_tc_chunks no_chunks{nullptr, 0, 0, 0, 1};
     int rc;
     const int am = a_mn ? mn_mode : 0, bm = b_mn ? mn_mode : 0;
-    if (wide && bk16) rc = launch_tc<256, 16>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm, post);
+    if (N <= 32) rc = launch_tc<32, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm, post);
+    else if (wide && bk16) rc = launch_tc<256, 16>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm, post);
     else if (wide) rc = launch_tc<256, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm, post);
     else rc = launch_tc<128, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm, post);
     if (rc == VKP_OK || !(a_mn || b_mn) || !strstr(vkp_last_error(), "MN-major")) return rc;

@@ -22,6 +22,7 @@ def _fused_backward(kind: int, y: Array, dy: Array) -> Array:
 
 Init = Callable[[GPU, Iterable[int]], Array]
 _GEMM_ACCUMULATE = 4   # VKP_GEMM_ACCUMULATE (include/vulkpy_b200.h)
+_GEMM_RELU = 8         # VKP_GEMM_RELU
 
 
 class Dense(Module):
@@ -52,14 +53,32 @@ class Dense(Module):
         y._keep.extend([self.w.value, self.b.value, x])
         return y
 
-    def backward(self, dy: Array) -> Array:
+    def _forward_relu(self, x: Array) -> Array:
+        """``ReLU()(self(x))`` as one kernel: the GEMM epilogue adds the bias and applies ``max(., 0)`` -- the
+        float32 operations of batch_affine.comp:25-39 followed by max_scalar.comp (``x.max(0.0)``, layers.py:186)."""
+        batch = x.shape[0]
+        y = Array(x._gpu, shape=(batch, self.output_dim))
+        y.job = x._gpu.gpu.gemm(False, True, batch, self.output_dim, x.shape[1], x.buffer, self.w.value.buffer, y.buffer,
+                                self.b.value.buffer, _GEMM_RELU)
+        y._keep.extend([self.w.value, self.b.value, x])
+        return y
+
+    def backward(self, dy: Array, relu_y: Optional[Array] = None) -> Array:
         """db = sum_batch dy, dW = dy^T x, dx = dy W.
 
         The reference forms dW by materialising ``dy[:, :, None] * x[:, None, :]``
         (batch x out x in) and summing over the batch (layers.py:126-141); the same
-        contraction is one GEMM here."""
+        contraction is one GEMM here.  ``relu_y`` (additive): the output of a ReLU that feeds this
+        layer; its backward ``max(sign(y), 0) * dx`` (layers.py:207-210) then runs in the epilogue
+        of the ``dx`` GEMM and the returned gradient is already the ReLU's input gradient."""
         self._backward_params(dy)
-        return dy @ self.w.value
+        if relu_y is None:
+            return dy @ self.w.value
+        dx = Array(dy._gpu, shape=(dy.shape[0], self.input_dim))
+        dx.job = dy._gpu.gpu.gemm(False, False, dy.shape[0], self.input_dim, self.output_dim, dy.buffer,
+                                  self.w.value.buffer, dx.buffer, None, 0, relu_mask=relu_y.buffer)
+        dx._keep = [dy, self.w.value, relu_y]
+        return dx
 
     def _backward_params(self, dy: Array):
         """Parameter gradients only (what ``Sequence`` needs from its first layer)."""

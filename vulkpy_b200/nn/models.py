@@ -21,22 +21,53 @@ class Sequence:
         self.L: Tuple[Module, ...] = tuple(layers)
         self.loss: Loss = loss
 
+    @staticmethod
+    def _stock(layer, cls) -> bool:
+        """`layer` is exactly the library's `cls` (a subclass may override forward / backward)."""
+        return type(layer) is cls
+
     def _forward(self, x: Array) -> Array:
-        for layer in self.L:
+        from .layers import Dense, ReLU
+        L = self.L
+        i = 0
+        while i < len(L):
+            layer = L[i]
+            if (not _opt.UNFUSED and i + 1 < len(L) and self._stock(layer, Dense) and self._stock(L[i + 1], ReLU)
+                    and len(x.shape) == 2):
+                # Dense followed by ReLU: one GEMM whose epilogue adds the bias and clamps at zero;
+                # both modules remember what their own forward would have (the ReLU's input is not kept:
+                # its backward only reads its output, layers.py:207-210)
+                y = layer._forward_relu(x)
+                layer._x, layer._y = x, y
+                L[i + 1]._x = L[i + 1]._y = y
+                x = y
+                i += 2
+                continue
             x = layer(x)
+            i += 1
         return x
 
     def _backward(self):
         """Layers in reverse.  The reference also asks the FIRST layer for the gradient of the
         network input and drops it (models.py:46-53); a layer that can produce its parameter
         gradients alone (``_backward_params``) is spared that contraction."""
+        from .layers import Dense, ReLU
         dx = self.loss.grad()
-        first = self.L[0] if self.L else None
-        for layer in reversed(self.L):
+        L = self.L
+        first = L[0] if L else None
+        i = len(L) - 1
+        while i >= 0:
+            layer = L[i]
             if layer is first and not _opt.UNFUSED and hasattr(layer, "_backward_params"):
                 layer._backward_params(dx)
+            elif (not _opt.UNFUSED and i >= 1 and self._stock(layer, Dense) and self._stock(L[i - 1], ReLU)
+                  and len(dx.shape) == 2 and layer.input_dim % 4 == 0):
+                # the ReLU in front of this Dense: its backward runs in the epilogue of the dx GEMM
+                dx = layer.backward(dx, relu_y=L[i - 1]._y)
+                i -= 1
             else:
                 dx = layer.backward(dx)
+            i -= 1
 
     def _known_parameters(self):
         """(parameters the one-launch zero_grad / update may own, the other layers).
