@@ -358,14 +358,19 @@ def config_c4(B, rng):
     del idx_h
     rows = {}
     k, v = hbm_row(B, "gather 2^26 random idx", lambda: table.gather(idx), 12 * NI,
-                   note="sector-bound: every 4-byte payload costs a 32-byte DRAM sector (ncu: profiles/r02_ncu_rows.md)")
-    v["sector_gbs"] = round((32 + 8) * NI / v["ms"] / 1e6, 1)
+                   note="DRAM-bound on fetch granularity: ncu counts 6.26 GB read from DRAM per launch = 93.4 B per 4-byte "
+                        "payload (195.8 M sectors for 67.1 M elements; L2 hit 10 %: the 256 MiB table is 2x the L2), "
+                        "profiles/r02_ncu_rows.md; cudaLimitMaxL2FetchGranularity 32/64/128 changes nothing "
+                        "(profiles/r02_gather_gran.txt)")
+    # DRAM bytes the launch really moves: measured 93.4 B per random element read + 4 B index read + 4 B write
+    v["dram_gbs_ncu_traffic"] = round((93.4 + 8) * NI / v["ms"] / 1e6, 1)
+    v["dram_frac_ncu_traffic"] = round(v["dram_gbs_ncu_traffic"] / B.peaks["hbm"], 4)
     rows[k] = v
     k, v = hbm_row(B, "gather 2^26 sorted idx", lambda: table.gather(idx_sorted), 12 * NI)
     rows[k] = v
     B.gpu.wait()
     return {"workload": "table 8192^2 float32 (256 MiB), 2^26 uint32 indices from np.random.default_rng(99), and a sorted copy",
-            "rows": rows, "clocks": B.sampler.window(t0, time.time()), "bound": "hbm (sectors)", "peak": B.peaks["hbm"]}
+            "rows": rows, "clocks": B.sampler.window(t0, time.time()), "bound": "hbm (random: DRAM fetch granularity; sorted: streaming)", "peak": B.peaks["hbm"]}
 
 
 def config_c5(B):

@@ -1,6 +1,6 @@
 """Long-format `ncu --metrics ... --csv --log-file X.csv` -> one markdown table (one row per kernel/grid, last launch).
 
-  python scripts/ncu_rows_md.py gpurun_out/r02_ncu_rows_v2.csv profiles/r02_ncu_rows_v2.md "title"
+  python scripts/ncu_rows_md.py gpurun_out/r02_ncu_rows_v2.csv profiles/r02_ncu_rows_v2.md "title" [regex: kernels to list launch by launch]
 """
 import collections
 import csv
@@ -18,14 +18,16 @@ SHORT = {
     "sm__inst_executed_pipe_lsu.sum": "lsu inst M", "lts__t_sector_hit_rate.pct": "L2 hit %",
     "dram__sectors_read.sum": "DRAM rd sectors M", "lts__t_sectors_srcunit_tex_op_read.sum": "L2 rd sectors (tex) M",
     "lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum": "L2 rd hit sectors M",
+    "lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum": "L2 rd miss sectors M",
     "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum": "L1 ld sectors M",
 }
 SCALE = {"DRAM rd MB": 1e-6, "DRAM wr MB": 1e-6, "warp inst M": 1e-6, "fp64 inst M": 1e-6, "fma inst M": 1e-6,
          "alu inst M": 1e-6, "xu inst M": 1e-6, "lsu inst M": 1e-6, "DRAM rd sectors M": 1e-6,
-         "L2 rd sectors (tex) M": 1e-6, "L2 rd hit sectors M": 1e-6, "L1 ld sectors M": 1e-6}
+         "L2 rd sectors (tex) M": 1e-6, "L2 rd hit sectors M": 1e-6, "L2 rd miss sectors M": 1e-6, "L1 ld sectors M": 1e-6}
 
 
-def main(src, dst, title):
+def main(src, dst, title, every=None):
+    import re
     rows = list(csv.reader(l for l in open(src) if l.startswith('"')))
     hdr = rows[0]
     c = {k: hdr.index(k) for k in ("ID", "Kernel Name", "Grid Size", "Metric Name", "Metric Unit", "Metric Value")}
@@ -35,6 +37,8 @@ def main(src, dst, title):
             continue
         name = r[c["Kernel Name"]].split("(")[0].replace("void ", "").replace("<unnamed>::", "")
         key = (name, r[c["Grid Size"]])
+        if every and re.search(every, name):
+            key = (name + " #" + r[c["ID"]], r[c["Grid Size"]])      # list every launch of these kernels
         d = per.setdefault(key, {})
         if d.get("_id") != r[c["ID"]]:
             d.clear()
@@ -71,4 +75,4 @@ def main(src, dst, title):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "ncu rows")
+    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "ncu rows", sys.argv[4] if len(sys.argv) > 4 else None)

@@ -27,7 +27,9 @@ def _tolerance(call):
     """(rtol, atol) for the buffers a call writes; (0, 0) means bit-exact."""
     m = call["method"]
     if call["kind"] == "rng":
-        return (0.0, 4e-6) if m == "normal" else (0.0, 0.0)
+        if m == "normal":                 # absolute error scales with stddev (args: n, buffer, mean, stddev)
+            return 0.0, 5e-6 * max(1.0, abs(float(call["args"][3]["v"])))
+        return 0.0, 0.0
     if m in ("fill", "fill_many", "argreduce", "argsort_u32"):
         return 0.0, 0.0
     if m == "submit":
@@ -41,7 +43,7 @@ def _tolerance(call):
         if b in ("matmul", "batch_affine"):
             return 1e-5, 1e-5
         if b.startswith("prng_"):
-            return 0.0, 4e-6
+            return 0.0, 2e-5              # Box-Muller shaders: 4e-6 x stddev (the suite uses stddev <= 3)
         if b.startswith("nn_cross_entropy"):
             return 2e-7, 1e-7
         return 5e-7, 1e-7                 # libdevice-grade transcendentals: <= 2 ulp
@@ -122,6 +124,7 @@ def replay(dev, make_rng, calls, arrays, exact=False, make_buffer=None):
                 continue                        # entropy-seeded generator: values are not comparable
         dev.wait()
         for b, e in outs:
+            b.host_acquire()                    # host-visible and synchronised (what Array.__array__ does)
             got, want = np.asarray(b.arr if hasattr(b, "arr") else b).copy(), rp.arr(e["post"])
             if exact:
                 np.testing.assert_array_equal(got, want, err_msg=where)

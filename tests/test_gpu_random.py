@@ -14,12 +14,30 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def test_docstring_vectors(gpu):
+# Box-Muller runs in one of two modes (vkp_math.cuh): the default evaluates log / sqrt / sin / cos on the
+# special-function unit -- what a Vulkan driver makes of the reference's shader on this GPU -- and stays within
+# NORMAL_FAST_ATOL of the float64 value for unit stddev (bound from the exhaustive sweep scripts/micro/mufu_error.cu:
+# |dr| <= 6.3e-7, |dsin|, |dcos| <= 7.1e-7, r <= 5.65; 3.1e-6 observed over 2^24 samples);
+# VKP_NORMAL_PRECISE=1 selects <= 2 ulp float32 routines.  Both consume the same uniforms.
+NORMAL_FAST_ATOL = 5e-6
+
+
+@pytest.fixture(params=["fast", "precise"])
+def normal_mode(request, monkeypatch):
+    monkeypatch.setenv("VKP_NORMAL_PRECISE", "1" if request.param == "precise" else "0")
+    return request.param
+
+
+def test_docstring_vectors(gpu, normal_mode):
     vec = json.load(open(os.path.join(GOLDEN, "reference_vectors.json")))
     r = vk.random.Xoshiro128pp(gpu, seed=0)
     np.testing.assert_array_equal(np.asarray(r.random(shape=(3,))), np.asarray(vec["random_3"], dtype=np.float32))
-    np.testing.assert_allclose(np.asarray(r.normal(shape=(3,))),
-                               np.asarray(vec["normal_3_after_random_3"], dtype=np.float32), rtol=3e-7)
+    got = np.asarray(r.normal(shape=(3,)))
+    want = np.asarray(vec["normal_3_after_random_3"], dtype=np.float32)
+    if normal_mode == "precise":
+        np.testing.assert_allclose(got, want, rtol=3e-7)
+    else:
+        np.testing.assert_allclose(got, want, rtol=0, atol=NORMAL_FAST_ATOL)
 
 
 def test_golden_streams(gpu):
@@ -68,14 +86,15 @@ def test_literal_single_dispatch_shader(gpu):
 
 @pytest.mark.parametrize("size", [64, 2, 3, 256])
 @pytest.mark.parametrize("n", [1, 2, 3, 10, 11, 127, 128, 129, 100001, 100002])
-def test_normal_vs_oracle(gpu, size, n):
+def test_normal_vs_oracle(gpu, size, n, normal_mode):
     r = vk.random.Xoshiro128pp(gpu, size, seed=5)
     o = orc.Xoshiro128pp(size, 5)
     got = np.asarray(r.normal(shape=(n,), mean=1.5, stddev=2.0))
     want = o.normal(n, 1.5, 2.0)
-    # fp32 log (CR), sqrt (IEEE), sin/cos (<= 2 ulp) with one rounding per shader operation
-    # (prng_box_muller.comp:26-31); the mean shifts the result, so compare absolutely
-    np.testing.assert_allclose(got, want, rtol=0, atol=4e-6)
+    # precise: fp32 log (CR), sqrt (IEEE), sin/cos (<= 2 ulp) with one rounding per shader operation
+    # (prng_box_muller.comp:26-31); the mean shifts the result, so compare absolutely.  fast: the
+    # special-function unit's error scales with stddev (2.0 here)
+    np.testing.assert_allclose(got, want, rtol=0, atol=4e-6 if normal_mode == "precise" else 2.0 * NORMAL_FAST_ATOL)
     # both consumed n (even) or n+1 (odd) uniforms: the streams stay in lock step
     np.testing.assert_array_equal(np.asarray(r.randint(shape=(9,))), o.randint(9))
 
@@ -117,7 +136,20 @@ def test_randrange_bit_exact(gpu):
                                       o.randrange(1000, low, high))
 
 
-def test_unfused_box_muller_ops(gpu):
+def test_normal_fast_error_over_2_pow_24_samples(gpu, monkeypatch):
+    """Both modes on the same uniforms: the default's distance from the <= 2 ulp evaluation, over 2^24 samples."""
+    n = 1 << 24
+    monkeypatch.setenv("VKP_NORMAL_PRECISE", "1")
+    p = np.asarray(vk.random.Xoshiro128pp(gpu, seed=11).normal(shape=(n,)))
+    monkeypatch.setenv("VKP_NORMAL_PRECISE", "0")
+    f = np.asarray(vk.random.Xoshiro128pp(gpu, seed=11).normal(shape=(n,)))
+    err = np.abs(f.astype(np.float64) - p)
+    print("normal: fast vs precise max abs", err.max(), "mean abs", err.mean())
+    assert err.max() <= NORMAL_FAST_ATOL
+    assert abs(f.mean()) < 2e-3 and abs(f.std() - 1) < 2e-3
+
+
+def test_unfused_box_muller_ops(gpu, normal_mode):
     """The two Box-Muller shaders through vkp_submit agree with the fused generator."""
     base = vk.random.PRNG.normal
     for n in (10, 11):

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <cstdarg>
 #include <cstring>
@@ -143,6 +144,13 @@ int vkp_finish_op(vkp_ctx* ctx, vkp_job** job);
 int vkp_workspace(vkp_ctx* ctx, int slot, size_t bytes, void** out);
 // call right after each <<<>>> launch
 int vkp_after_launch(vkp_ctx* ctx, const char* what);
+
+// VKP_NORMAL_PRECISE=1: Box-Muller's log / sqrt / sin / cos as <= 2 ulp float32 routines instead of the
+// special-function unit (vkpm::box_muller_fast); read per call so a test can flip it inside one process
+static inline bool vkp_normal_precise() {
+  const char* e = getenv("VKP_NORMAL_PRECISE");
+  return e && e[0] == '1';
+}
 
 static inline unsigned vkp_grid_for(vkp_ctx* ctx, size_t work_items, unsigned per_block,
                                     unsigned blocks_per_sm) {

@@ -196,6 +196,31 @@ struct TPowScalar {
   }
   __device__ float slow(float a, float) const { return REV ? vkpm::pow_f(s, a) : vkpm::pow_f(a, s); }
 };
+// a ** s, vector form: the domain tests leave the per-element path.  |s| < 2^19 is a per-thread test (it bounds
+// |s log2 a| < 2^26, so k = rint(32 s log2 a) is exact); the bases must be positive normal floats and
+// -126*32 <= k < 128*32 (the result is then a normal float: no flush needed) -- both tested through the
+// min / max over the four elements.  Anything else re-evaluates the vector with pow_f.
+struct TPowScalarV {
+  float s;
+  __device__ float fast(const LaneTables& t, float a, float, bool& sp) const { return vkpm::pow_core(a, s, t, sp); }
+  __device__ float slow(float a, float) const { return vkpm::pow_f(a, s); }
+  __device__ float4 fast4(const LaneTables& t, float4 a, float4, bool& sp) const {
+    const double sd = (double)s;
+    int k0, k1, k2, k3;
+    float4 r;
+    r.x = vkpm::pow_core_nc(a.x, sd, t, k0);
+    r.y = vkpm::pow_core_nc(a.y, sd, t, k1);
+    r.z = vkpm::pow_core_nc(a.z, sd, t, k2);
+    r.w = vkpm::pow_core_nc(a.w, sd, t, k3);
+    const uint32_t u0 = __float_as_uint(a.x), u1 = __float_as_uint(a.y), u2 = __float_as_uint(a.z),
+                   u3 = __float_as_uint(a.w);
+    const uint32_t umin = min(min(u0, u1), min(u2, u3)), umax = max(max(u0, u1), max(u2, u3));
+    const int kmin = min(min(k0, k1), min(k2, k3)), kmax = max(max(k0, k1), max(k2, k3));
+    sp |= (umin < 0x00800000u) | (umax >= 0x7f800000u) | (kmin < -126 * 32) | (kmax >= 128 * 32) |
+          !(fabsf(s) < 524288.0f);
+    return r;
+  }
+};
 
 template <class F>
 __device__ __noinline__ float4 redo_slow(const F f, float4 a, float4 b) {
@@ -203,54 +228,81 @@ __device__ __noinline__ float4 redo_slow(const F f, float4 a, float4 b) {
   return make_float4(f.slow(a.x, b.x), f.slow(a.y, b.y), f.slow(a.z, b.z), f.slow(a.w, b.w));
 }
 
-template <int NIN, class F>
-__global__ void __launch_bounds__(EW_BLOCK)
+// minimum resident CTAs per SM (register cap): the two-input pow kernel is fastest at 48 registers
+// (profiles/r02_pow_variants.txt: 82 -> 48 registers, 5623 -> 5860 GB/s), the others are left to the compiler
+template <class F> struct TabMinBlocks { static constexpr int v = 1; };
+template <> struct TabMinBlocks<TPow> { static constexpr int v = 5; };
+
+// one vector (four elements) through the fast path; functors with a vector form (fast4) test their domain
+// with min / max over the four elements instead of per element
+template <class F, class = void> struct HasFast4 { static constexpr bool v = false; };
+template <class F> struct HasFast4<F, decltype((void)&F::fast4)> { static constexpr bool v = true; };
+template <class F>
+__device__ __forceinline__ float4 tab_eval4(const F& f, const LaneTables& tab, float4 a, float4 b, bool& sp) {
+  if constexpr (HasFast4<F>::v) {
+    return f.fast4(tab, a, b, sp);
+  } else {
+    float4 r;
+    r.x = f.fast(tab, a.x, b.x, sp);
+    r.y = f.fast(tab, a.y, b.y, sp);
+    r.z = f.fast(tab, a.z, b.z, sp);
+    r.w = f.fast(tab, a.w, b.w, sp);
+    return r;
+  }
+}
+
+// FULL: CTA `blockIdx.x` owns one whole tile -- no bounds test anywhere, all loads issued before the first
+// use.  (One kernel with a CTA-uniform "whole tile?" branch compiled to predicated loads and a serialised
+// evaluation: 0.58 ms against 0.48 ms for a**2.7 on 2^28 elements, scripts/micro/pow_variants.cu.)
+// !FULL: ONE CTA for what is left after the whole tiles: the partial tile, predicated, plus the n % 4 tail.
+template <int NIN, class F, bool FULL>
+__global__ void __launch_bounds__(EW_BLOCK, TabMinBlocks<F>::v)
 ew_tab_kernel(F f, const __grid_constant__ vkpm::MathCoef coef, const float* in0, const float* in1, float* out,
-              size_t n) {
+              size_t n, size_t first_tile) {
   const LaneTables tab(coef);
   const size_t nvec = n >> 2;
   const float4* v0 = reinterpret_cast<const float4*>(in0);
   const float4* v1 = reinterpret_cast<const float4*>(in1);
   float4* vo = reinterpret_cast<float4*>(out);
-  const size_t base = (size_t)blockIdx.x * EW_TILE_VEC + threadIdx.x;
+  const size_t base = (first_tile + blockIdx.x) * EW_TILE_VEC + threadIdx.x;
   float4 a[EW_UNROLL], b[EW_UNROLL];
-  // Whole tile in range (every CTA but the last): all loads are issued before the first use and
-  // carry no predicate -- the predicated form below made the compiler load one vector, evaluate it,
-  // and only then fetch the other three (two exposed memory latencies per CTA:
-  // profiles/r02_pow_sass_notes.md).  The test is CTA-uniform, the shuffles stay warp-collective.
-  const bool full = (size_t)(blockIdx.x + 1) * EW_TILE_VEC <= nvec;
-  if (full) {
+  if (FULL) {
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; u++) {
       a[u] = v0[base + (size_t)u * EW_BLOCK];
       if (NIN > 1) b[u] = v1[base + (size_t)u * EW_BLOCK];
     }
-  } else {
-    const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; u++) {
-      const size_t i = base + (size_t)u * EW_BLOCK;
-      a[u] = one;
-      b[u] = one;
-      if (i < nvec) {
-        a[u] = v0[i];
-        if (NIN > 1) b[u] = v1[i];
-      }
+      bool sp = false;
+      float4 r = tab_eval4(f, tab, a[u], b[u], sp);
+      if (sp) r = redo_slow(f, a[u], b[u]);   // rare: zero / negative / denormal / inf / nan / overflow
+      vo[base + (size_t)u * EW_BLOCK] = r;
+    }
+    return;
+  }
+  // every lane of a warp evaluates the functor together (lookups are shuffles): out-of-range lanes compute on
+  // dummy inputs and only their loads / stores are predicated off
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+  for (int u = 0; u < EW_UNROLL; u++) {
+    const size_t i = base + (size_t)u * EW_BLOCK;
+    a[u] = one;
+    b[u] = one;
+    if (i < nvec) {
+      a[u] = v0[i];
+      if (NIN > 1) b[u] = v1[i];
     }
   }
 #pragma unroll
   for (int u = 0; u < EW_UNROLL; u++) {
     const size_t i = base + (size_t)u * EW_BLOCK;
     bool sp = false;
-    float4 r;
-    r.x = f.fast(tab, a[u].x, b[u].x, sp);
-    r.y = f.fast(tab, a[u].y, b[u].y, sp);
-    r.z = f.fast(tab, a[u].z, b[u].z, sp);
-    r.w = f.fast(tab, a[u].w, b[u].w, sp);
-    if (sp) r = redo_slow(f, a[u], b[u]);   // rare: zero / negative / denormal / inf / nan / overflow
-    if (full || i < nvec) vo[i] = r;
+    float4 r = tab_eval4(f, tab, a[u], b[u], sp);
+    if (sp) r = redo_slow(f, a[u], b[u]);
+    if (i < nvec) vo[i] = r;
   }
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x < 32) {   // n % 4 tail, whole first warp participates
+  if (threadIdx.x < 32) {   // n % 4 tail, whole first warp participates
     const size_t i = (nvec << 2) + threadIdx.x;
     const float a1 = i < n ? in0[i] : 1.f;
     const float b1 = (NIN > 1 && i < n) ? in1[i] : 1.f;
@@ -265,11 +317,19 @@ template <int NIN, class F>
 int launch_ew_tab(vkp_ctx* ctx, const char* name, F f, const void* in0, const void* in1, void* out, size_t n) {
   if (n == 0) return VKP_OK;
   const size_t nvec = n >> 2;
-  const size_t tiles = (nvec + EW_TILE_VEC - 1) / EW_TILE_VEC;
-  const unsigned grid = (unsigned)(tiles ? tiles : 1);
+  const size_t full_tiles = nvec / EW_TILE_VEC;
   const vkpm::MathCoef& coef = vkpt::host_coef();
-  ew_tab_kernel<NIN, F><<<grid, EW_BLOCK, 0, ctx->stream>>>(f, coef, (const float*)in0, (const float*)in1, (float*)out, n);
-  return vkp_after_launch(ctx, name);
+  if (full_tiles) {
+    ew_tab_kernel<NIN, F, true><<<(unsigned)full_tiles, EW_BLOCK, 0, ctx->stream>>>(
+        f, coef, (const float*)in0, (const float*)in1, (float*)out, n, 0);
+    VKP_TRY(vkp_after_launch(ctx, name));
+  }
+  if (full_tiles * EW_TILE_VEC * 4 < n) {
+    ew_tab_kernel<NIN, F, false><<<1, EW_BLOCK, 0, ctx->stream>>>(
+        f, coef, (const float*)in0, (const float*)in1, (float*)out, n, full_tiles);
+    VKP_TRY(vkp_after_launch(ctx, name));
+  }
+  return VKP_OK;
 }
 
 // ---- fused element-wise chains (lazy element-wise fusion) -------------------
@@ -415,6 +475,7 @@ ew_chain_kernel(const __grid_constant__ ChainProg prog, const __grid_constant__ 
 // ---- Box-Muller (prng_box_muller.comp:19-32, prng_ibox_muller.comp:16-27) -----------------
 // One thread per pair.  Unlike the reference dispatch (floor(n/2) invocations rounded up to a
 // workgroup, random.py:106-121) the last element of an odd-length output is always written.
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 box_muller_kernel(const float* a, float* b, size_t n, float mean, float stddev) {
   const size_t npair = (n + 1) >> 1;
@@ -422,7 +483,7 @@ box_muller_kernel(const float* a, float* b, size_t n, float mean, float stddev) 
     const size_t j = 2 * i, k = j + 1;
     const float2 u = *reinterpret_cast<const float2*>(a + j);  // a has an even number of elements
     float o0, o1;
-    vkpm::box_muller_pair(u.x, u.y, mean, stddev, o0, o1);
+    vkpm::box_muller_pair<FAST>(u.x, u.y, mean, stddev, o0, o1);
     if (k < n) *reinterpret_cast<float2*>(b + j) = make_float2(o0, o1);
     else b[j] = o0;
   }
@@ -499,7 +560,7 @@ int dispatch_scalar(vkp_ctx* ctx, int sub, float s, const void* a, void* out, si
       // x ** 2.0 (MSELoss, Ridge, Adam, AdaGrad: nn/losses.py:294-296, nn/optimizers.py:131,239) is the
       // exactly rounded square, also on ties and for negative x
       if (s == 2.0f) return launch_ew<1>(ctx, "pow_scalar(2)", USquare(), a, nullptr, nullptr, out, n);
-      return launch_ew_tab<1>(ctx, "pow_scalar", TPowScalar<false>{s}, a, nullptr, out, n);
+      return launch_ew_tab<1>(ctx, "pow_scalar", TPowScalarV{s}, a, nullptr, out, n);
     case VKB_RSUB: return launch_scalar<FSub>(ctx, "rsub_scalar", true, s, a, out, n);
     case VKB_RDIV: return launch_scalar<FDiv>(ctx, "rdiv_scalar", true, s, a, out, n);
     case VKB_RPOW: return launch_ew_tab<1>(ctx, "rpow_scalar", TPowScalar<true>{s}, a, nullptr, out, n);
@@ -598,8 +659,12 @@ int vkp_launch_elementwise(vkp_ctx* ctx, int fam, int sub, void* const* bufs, in
       NEED(2, vkp_vectorscalar2_params);
       if (p->size == 0) return VKP_OK;
       const unsigned grid = vkp_grid_for(ctx, (p->size + 1) / 2, 256, 8);
-      box_muller_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)bufs[0], (float*)bufs[1], p->size,
-                                                        p->scalar[0], p->scalar[1]);
+      if (vkp_normal_precise())
+        box_muller_kernel<false><<<grid, 256, 0, ctx->stream>>>((const float*)bufs[0], (float*)bufs[1], p->size,
+                                                               p->scalar[0], p->scalar[1]);
+      else
+        box_muller_kernel<true><<<grid, 256, 0, ctx->stream>>>((const float*)bufs[0], (float*)bufs[1], p->size,
+                                                              p->scalar[0], p->scalar[1]);
       return vkp_after_launch(ctx, "prng_box_muller");
     }
     case VKF_IBOX_MULLER: {  // A (rw, even n)
@@ -607,8 +672,12 @@ int vkp_launch_elementwise(vkp_ctx* ctx, int fam, int sub, void* const* bufs, in
       if (p->size == 0) return VKP_OK;
       VKP_CHECK(p->size % 2 == 0, "prng_ibox_muller needs an even element count (random.py:109-115)");
       const unsigned grid = vkp_grid_for(ctx, p->size / 2, 256, 8);
-      box_muller_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)bufs[0], (float*)bufs[0], p->size,
-                                                        p->scalar[0], p->scalar[1]);
+      if (vkp_normal_precise())
+        box_muller_kernel<false><<<grid, 256, 0, ctx->stream>>>((const float*)bufs[0], (float*)bufs[0], p->size,
+                                                               p->scalar[0], p->scalar[1]);
+      else
+        box_muller_kernel<true><<<grid, 256, 0, ctx->stream>>>((const float*)bufs[0], (float*)bufs[0], p->size,
+                                                              p->scalar[0], p->scalar[1]);
       return vkp_after_launch(ctx, "prng_ibox_muller");
     }
     case VKF_RANDRANGE: {  // A ([0,1) floats), B (u32 out)

@@ -12,7 +12,12 @@
 namespace {
 
 constexpr int GA_BLOCK = 256;
-constexpr int GA_UNROLL = 2;
+// 4 index vectors (16 dependent 4-byte reads) in flight per thread and a grid of 16 CTAs per SM: 1.085 ms for
+// 2^26 random indices into 256 MiB against 1.155 ms at 2 / 8 (profiles/r02_gather_gran.txt).  The random gather
+// is DRAM-bound, not latency-bound: ncu counts 6.26 GB read from DRAM per launch (93 B per 4-byte element, the
+// memory system's fetch granularity; cudaLimitMaxL2FetchGranularity 32/64/128 makes no difference), i.e.
+// 5.6 TB/s of DRAM traffic (profiles/r02_ncu_rows.md).
+constexpr int GA_UNROLL = 4;
 
 __global__ void __launch_bounds__(GA_BLOCK)
 gather_kernel(const float* __restrict__ a, const uint32_t* __restrict__ idx, float* __restrict__ c, size_t n) {
@@ -80,7 +85,7 @@ int vkp_launch_gather(vkp_ctx* ctx, int fam, int sub, void* const* bufs, int nbu
     VKP_CHECK(nbuf == 3 && pbytes == sizeof(vkp_vector_params), "gather: bad arguments");
     const auto* p = static_cast<const vkp_vector_params*>(params);
     if (p->size == 0) return VKP_OK;
-    const unsigned grid = vkp_grid_for(ctx, (p->size + 3) / 4, GA_BLOCK * GA_UNROLL, 8);
+    const unsigned grid = vkp_grid_for(ctx, (p->size + 3) / 4, GA_BLOCK * GA_UNROLL, 16);
     gather_kernel<<<grid, GA_BLOCK, 0, ctx->stream>>>((const float*)bufs[0], (const uint32_t*)bufs[1],
                                                       (float*)bufs[2], p->size);
     return vkp_after_launch(ctx, "gather");

@@ -327,9 +327,22 @@ VKP_HD double small_int_to_double(int e) {
 // log2(e) r^7/7 < 2^-41 absolute and < 2^-36 relative to the result.
 template <class TA>
 VKP_HD double log2_tab(uint32_t u, const TA& ta) {
+#if defined(VKPM_LOG_BIAS)
+  // biased exponent: d = (u - bits(2/3)) + (128 << 23) never wraps for a finite positive u, so e + 128 is a
+  // LOGICAL shift and the int -> double step needs no sign flip
+  const uint32_t d = u + 0x00d55555u;
+  const uint32_t mb = u + 0x40000000u - (d & 0xff800000u);  // float bits of m = x / 2^e
+  const double ed = hilo2d(0x43300000u, d >> 23) - 4503599627370624.0;   // (2^52 + e + 128) - (2^52 + 128)
+#else
   const uint32_t d = u - 0x3f2aaaabu;                       // bits of 2/3
   const int e = (int)d >> 23;
   const uint32_t mb = u - (d & 0xff800000u);                // float bits of m = x / 2^e
+#if !defined(VKPM_LOG_NO_I2F)
+  const double ed = (double)e;                              // one conversion-unit instruction
+#else
+  const double ed = small_int_to_double(e);
+#endif
+#endif
   const double md = (double)bits2f(mb);                     // exact (one conversion; no bit assembly)
   // interval index = bits 18..22 of d; the accessor uses only the low 5 bits of the index it is given
   const double r = dfma(md, ta.rc(d >> 18), -1.0);          // exact
@@ -339,7 +352,7 @@ VKP_HD double log2_tab(uint32_t u, const TA& ta) {
   p = dfma(p, r, ta.lc(3));
   p = dfma(p, r, ta.lc(4));
   p = dfma(p, r, ta.lc(5));
-  return dfma(p, r, small_int_to_double(e) + ta.l2(d >> 18));
+  return dfma(p, r, ed + ta.l2(d >> 18));
 }
 
 // 2^t; meaningful for |t| <= 150 (other inputs give garbage but never trap)
@@ -355,7 +368,13 @@ VKP_HD double exp2_tab(double t, const TA& ta) {
   p = dfma(p, r, ta.ec(3));
   p = dfma(p, r, 1.0);
   const double v = p * ta.e2(k);             // in [0.98, 2.02]; the accessor uses the low 5 bits of k
+#if !defined(VKPM_EXP_NO_MAD) && defined(__CUDA_ARCH__)
+  uint32_t hi;                                                     // += (k >> 5) in the exponent field: LOP3 + IMAD
+  asm("mad.lo.u32 %0, %1, 32768, %2;" : "=r"(hi) : "r"((uint32_t)(k & ~31)), "r"(hi32(v)));
+  return hilo2d(hi, lo32(v));
+#else
   return hilo2d(hi32(v) + ((uint32_t)(k & ~31) << 15), lo32(v));   // += (k >> 5) in the exponent field
+#endif
 }
 
 // Fast cores: every lane of a warp calls them together on the device (lookups are shuffles).
@@ -391,6 +410,26 @@ VKP_HD float pow_core(float x, float y, const TA& ta, bool& special) {
   const double t = (double)y * log2_tab(ux, ta);
   special |= !((ux - 0x00800000u) < 0x7f000000u) | !((hi32(t) & 0x7fffffffu) < 0x4062c000u);   // x not positive
   return d2f_ftz(exp2_tab(t, ta));                                           // normal, or |t| >= 150 / nan
+}
+
+// pow without the domain tests: returns the value of pow_core and k = rint(32 y log2(x)) (only meaningful when
+// |y log2 x| < 2^26: callers bound |y| < 2^19 and x to positive normal floats).  The caller tests
+// -126*32 <= k < 128*32 -- inside that range the result is a normal float (no flush needed), outside it
+// (or for x / y outside their domains) it must call pow_f.  Lets a kernel test min / max over a vector.
+template <class TA>
+VKP_HD float pow_core_nc(float x, double yd, const TA& ta, int& k_out) {
+  const double t = yd * log2_tab(f2bits(x), ta);
+  const double magic = 6755399441055744.0;
+  const double kd = dfma(t, 32.0, magic);
+  k_out = (int)lo32(kd);
+  const double v = exp2_tab(t, ta);
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("cvt.rn.f32.f64 %0, %1;" : "=f"(r) : "d"(v));
+  return r;
+#else
+  return (float)v;
+#endif
 }
 
 // convenience wrappers (host tests, single-element callers)
@@ -539,11 +578,42 @@ VKP_HD void box_muller_core(float om, float u1, float mean, float stddev, float&
   o1 = mean + r * c;
 }
 
+// The same pair through the special-function unit -- what the reference's shader turns into on this very GPU:
+// a Vulkan driver compiles GLSL log / sqrt / sin / cos to the hardware approximations (lg2 * ln2, sqrt.approx,
+// sin.approx / cos.approx), whose error the Vulkan spec allows to be far larger (sin / cos: 2^-11 absolute) than
+// what is measured here over EVERY input the generator can produce (scripts/micro/mufu_error.cu, numbers in
+// DESIGN.md).  lg2.approx has only ABSOLUTE accuracy near 1, so for u0 = 1 - om < 2^-5 the logarithm is the
+// series 2 (u + u^2/2 + u^3/3 + u^4/4 + u^5/5) instead (truncation < 2^-26 relative).
+VKP_HD void box_muller_fast(float om, float u1, float mean, float stddev, float& o0, float& o1) {
+#if defined(__CUDA_ARCH__)
+  float l2, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(om));
+  float L = l2 * -1.3862943611198906f;                 // -2 ln(om) >= 0
+  const float u0 = 1.0f - om;                          // exact
+  if (u0 < 0.03125f) {
+    float p = ffma(u0, 0.4f, 0.5f);
+    p = ffma(p, u0, 0.6666667f);
+    p = ffma(p, u0, 1.0f);
+    p = ffma(p, u0, 2.0f);
+    L = p * u0;
+  }
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(L));
+  r *= stddev;
+  const float angle = 6.28318530718f * u1;
+  o0 = mean + r * __sinf(angle);
+  o1 = mean + r * __cosf(angle);
+#else
+  box_muller_core(om, u1, mean, stddev, o0, o1);
+#endif
+}
+
+template <bool FAST = false>
 VKP_HD void box_muller_pair(float u0, float u1, float mean, float stddev, float& o0, float& o1) {
   // uniforms outside [0, 1) can only come from a caller-made buffer; keep log's domain
   float om = 1.0f - u0;
   om = om < 1.1920929e-7f ? 1.1920929e-7f : (om > 1.0f ? 1.0f : om);
-  box_muller_core(om, u1, mean, stddev, o0, o1);
+  if (FAST) box_muller_fast(om, u1, mean, stddev, o0, o1);
+  else box_muller_core(om, u1, mean, stddev, o0, o1);
 }
 
 VKP_HD float sign_f(float x) {

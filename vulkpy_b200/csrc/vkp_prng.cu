@@ -234,6 +234,7 @@ xoshiro_stream_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ st
 // Fused uniform -> Box-Muller (random.py:60-124 + prng_box_muller.comp:19-32): a thread owns the
 // lane pair (l0, l0+1), whose draws are the adjacent outputs (2i, 2i+1); the uniforms never leave
 // registers.  n_draw = n rounded up to even (the reference draws n+1 uniforms for odd n).
+template <bool FAST>
 __global__ void __launch_bounds__(128)
 xoshiro_normal_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ state_out, float* __restrict__ out,
                       const uint4* __restrict__ jump, uint32_t size, uint64_t n_draw, uint64_t n_out,
@@ -265,7 +266,8 @@ xoshiro_normal_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ st
   {                                                                                                  \
     const float om = 2.0f - __uint_as_float((next_dev(s0) >> 9) | 0x3f800000u);                      \
     const float u1 = u2f01(next_dev(s1));                                                            \
-    vkpm::box_muller_core(om, u1, mean, stddev, o0, o1);                                             \
+    if (FAST) vkpm::box_muller_fast(om, u1, mean, stddev, o0, o1);                                   \
+    else vkpm::box_muller_core(om, u1, mean, stddev, o0, o1);                                        \
   }
   const uint64_t e1 = seg_end < full ? seg_end : full;
   uint64_t iters = e1 > start ? e1 - start : 0;
@@ -437,8 +439,14 @@ static int rng_generate(vkp_rng* rng, void* out, uint64_t n_out, float mean, flo
   xoshiro_stream_kernel<LPT, (MODE == MODE_NORMAL ? MODE_F32 : MODE)><<<grid, 128, 0, ctx->stream>>>(     \
       sin_, sout, (uint32_t*)out, rng->jump, size, n_draw, log2L, nseg, cs)
     if (MODE == MODE_NORMAL) {
-      xoshiro_normal_kernel<<<grid, 128, 0, ctx->stream>>>(sin_, sout, (float*)out, rng->jump, size, n_draw, n_out,
-                                                           log2L, nseg, mean, stddev);
+      // VKP_NORMAL_PRECISE=1: log / sqrt / sin / cos as <= 2 ulp float32 routines instead of the special-function
+      // unit (see vkpm::box_muller_fast); read per call so a test can flip it
+      if (vkp_normal_precise())
+        xoshiro_normal_kernel<false><<<grid, 128, 0, ctx->stream>>>(sin_, sout, (float*)out, rng->jump, size, n_draw,
+                                                                    n_out, log2L, nseg, mean, stddev);
+      else
+        xoshiro_normal_kernel<true><<<grid, 128, 0, ctx->stream>>>(sin_, sout, (float*)out, rng->jump, size, n_draw,
+                                                                   n_out, log2L, nseg, mean, stddev);
     }
     else if (lpt == 4) { LAUNCH(4); }
     else if (lpt == 2) { LAUNCH(2); }
