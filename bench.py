@@ -675,6 +675,17 @@ def sharded_block(B):
     single_mlp = make_mlp()
     row("data-parallel MLP step, 8192 rows per GPU (gradient bucket through the peer mailbox)",
         lambda: dpm.train(xb, yb)[1], lambda: single_mlp.train(xb, yb)[1], Bl * world * 1e3, "rows/s aggregate", min_ms=100.0)
+    # the exchange alone, back to back: what the gradient bucket costs on the device when no rank is late
+    grads = [p.grad for p in dpm.parameters()]
+    bucket_bytes = sum(4 * gr.buffer.size() for gr in grads)
+    r = row("gradient bucket all-reduce alone (peer mailbox, two-shot), back to back",
+            lambda: g.t.allreduce_many(grads, "sum", 1.0)[0], None, bucket_bytes / GB, "GB/s of bucket per rank", min_ms=20.0)
+    r["bucket_bytes"] = bucket_bytes
+    dp_row = rows_t["data-parallel MLP step, 8192 rows per GPU (gradient bucket through the peer mailbox)"]
+    dp_row["limiter"] = (f"step = local step {dp_row.get('ms_one_gpu_same_local_work')} ms + exchange; the exchange alone takes "
+                         f"{r['ms']} ms back to back, the rest of the difference is rank skew: the host enqueues "
+                         f"{dp_row['launches']} launches per step in about the time the device runs them, so a late "
+                         "rank stalls all of them at the flag wait")
     # property: replicas stay identical (same reduced gradients, same optimizer step on every rank)
     sig = gathered(np.asarray(mlp.L[0].w.value.sum()).tobytes() + np.asarray(mlp.L[2].w.value.sum()).tobytes())
     assert all(s == sig[0] for s in sig), "data-parallel replicas diverged"

@@ -192,6 +192,12 @@ VKP_API int vkp_nn_activation_backward(vkp_ctx* ctx, int kind, const float* y, c
 /* Softmax.forward over axis 1 of [rows, cols] (nn/layers.py:297-300) */
 VKP_API int vkp_nn_softmax_forward(vkp_ctx* ctx, const float* x, float* y, uint32_t rows, uint32_t cols,
                                    vkp_job** job);
+/* Tail of a classifier's training step in one launch: p = softmax(z) (nn/layers.py:297-300),
+ * L = -t log(p + 1e-8) (nn_cross_entropy.comp:25), dz = ((1-p) p) * ((-t / (p + 1e-8)) [* scale])
+ * (nn_cross_entropy_backward.comp:25, nn/losses.py:58-68, nn/layers.py:320-323); the same float32 operations
+ * in the same order as the five launches it replaces.  z, t, p, L, dz: [rows, cols]. */
+VKP_API int vkp_nn_softmax_ce_train(vkp_ctx* ctx, const float* z, const float* t, float* p, float* L, float* dz,
+                                    uint32_t rows, uint32_t cols, float scale, int has_scale, vkp_job** job);
 
 /* ---- argmax / argmin / permutation.  The reference lists them as missing
  * (README.md:73 "argmax, argmin", :77 "shuffle") and its training example does them on the host

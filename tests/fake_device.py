@@ -267,6 +267,17 @@ class FakeDevice:
         y.arr[:] = (e / s[:, None]).astype(F).reshape(-1)
         return self._done("nn_softmax_forward", 2)
 
+    def nn_softmax_ce_train(self, z, t, p, L, dz, rows, cols, scale):
+        self.nn_softmax_forward(z, p, rows, cols)
+        self.launches -= 1
+        self.log.pop()
+        L.arr[:] = orc.cross_entropy(p.arr, t.arr)
+        g = orc.cross_entropy_backward(p.arr, t.arr)
+        if scale is not None:
+            g = (g * F(scale)).astype(F)
+        dz.arr[:] = (((F(1) - p.arr).astype(F) * p.arr).astype(F) * g).astype(F)
+        return self._done("nn_softmax_ce_train", 5)
+
 
 class FakeRng:
     """``_backend.Xoshiro128pp`` over the oracle generator."""

@@ -96,7 +96,7 @@ def _wrap(cls, name, kind):
 def install():
     import fake_device
     for m in ("submit", "ew_chain", "fill", "fill_many", "gemm", "argreduce", "argsort_u32", "nn_adam",
-              "nn_adam_apply_many", "nn_activation_backward", "nn_softmax_forward"):
+              "nn_adam_apply_many", "nn_activation_backward", "nn_softmax_forward", "nn_softmax_ce_train"):
         _wrap(fake_device.FakeDevice, m, "dev")
     for m in ("random_uint32", "random_float", "normal", "advance"):
         _wrap(fake_device.FakeRng, m, "rng")

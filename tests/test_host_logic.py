@@ -302,7 +302,8 @@ def test_sequence_train_one_launch_paths(vk, gpu, optname):
             np.testing.assert_array_equal(np.asarray(pa.value), np.asarray(pb.value))
             np.testing.assert_array_equal(np.asarray(pa.grad), np.asarray(pb.grad))
     names = [n for n, _ in gpu.gpu.log]
-    assert "fill_many" in names                      # all gradients zeroed by one launch
+    assert "fill_many" not in names                  # zero_grad launches nothing: the first contribution overwrites
+    assert "nn_softmax_ce_train" in names            # Softmax + CrossEntropy forward / backward tail: one launch
     if optname == "adam":
         assert "nn_adam_apply_many" in names         # all parameters stepped by one launch
     loss0 = float(np.asarray(a.train(A(vk, gpu, x), A(vk, gpu, y))[1]).reshape(-1)[0])

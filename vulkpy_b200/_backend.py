@@ -73,6 +73,7 @@ PROTOTYPES = {
     "vkp_nn_adam": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _sz] + [C.c_float] * 8 + [C.POINTER(_vp)]),
     "vkp_nn_activation_backward": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _sz, C.POINTER(_vp)]),
     "vkp_nn_softmax_forward": (C.c_int, [_vp, _vp, _vp, _u32, _u32, C.POINTER(_vp)]),
+    "vkp_nn_softmax_ce_train": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, C.c_float, C.c_int, C.POINTER(_vp)]),
     "vkp_job_wait": (C.c_int, [_vp, _u64]),
     "vkp_job_done": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "vkp_job_release": (C.c_int, [_vp]),
@@ -393,6 +394,13 @@ class Device:
     def nn_softmax_forward(self, x: Buffer, y: Buffer, rows: int, cols: int) -> Job:
         job = _vp()
         _check(lib.vkp_nn_softmax_forward(self._ctx, x.ptr, y.ptr, rows, cols, C.byref(job)))
+        return Job(job.value)
+
+    def nn_softmax_ce_train(self, z: Buffer, t: Buffer, p: Buffer, L: Buffer, dz: Buffer, rows: int, cols: int,
+                            scale: Optional[float]) -> Job:
+        job = _vp()
+        _check(lib.vkp_nn_softmax_ce_train(self._ctx, z.ptr, t.ptr, p.ptr, L.ptr, dz.ptr, rows, cols,
+                                           0.0 if scale is None else float(scale), 0 if scale is None else 1, C.byref(job)))
         return Job(job.value)
 
     def wait(self):

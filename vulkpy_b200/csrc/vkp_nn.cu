@@ -146,6 +146,68 @@ softmax_fwd_kernel(const __grid_constant__ vkpm::MathCoef coef, const float* __r
   }
 }
 
+// The tail of a classifier's training step in one launch (Sequence.train with a Softmax last layer and
+// CrossEntropyLoss): per row
+//   p  = softmax(z)                                 exactly softmax_fwd_kernel above        (nn/layers.py:297-300)
+//   L  = (-t) * log(p + 1e-8)                       nn_cross_entropy.comp:25 (the loss still reduces L by its own jobs)
+//   g  = (-t) / (p + 1e-8);  g *= scale             nn_cross_entropy_backward.comp:25, losses.py:58-68 (1/batch for "mean")
+//   dz = ((1 - p) * p) * g                          Softmax.backward, nn/layers.py:320-323
+// -- the float32 operations of the five launches it replaces, in their order, one rounding each (-fmad=false),
+// so p, L and dz are bit-identical to the op-by-op path.  One warp per row.
+__global__ void __launch_bounds__(NB)
+softmax_ce_train_kernel(const __grid_constant__ vkpm::MathCoef coef, const float* __restrict__ z,
+                        const float* __restrict__ t, float* __restrict__ p, float* __restrict__ L,
+                        float* __restrict__ dz, uint32_t rows, uint32_t cols, float scale, int has_scale) {
+  const vkpt::LaneTables tab(coef);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps_per_grid = gridDim.x * (NB / 32);
+  const uint32_t nwarp_rows = (rows + warps_per_grid - 1) / warps_per_grid;
+  for (uint32_t it = 0; it < nwarp_rows; it++) {   // warp-uniform trip count (shuffles inside)
+    const uint32_t row = (blockIdx.x * (NB / 32) + (threadIdx.x >> 5)) + it * warps_per_grid;
+    const bool live_row = row < rows;
+    const size_t off = (size_t)(live_row ? row : 0) * cols;
+    const float* xr = z + off;
+    float* yr = p + off;
+    float mx = -INFINITY;
+    for (uint32_t k = lane; k < cols; k += 32) mx = fmaxf(mx, xr[k]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    const uint32_t nk = (cols + 31) / 32;
+    for (uint32_t j = 0; j < nk; j++) {
+      const uint32_t k = j * 32 + lane;
+      const bool ok = k < cols;
+      bool sp = false;
+      const float d = ok ? (xr[k] - mx) : 0.f;
+      float e = vkpm::exp_core(d, tab, sp);
+      if (sp) e = vkpm::exp_f(d);
+      if (!ok) e = 0.f;
+      if (live_row && ok) yr[k] = e;
+      for (uint32_t l = 0; l < 32; l++) {
+        const float el = __shfl_sync(0xffffffffu, e, l);
+        if (j * 32 + l < cols) sum = sum + el;
+      }
+    }
+    __syncwarp();
+    for (uint32_t j = 0; j < nk; j++) {          // every lane runs the table-driven log together
+      const uint32_t k = j * 32 + lane;
+      const bool ok = live_row && k < cols;
+      const float pk = ok ? yr[k] / sum : 1.0f;
+      const float tk = ok ? t[off + k] : 0.0f;
+      const float q = pk + 1e-8f;
+      bool sp = false;
+      float lg = vkpm::log_core(q, tab, sp);
+      if (sp) lg = vkpm::log_f(q);
+      float g = (-tk) / q;
+      if (has_scale) g = g * scale;
+      if (ok) {
+        yr[k] = pk;
+        L[off + k] = (-tk) * lg;
+        dz[off + k] = ((1.0f - pk) * pk) * g;
+      }
+    }
+  }
+}
+
 }  // namespace
 
 #define NN_PROLOGUE(...)                                   \
@@ -240,6 +302,18 @@ extern "C" int vkp_nn_softmax_forward(vkp_ctx* ctx, const float* x, float* y, ui
     const unsigned grid = vkp_grid_for(ctx, rows, NB / 32, 16);
     softmax_fwd_kernel<<<grid, NB, 0, ctx->stream>>>(vkpt::host_coef(), x, y, rows, cols);
     VKP_TRY(vkp_after_launch(ctx, "nn_softmax_forward"));
+  }
+  return vkp_finish_op(ctx, job);
+}
+
+extern "C" int vkp_nn_softmax_ce_train(vkp_ctx* ctx, const float* z, const float* t, float* p, float* L, float* dz,
+                                       uint32_t rows, uint32_t cols, float scale, int has_scale, vkp_job** job) {
+  VKP_RANGE(__func__);
+  NN_PROLOGUE((void*)z, (void*)t, p, L, dz);
+  if (rows && cols) {
+    const unsigned grid = vkp_grid_for(ctx, rows, NB / 32, 16);
+    softmax_ce_train_kernel<<<grid, NB, 0, ctx->stream>>>(vkpt::host_coef(), z, t, p, L, dz, rows, cols, scale, has_scale);
+    VKP_TRY(vkp_after_launch(ctx, "nn_softmax_ce_train"));
   }
   return vkp_finish_op(ctx, job);
 }

@@ -436,8 +436,12 @@ class DataParallel:
 
     def train(self, x, y):
         net, g = self.net, self.group
-        pred = net._forward(x)
-        loss = net.loss(pred, y)
+        forward_loss = getattr(net, "_forward_loss", None)      # Sequence: the fused Softmax + CrossEntropy tail
+        if forward_loss is not None:
+            pred, loss = forward_loss(x, y)
+        else:
+            pred = net._forward(x)
+            loss = net.loss(pred, y)
         net._zero_grad()
         net._backward()
         inv = 1.0 / g.world

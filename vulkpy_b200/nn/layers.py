@@ -82,15 +82,20 @@ class Dense(Module):
 
     def _backward_params(self, dy: Array):
         """Parameter gradients only (what ``Sequence`` needs from its first layer)."""
-        self.b.add_grad(dy.sum(axis=0))
+        if _opt.UNFUSED:
+            self.b.add_grad(dy.sum(axis=0))
+        else:
+            self.b._take_grad(dy.sum(axis=0))
         x = self._x
         dev = dy._gpu.gpu
         g = self.w.grad
         if g is not None and not _opt.UNFUSED:
             # `grad += dy^T x` in the GEMM epilogue: the accumulated float32 product is added to
-            # the old value with one rounding, exactly what add_grad's `+=` does to a temporary
+            # the old value with one rounding, exactly what add_grad's `+=` does to a temporary; a gradient
+            # still marked zero (Sequence._zero_grad) is simply overwritten
+            fresh, self.w._fresh = self.w._fresh, False
             g.job = dev.gemm(True, False, self.output_dim, self.input_dim, dy.shape[0],
-                             dy.buffer, x.buffer, g.buffer, None, _GEMM_ACCUMULATE)
+                             dy.buffer, x.buffer, g.buffer, None, 0 if fresh else _GEMM_ACCUMULATE)
             g._keep = [dy, x]
             return
         dW = Array(dy._gpu, shape=(self.output_dim, self.input_dim))

@@ -26,9 +26,9 @@ class Sequence:
         """`layer` is exactly the library's `cls` (a subclass may override forward / backward)."""
         return type(layer) is cls
 
-    def _forward(self, x: Array) -> Array:
+    def _forward(self, x: Array, upto: Optional[int] = None) -> Array:
         from .layers import Dense, ReLU
-        L = self.L
+        L = self.L if upto is None else self.L[:upto]
         i = 0
         while i < len(L):
             layer = L[i]
@@ -47,15 +47,56 @@ class Sequence:
             i += 1
         return x
 
+    def _forward_loss(self, x: Array, y: Array) -> Tuple[Array, Array]:
+        """``pred = forward(x); loss = self.loss(pred, y)`` of a training step.
+
+        A stock ``Softmax`` last layer under a stock ``CrossEntropyLoss`` runs as ONE launch
+        (``vkp_nn_softmax_ce_train``) that also produces the gradient with respect to the Softmax input --
+        the float32 operations of Softmax.forward (layers.py:297-300), nn_cross_entropy.comp:25,
+        nn_cross_entropy_backward.comp:25 with the 1/batch scale of losses.py:58-68 and Softmax.backward
+        (layers.py:320-323), in that order, bit-identical to the five launches it replaces; the modules are
+        left in the state their own calls would have produced.  ``_backward`` picks the gradient up."""
+        from .layers import Softmax
+        from .losses import CrossEntropyLoss, _chains
+        self._tail_dz = None
+        L, loss = self.L, self.loss
+        if (not _opt.UNFUSED and len(L) >= 2 and self._stock(L[-1], Softmax) and type(loss) is CrossEntropyLoss
+                and len(y.shape) == 2):
+            z = self._forward(x, upto=len(L) - 1)
+            if len(z.shape) == 2 and tuple(z.shape) == tuple(y.shape):
+                rows, cols = z.shape
+                p, Lij, dz = (Array(z._gpu, shape=z.shape) for _ in range(3))
+                scale = loss.scale_backward(z) if loss.scale_backward is not None else None
+                job = z._gpu.gpu.nn_softmax_ce_train(z.buffer, y.buffer, p.buffer, Lij.buffer, dz.buffer, rows, cols, scale)
+                for a in (p, Lij, dz):
+                    a.job = job
+                    a._keep = [z, y]
+                sm = L[-1]
+                sm._x, sm._y = z, p
+                loss._x, loss._y = p, y
+                with _chains():
+                    value = loss.reduce(Lij.sum(axis=1))
+                self._tail_dz = dz
+                return p, value
+            pred = L[-1](z)
+        else:
+            pred = self._forward(x)
+        return pred, loss(pred, y)
+
     def _backward(self):
         """Layers in reverse.  The reference also asks the FIRST layer for the gradient of the
         network input and drops it (models.py:46-53); a layer that can produce its parameter
         gradients alone (``_backward_params``) is spared that contraction."""
         from .layers import Dense, ReLU
-        dx = self.loss.grad()
         L = self.L
         first = L[0] if L else None
         i = len(L) - 1
+        dz, self._tail_dz = getattr(self, "_tail_dz", None), None
+        if dz is not None:          # loss.grad() and Softmax.backward already ran inside _forward_loss's launch
+            dx = dz
+            i -= 1
+        else:
+            dx = self.loss.grad()
         while i >= 0:
             layer = L[i]
             if layer is first and not _opt.UNFUSED and hasattr(layer, "_backward_params"):
@@ -68,6 +109,9 @@ class Sequence:
             else:
                 dx = layer.backward(dx)
             i -= 1
+        if not _opt.UNFUSED:        # parameters no layer wrote a gradient to: the deferred zero fill happens now
+            for p in self._known_parameters()[0]:
+                p._materialize_zero()
 
     def _known_parameters(self):
         """(parameters the one-launch zero_grad / update may own, the other layers).
@@ -99,13 +143,12 @@ class Sequence:
         params, rest = self._known_parameters()
         for layer in rest:
             layer.zero_grad()
-        # all gradients in one device fill (the reference zeroes each through its host view)
-        for i in range(0, len(params), 16):
-            part = [p.grad for p in params[i:i + 16]]
-            job = part[0]._gpu.gpu.fill_many([g.buffer for g in part], 0)
-            for g in part:
-                g.job = job
-                g._keep = []
+        # No launch at all: the gradients are marked "zero" and the first contribution of the backward pass
+        # that follows OVERWRITES instead of accumulating (0 + x = x in float32; the reference zeroes each
+        # gradient through its host view, parameters.py:81-86).  Whatever received nothing is filled at the
+        # end of `_backward`; any other access goes through Parameter.add_grad / zero_grad, which honour the mark.
+        for p in params:
+            p._fresh = True
 
     def _update(self):
         if _opt.UNFUSED:
@@ -137,8 +180,7 @@ class Sequence:
                 p.value._keep = [p.grad]
 
     def train(self, x: Array, y: Array) -> Tuple[Array, Array]:
-        pred = self._forward(x)
-        loss = self.loss(pred, y)
+        pred, loss = self._forward_loss(x, y)
         self._zero_grad()
         self._backward()
         self._update()

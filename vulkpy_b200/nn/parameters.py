@@ -29,21 +29,44 @@ class Parameter:
             self.grad = zeros(gpu, shape=shape)
             self.opt_state = (opt or Adam(gpu)).init_state(shape)
         self.R: Optional[Regularizer] = regularizer
+        # True: `grad` stands for zeros that were never written (Sequence's launch-free zero_grad); the next
+        # contribution overwrites.  Every public path below resolves the mark first.
+        self._fresh = False
 
     def is_trainable(self) -> bool:
         return self.grad is not None
 
+    def _materialize_zero(self):
+        if self._fresh:
+            self._fresh = False
+            if self.grad is not None:
+                self.grad[:] = 0.0
+
+    def _take_grad(self, grad: Array):
+        """``add_grad`` of a temporary nobody else holds: on a fresh gradient the temporary BECOMES the
+        gradient (0 + x = x), otherwise ``grad += temporary``."""
+        if self.grad is None:
+            return
+        if self._fresh and tuple(grad.shape) == tuple(self.grad.shape):
+            self._fresh = False
+            self.grad = grad
+            return
+        self.add_grad(grad)
+
     def add_grad(self, grad: Array):
         if self.grad is not None:
+            self._materialize_zero()
             self.grad += grad
 
     def zero_grad(self):
         """Device fill (the reference zeroes through the host view: parameters.py:81-86)."""
+        self._fresh = False
         if self.grad is not None:
             self.grad[:] = 0.0
 
     def update(self):
         if self.grad is not None:
+            self._materialize_zero()
             self.value += self.opt_state.grad2diff(self.grad)
 
     def regular_loss(self) -> Array:
