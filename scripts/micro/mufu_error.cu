@@ -20,7 +20,8 @@ __device__ double atomicMaxD(double* addr, double v) {
   return __longlong_as_double(old);
 }
 
-// out[0..7]: max |r_fast - r| for om in (2^-(b+1), 2^-b] b=0 (0.5,1], 1, 2, 3.., out[8]: om > 1-2^-5, out[9]: om in (0.5, 1-2^-5]
+// out[0..7]: max |r_fast - r| for om in (2^-(b+1), 2^-b] b=0 (0.5,1], 1, 2, 3.., out[8]: om > 1-2^-5, out[9]: om in (0.5, 1-2^-5],
+// out[11]: om in (0.5, 1-2^-10] (the range the lg2 path serves since the series threshold moved to u0 < 2^-10)
 __global__ void log_err(double* out, double* lg_abs) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x + 1;
   if (k > (1u << 23)) return;
@@ -37,6 +38,7 @@ __global__ void log_err(double* out, double* lg_abs) {
   while (t <= 0.5f && b < 7) { t *= 2.0f; b++; }
   if (b == 0) {
     atomicMaxD(out + (om > 0.96875f ? 8 : 9), e);
+    if (om <= 1.0f - 0.0009765625f) atomicMaxD(out + 11, e);
     atomicMaxD(lg_abs, fabs((double)l2 - log2((double)om)));
   }
   atomicMaxD(out + b, e);
@@ -44,16 +46,14 @@ __global__ void log_err(double* out, double* lg_abs) {
   if (b > 0) atomicMaxD(out + 10, e / rd);
 }
 
-// series branch: u0 < 2^-5
+// series branch: u0 < 2^-10 (vkp_math.cuh BM_SERIES_BELOW)
 __global__ void series_err(double* out) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;     // u0 = k 2^-23, k < 2^18
-  if (k >= (1u << 18)) return;
+  if (k >= (1u << 13)) return;                                   // u0 < 2^-10
   const float u = (float)k * 1.1920928955078125e-7f;
-  float p = fmaf(u, 0.4f, 0.5f);
-  p = fmaf(p, u, 0.6666667f);
-  p = fmaf(p, u, 1.0f);
+  float p = fmaf(u, 0.6666667f, 1.0f);
   p = fmaf(p, u, 2.0f);
-  const float L = p * u;                                         // 2 (u + u^2/2 + u^3/3 + u^4/4 + u^5/5)
+  const float L = p * u;                                         // 2 (u + u^2/2 + u^3/3)
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(L));
   const double rd = sqrt(-2.0 * log1p(-(double)u));
@@ -84,10 +84,11 @@ int main() {
   for (int b = 0; b < 8; b++) printf("r = sqrt(-2 ln om): om in (2^-%d, 2^-%d]%s  max abs err %.3e\n", b + 1, b, b == 7 ? " and below" : "", h[b]);
   printf("   om in (1-2^-5, 1]: %.3e   om in (0.5, 1-2^-5]: %.3e   max rel err for om <= 0.5: %.3e\n", h[8], h[9], h[10]);
   printf("   lg2.approx max abs err on (0.5, 1]: %.3e (2^-22 = 2.38e-7)\n", h[12]);
+  printf("   om in (0.5, 1-2^-10] (lg2 path as shipped): %.3e\n", h[11]);
   cudaMemset(d, 0, 16 * 8);
-  series_err<<<(1 << 18) / 256, 256>>>(d);
+  series_err<<<(1 << 13) / 256, 256>>>(d);
   cudaMemcpy(h, d, 16 * 8, cudaMemcpyDeviceToHost);
-  printf("series branch u0 < 2^-5: max abs err of r %.3e, max rel %.3e\n", h[0], h[1]);
+  printf("series branch u0 < 2^-10: max abs err of r %.3e, max rel %.3e\n", h[0], h[1]);
   cudaMemset(d, 0, 16 * 8);
   sincos_err<<<(1 << 23) / 256, 256>>>(d);
   cudaMemcpy(h, d, 16 * 8, cudaMemcpyDeviceToHost);

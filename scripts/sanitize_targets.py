@@ -45,6 +45,8 @@ elif target == "ew":
     gpu = vk.GPU(0)
     a_h, b_h = rs.uniform(0.5, 2, (257, 131)).astype(F), rs.uniform(-2, 2, (257, 131)).astype(F)
     a, b = vk.Array(gpu, data=a_h), vk.Array(gpu, data=b_h)
+    big = vk.Array(gpu, data=rs.uniform(0.5, 2, (1 << 15) + 4103).astype(F))
+    (big ** 2.7).wait()   # binomial-series kernel (shared-memory tables)
     for r in (a + b, a ** b, a ** 2.7, a.log(), b.exp(), a + vk.Array(gpu, data=b_h[0]), a.sum(axis=1), a.sum(),
               a.gather(vk.U32Array(gpu, data=rs.integers(0, a_h.size, 999, dtype=np.uint32)))):
         r.wait()

@@ -230,6 +230,33 @@ def test_pow_vs_oracle(gpu, rs):
     np.testing.assert_allclose(got, orc.binary("pow", x, y), rtol=1.2e-7)
 
 
+@pytest.mark.parametrize("s", [2.7, 0.5, -1.5, 3.0, 7.7, -7.75, 1 / 3, -0.25, 9.5])
+def test_pow_scalar_binomial_kernel(gpu, rs, s):
+    """a ** s on >= 2^15 elements takes the binomial-series kernel (ew_pows_kernel; |s| > 7.75 stays on the
+    general one): correctly rounded against float64 like the oracle, over the whole positive range, with
+    zeros / negatives / subnormals / inf / nan sprinkled in (their vectors re-run through pow_f), ragged
+    sizes (partial tile + n % 4 tail) and in place (pow_scalar.comp:25, ipow_scalar.comp)."""
+    for n in (1 << 15, (1 << 16) + 4099, (1 << 17) + 1):
+        x = np.concatenate([rs.uniform(0.5, 2.0, n // 2), np.exp(rs.uniform(-80, 80, n - n // 2))]).astype(F)
+        x[rs.integers(0, n, 64)] = rs.choice(F([0.0, -0.0, -1.5, -2.0, 1e-40, np.inf, np.nan, 1.0]), 64)
+        want = orc.scalar("pow", x, s)
+        got = np.asarray(A(gpu, x) ** s)
+        np.testing.assert_allclose(got, want, rtol=1.2e-7, equal_nan=True)
+        assert (got != want).mean() < 1e-3                    # both are <= 0.5001 ulp: they differ on near-ties only
+        b = A(gpu, x)
+        b **= s
+        np.testing.assert_array_equal(np.asarray(b), got)
+
+
+def test_pow_scalar_kernels_agree(gpu, rs):
+    """below 2^15 elements the general table kernel runs; both kernels round the same values"""
+    x = rs.uniform(0.1, 10.0, 1 << 15).astype(F)
+    big = np.asarray(A(gpu, x) ** 2.7)
+    small = np.concatenate([np.asarray(A(gpu, x[i:i + 4096]) ** 2.7) for i in range(0, x.size, 4096)])
+    assert (big != small).mean() < 1e-3
+    np.testing.assert_allclose(big, small, rtol=1.2e-7)
+
+
 # ------------------------------------------------------------------------- clamp
 def test_clamp_family(gpu):
     x = [1, 2, 3]

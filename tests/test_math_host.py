@@ -22,6 +22,16 @@ void f_exp2(const float* x, float* y, long n){ vkpm::HostTables t; for(long i=0;
 void f_log(const float* x, float* y, long n){ vkpm::HostTables t; for(long i=0;i<n;i++) y[i]=vkpm::log_fast(x[i],t); }
 void f_log2(const float* x, float* y, long n){ vkpm::HostTables t; for(long i=0;i<n;i++) y[i]=vkpm::log2_fast(x[i],t); }
 void f_pow(const float* x, const float* y, float* z, long n){ vkpm::HostTables t; for(long i=0;i<n;i++) z[i]=vkpm::pow_fast(x[i],y[i],t); }
+int p_plan(float s){ vkpm::PowsCoef c; return vkpm::pows_plan(s, c); }
+void p_pows(const float* x, float s, float* z, long n){
+  vkpm::PowsCoef c; const int D = vkpm::pows_plan(s, c);
+  vkpm::PowsHostTables t(s, c);
+  for(long i=0;i<n;i++){
+    const uint32_t u = vkpm::f2bits(x[i]);
+    if (D == 0 || !((u - 0x00800000u) < 0x7f000000u)) { z[i] = vkpm::pow_f(x[i], s); continue; }
+    z[i] = D == 6 ? vkpm::pows_core<6>(u, t) : D == 8 ? vkpm::pows_core<8>(u, t) : vkpm::pows_core<10>(u, t);
+  }
+}
 void f_sincos(const float* x, float* s, float* c, long n){ for(long i=0;i<n;i++) vkpm::sincos_small(x[i], s[i], c[i]); }
 void f_asinh(const float* x, float* y, long n){ for(long i=0;i<n;i++) y[i]=vkpm::asinh_f(x[i]); }
 void f_bm_log(const float* x, float* y, long n){ for(long i=0;i<n;i++) y[i]=vkpm::bm_log(x[i]); }
@@ -226,3 +236,35 @@ def test_asinh(hm):
     assert np.all(np.signbit(got) == np.signbit(x))
     sp = call1(hm, "f_asinh", [np.inf, -np.inf, np.nan])
     assert sp[0] == np.inf and sp[1] == -np.inf and np.isnan(sp[2])
+
+
+@pytest.mark.parametrize("s", [2.7, 0.5, -1.5, 3.0, 7.7, -7.75, 1 / 3, 1e-3, -0.25, 5.5, 1.0, 0.0, 6.3])
+def test_pow_scalar_binomial(hm, s):
+    """pows_core (the a ** s kernel for a launch-constant s): 2^(s e) * rc^-s * binomial series, <= 0.5001 ulp
+    over the whole positive normal range; overflow -> inf, underflow -> 0 come out of the final conversion."""
+    rs = np.random.default_rng(11)
+    n = 400_000
+    x = np.concatenate([rs.uniform(0.5, 2, n), np.exp(rs.uniform(-87, 88, n)), 1 + rs.uniform(-1e-2, 1e-2, n),
+                        rs.uniform(0.9, 1.4, n)]).astype(np.float32)
+    s32 = np.float32(s)
+    hm.p_plan.argtypes = [C.c_float]
+    assert hm.p_plan(s32) in (6, 8, 10)
+    z = np.empty_like(x)
+    hm.p_pows(C.c_void_p(x.ctypes.data), C.c_float(s32), C.c_void_p(z.ctypes.data), C.c_long(x.size))
+    with np.errstate(all="ignore"):
+        ex = np.power(x.astype(np.float64), np.float64(s32))
+    ok = np.isfinite(ex) & (np.abs(ex) > 1.2e-38) & (np.abs(ex) < 3.4e38)
+    assert ulps(z[ok], ex[ok]).max() <= 0.5001
+    assert np.all(np.isinf(z[ex > 3.5e38])) and np.all(z[ex < 1.1e-38] == 0)
+    # the reference's own points (SURVEY Appendix A) and exact cases
+    if s == 2.7:
+        z3 = np.empty(3, np.float32)
+        x3 = np.float32([1, 2, 3])
+        hm.p_pows(C.c_void_p(x3.ctypes.data), C.c_float(s32), C.c_void_p(z3.ctypes.data), C.c_long(3))
+        assert bits(z3) == ["0x3f800000", "0x40cfefc6", "0x419b5a2a"]
+
+
+def test_pow_scalar_binomial_plan(hm):
+    hm.p_plan.argtypes = [C.c_float]
+    assert hm.p_plan(2.7) == 6 and hm.p_plan(7.7) == 8
+    assert hm.p_plan(8.0) == 0 and hm.p_plan(float("nan")) == 0 and hm.p_plan(float("inf")) == 0

@@ -332,6 +332,159 @@ int launch_ew_tab(vkp_ctx* ctx, const char* name, F f, const void* in0, const vo
   return VKP_OK;
 }
 
+// ---- a ** s with a launch-constant exponent: binomial-series kernel (vkp_math.cuh, pows_core) ----------
+// Tables (rc_i^-s x 32, 2^(s e) x 256) are built on the device once per distinct s (pows_build_kernel,
+// cached per device: same stream, so a rebuild is ordered after the last reader).  rc_i and rc_i^-s live one
+// entry per lane (lookups are shuffles: every lane of a warp evaluates together), 2^(s e) in shared memory.
+constexpr int POWS_SLOTS = 4;
+constexpr size_t POWS_TAB_DOUBLES = 32 + 256;
+constexpr size_t POWS_MIN_N = (size_t)1 << 15;   // below: the general kernel (one launch, no tables)
+
+struct PowsLaneTables {
+  const char* es_;           // shared memory, 256 doubles
+  uint32_t rc_;              // high word of this lane's rc entry (the low word is zero)
+  double cs_;                // this lane's rc^-s
+  const vkpm::PowsCoef& c;
+  __device__ double rc(uint32_t d) const { return __hiloint2double((int)vkpt::LaneTables::shfl5(rc_, d >> 18), 0); }
+  __device__ double cs(uint32_t d) const {
+    return __hiloint2double((int)vkpt::LaneTables::shfl5((uint32_t)__double2hiint(cs_), d >> 18),
+                            (int)vkpt::LaneTables::shfl5((uint32_t)__double2loint(cs_), d >> 18));
+  }
+  __device__ double es(uint32_t d) const { return *reinterpret_cast<const double*>(es_ + ((d >> 20) & 0x7f8u)); }
+  __device__ double b(int k) const { return c.b[k]; }
+};
+
+__global__ void pows_build_kernel(double* tab, float s) {
+  const uint32_t t = threadIdx.x;             // 256 threads
+  const double sd = (double)s;
+  if (t < 32) tab[t] = pow(vkpt::g_tab_rc[t], -sd);
+  tab[32 + t] = exp2(sd * (double)vkpm::pows_slot_exponent(t));   // s e is exact in binary64
+}
+
+__device__ __noinline__ float4 pows_slow4(float4 a, float s) {
+  return make_float4(vkpm::pow_f(a.x, s), vkpm::pow_f(a.y, s), vkpm::pow_f(a.z, s), vkpm::pow_f(a.w, s));
+}
+__device__ __noinline__ float pows_slow1(float x, float s) { return vkpm::pow_f(x, s); }
+
+// all lanes of a warp call this together (shuffles); vectors with a zero / subnormal / negative / inf / nan
+// element are re-evaluated with pow_f afterwards (rare)
+template <int D>
+__device__ __forceinline__ float4 pows_eval4(const PowsLaneTables& t, float s, float4 a) {
+  const uint32_t u0 = __float_as_uint(a.x), u1 = __float_as_uint(a.y), u2 = __float_as_uint(a.z),
+                 u3 = __float_as_uint(a.w);
+  const uint32_t umin = min(min(u0, u1), min(u2, u3)), umax = max(max(u0, u1), max(u2, u3));
+  float4 r = make_float4(vkpm::pows_core<D>(u0, t), vkpm::pows_core<D>(u1, t), vkpm::pows_core<D>(u2, t),
+                         vkpm::pows_core<D>(u3, t));
+  if ((umin < 0x00800000u) | (umax >= 0x7f800000u)) r = pows_slow4(a, s);
+  return r;
+}
+
+template <int D, bool FULL>
+__global__ void __launch_bounds__(EW_BLOCK)
+ew_pows_kernel(const double* __restrict__ tab, const __grid_constant__ vkpm::PowsCoef coef, float s,
+               const float* in0, float* out, size_t n, size_t first_tile) {
+  __shared__ __align__(16) double s_es[256];
+  const size_t nvec = n >> 2;
+  const float4* v0 = reinterpret_cast<const float4*>(in0);
+  float4* vo = reinterpret_cast<float4*>(out);
+  const size_t base = (first_tile + blockIdx.x) * EW_TILE_VEC + threadIdx.x;
+  const double cs_lane = tab[threadIdx.x & 31];
+  double2 tv = make_double2(0.0, 0.0);
+  if (threadIdx.x < 128) tv = reinterpret_cast<const double2*>(tab + 32)[threadIdx.x];
+  float4 a[EW_UNROLL];
+#pragma unroll
+  for (int u = 0; u < EW_UNROLL; u++) {
+    const size_t i = base + (size_t)u * EW_BLOCK;
+    if (FULL || i < nvec) a[u] = v0[i];
+    else a[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  if (threadIdx.x < 128) reinterpret_cast<double2*>(s_es)[threadIdx.x] = tv;
+  __syncthreads();
+  vkpm::PowsCoef c;
+#pragma unroll
+  for (int k = 0; k <= D; k++) c.b[k] = vkpt::pin(coef.b[k]);
+  const PowsLaneTables t{reinterpret_cast<const char*>(s_es),
+                         (uint32_t)__double2hiint(vkpt::g_tab_rc[threadIdx.x & 31]), cs_lane, c};
+#pragma unroll
+  for (int u = 0; u < EW_UNROLL; u++) {
+    const size_t i = base + (size_t)u * EW_BLOCK;
+    const float4 r = pows_eval4<D>(t, s, a[u]);
+    if (FULL || i < nvec) vo[i] = r;
+  }
+  if (!FULL && threadIdx.x < 32) {   // n % 4 tail, whole first warp participates
+    const size_t i = (nvec << 2) + threadIdx.x;
+    const float x = i < n ? in0[i] : 1.f;
+    const uint32_t u = __float_as_uint(x);
+    float r = vkpm::pows_core<D>(u, t);
+    if (!((u - 0x00800000u) < 0x7f000000u)) r = pows_slow1(x, s);
+    if (i < n) out[i] = r;
+  }
+}
+
+struct PowsCache {
+  double* tab[POWS_SLOTS] = {};
+  uint32_t key[POWS_SLOTS] = {};
+  uint64_t stamp[POWS_SLOTS] = {};
+  uint64_t clock = 0;
+};
+std::mutex g_pows_mu;
+PowsCache g_pows[64];   // per device (one context = one stream per device)
+
+template <int D>
+int launch_pows_d(vkp_ctx* ctx, const double* tab, const vkpm::PowsCoef& coef, float s, const void* in0, void* out,
+                  size_t n) {
+  const size_t nvec = n >> 2;
+  const size_t full_tiles = nvec / EW_TILE_VEC;
+  if (full_tiles) {
+    ew_pows_kernel<D, true><<<(unsigned)full_tiles, EW_BLOCK, 0, ctx->stream>>>(tab, coef, s, (const float*)in0,
+                                                                                (float*)out, n, 0);
+    VKP_TRY(vkp_after_launch(ctx, "pow_scalar"));
+  }
+  if (full_tiles * EW_TILE_VEC * 4 < n) {
+    ew_pows_kernel<D, false><<<1, EW_BLOCK, 0, ctx->stream>>>(tab, coef, s, (const float*)in0, (float*)out, n,
+                                                              full_tiles);
+    VKP_TRY(vkp_after_launch(ctx, "pow_scalar"));
+  }
+  return VKP_OK;
+}
+
+// returns VKP_OK and sets *done when the binomial kernel took the operation
+int launch_pows(vkp_ctx* ctx, float s, const void* in0, void* out, size_t n, bool* done) {
+  *done = false;
+  static const bool off = getenv("VKP_POWS_BINOMIAL") && atoi(getenv("VKP_POWS_BINOMIAL")) == 0;
+  if (off || n < POWS_MIN_N) return VKP_OK;
+  vkpm::PowsCoef coef;
+  const int D = vkpm::pows_plan(s, coef);
+  if (!D) return VKP_OK;
+  uint32_t key;
+  memcpy(&key, &s, 4);
+  const double* tab = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_pows_mu);
+    PowsCache& pc = g_pows[ctx->device & 63];
+    int slot = -1, lru = 0;
+    for (int i = 0; i < POWS_SLOTS; i++) {
+      if (pc.tab[i] && pc.key[i] == key) slot = i;
+      if (pc.stamp[i] < pc.stamp[lru]) lru = i;
+    }
+    if (slot < 0) {
+      slot = lru;
+      if (!pc.tab[slot]) VKP_CUDA(cudaMalloc(&pc.tab[slot], POWS_TAB_DOUBLES * sizeof(double)));
+      pows_build_kernel<<<1, 256, 0, ctx->stream>>>(pc.tab[slot], s);
+      VKP_TRY(vkp_after_launch(ctx, "pow_scalar(tables)"));
+      pc.key[slot] = key;
+    }
+    pc.stamp[slot] = ++pc.clock;
+    tab = pc.tab[slot];
+  }
+  *done = true;
+  switch (D) {
+    case 6: return launch_pows_d<6>(ctx, tab, coef, s, in0, out, n);
+    case 8: return launch_pows_d<8>(ctx, tab, coef, s, in0, out, n);
+    default: return launch_pows_d<10>(ctx, tab, coef, s, in0, out, n);
+  }
+}
+
 // ---- fused element-wise chains (lazy element-wise fusion) -------------------
 // A chain is what the reference issues as a sequence of same-shape element-wise jobs whose
 // intermediate arrays nobody else reads, e.g. Sigmoid.forward (nn/layers.py:239-243):
@@ -560,6 +713,11 @@ int dispatch_scalar(vkp_ctx* ctx, int sub, float s, const void* a, void* out, si
       // x ** 2.0 (MSELoss, Ridge, Adam, AdaGrad: nn/losses.py:294-296, nn/optimizers.py:131,239) is the
       // exactly rounded square, also on ties and for negative x
       if (s == 2.0f) return launch_ew<1>(ctx, "pow_scalar(2)", USquare(), a, nullptr, nullptr, out, n);
+      {
+        bool done = false;
+        VKP_TRY(launch_pows(ctx, s, a, out, n, &done));
+        if (done) return VKP_OK;
+      }
       return launch_ew_tab<1>(ctx, "pow_scalar", TPowScalarV{s}, a, nullptr, out, n);
     case VKB_RSUB: return launch_scalar<FSub>(ctx, "rsub_scalar", true, s, a, out, n);
     case VKB_RDIV: return launch_scalar<FDiv>(ctx, "rdiv_scalar", true, s, a, out, n);

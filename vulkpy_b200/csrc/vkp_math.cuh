@@ -432,6 +432,91 @@ VKP_HD float pow_core_nc(float x, double yd, const TA& ta, int& k_out) {
 #endif
 }
 
+// =============================================================================================
+// a ** s for a LAUNCH-CONSTANT exponent s (pow_scalar.comp:25): no logarithm, no exponential.
+//   x = 2^e m, m in [2/3, 4/3), interval i and rc_i exactly as in log2_tab (r = m rc_i - 1 exact,
+//   |r| <= 0.0209):
+//       x^s = 2^(s e) * rc_i^(-s) * (1 + r)^s
+//   2^(s e): 256-entry table indexed by the low byte of e;  rc_i^(-s): 32-entry table;  (1 + r)^s: the
+//   binomial series sum_k C(s, k) r^k cut at degree D (host picks D = 6 / 8 / 10 so that the tail is
+//   below 2^-42; s = 2.7 needs 6).  9 binary64 operations per element at D = 6 (pow_core: 17), two
+//   conversions, no range test besides "x is a positive normal float": the tables are binary64, so
+//   2^(s e) cannot overflow for |s| <= 7.75 and the final conversion produces inf / flushes by itself.
+//   Relative error before the final rounding < 2^-41  ->  <= 0.5001 ulp, same contract as pow_core.
+// A first version with 128 intervals (D = 4, 7 binary64 operations, tables in shared memory) halved the
+// instruction count but ran no faster than pow_core: 6.3 shared-memory wavefronts per warp of elements
+// (random 16-byte table reads conflict) kept that pipe 82 % busy (profiles/r02_ncu_rows_v3.md).  With 32
+// intervals rc_i and rc_i^(-s) live one entry per lane and a lookup is a shuffle (3 wavefronts); only
+// 2^(s e) stays in shared memory, where neighbouring elements mostly share their exponent (broadcast).
+// Tables depend on s: built on the device by pows_build_kernel (vkp_elementwise.cu) or on the host
+// (PowsHostTables, tests) with the same formulas; coefficients C(s, k) come from pows_plan.
+// =============================================================================================
+struct PowsCoef {
+  double b[11];   // b[k] = C(s, k); b[0] = 1
+};
+
+// exponent e of x = 2^e m for the table slot jb = e & 255 (e runs over -126 .. 128)
+VKP_HD int pows_slot_exponent(uint32_t jb) { return jb <= 128u ? (int)jb : (int)jb - 256; }
+
+// Host: pick the series degree for exponent s (0: this path does not apply) and fill the coefficients.
+inline int pows_plan(float s, PowsCoef& c) {
+  if (!(std::fabs(s) <= 7.75f)) return 0;                  // also nan; keeps |s e| < 1000
+  static double rmax = 0.0;
+  if (rmax == 0.0) {
+    static const double rc[32] = {VKPM_TABLE_RC};
+    double m = 0.0;
+    for (uint32_t i = 0; i < 32; i++) {
+      const uint32_t first = 0x3f2aaaabu + (i << 18);
+      m = std::fmax(m, std::fabs((double)bits2f(first) * rc[i] - 1.0));
+      m = std::fmax(m, std::fabs((double)bits2f(first + 0x3ffffu) * rc[i] - 1.0));
+    }
+    rmax = m;
+  }
+  long double bk[21];
+  bk[0] = 1.0L;
+  for (int k = 1; k <= 20; k++) bk[k] = bk[k - 1] * ((long double)s - (k - 1)) / k;
+  for (int k = 0; k <= 10; k++) c.b[k] = (double)bk[k];
+  for (int D = 6; D <= 10; D += 2) {
+    long double tail = 0.0L, rk = 1.0L;
+    for (int k = 1; k <= 20; k++) {
+      rk *= rmax;
+      if (k > D) tail += std::fabs(bk[k]) * rk;
+    }
+    if (tail < 0x1p-42L) return D;
+  }
+  return 0;
+}
+struct PowsHostTables {
+  double rc_[32], cs_[32], es_[256];
+  PowsCoef c_;
+  explicit PowsHostTables(float s, const PowsCoef& c) : c_(c) {
+    static const double rc[32] = {VKPM_TABLE_RC};
+    for (uint32_t i = 0; i < 32; i++) {
+      rc_[i] = rc[i];
+      cs_[i] = std::pow(rc[i], -(double)s);
+    }
+    for (uint32_t j = 0; j < 256; j++) es_[j] = std::exp2((double)s * pows_slot_exponent(j));
+  }
+  double rc(uint32_t d) const { return rc_[(d >> 18) & 31u]; }
+  double cs(uint32_t d) const { return cs_[(d >> 18) & 31u]; }
+  double es(uint32_t d) const { return es_[(d >> 23) & 255u]; }
+  double b(int k) const { return c_.b[k]; }
+};
+
+// u = bits of a positive NORMAL finite float.  Accessors take d = u - bits(2/3) and pick their bit field.
+template <int D, class PT>
+VKP_HD float pows_core(uint32_t u, const PT& t) {
+  const uint32_t d = u - 0x3f2aaaabu;
+  const uint32_t mb = u - (d & 0xff800000u);                // float bits of m = x / 2^e
+  const double md = (double)bits2f(mb);
+  const double r = dfma(md, t.rc(d), -1.0);                 // exact
+  double p = t.b(D);
+#pragma unroll
+  for (int k = D - 1; k >= 1; k--) p = dfma(p, r, t.b(k));
+  p = dfma(p, r, 1.0);
+  return d2f_ftz((p * t.cs(d)) * t.es(d));
+}
+
 // convenience wrappers (host tests, single-element callers)
 template <class TA>
 VKP_HD float exp_fast(float x, const TA& ta) {
@@ -582,26 +667,46 @@ VKP_HD void box_muller_core(float om, float u1, float mean, float stddev, float&
 // a Vulkan driver compiles GLSL log / sqrt / sin / cos to the hardware approximations (lg2 * ln2, sqrt.approx,
 // sin.approx / cos.approx), whose error the Vulkan spec allows to be far larger (sin / cos: 2^-11 absolute) than
 // what is measured here over EVERY input the generator can produce (scripts/micro/mufu_error.cu, numbers in
-// DESIGN.md).  lg2.approx has only ABSOLUTE accuracy near 1, so for u0 = 1 - om < 2^-5 the logarithm is the
-// series 2 (u + u^2/2 + u^3/3 + u^4/4 + u^5/5) instead (truncation < 2^-26 relative).
+// DESIGN.md).  lg2.approx has only ABSOLUTE accuracy near 1 (measured 2^-22), i.e. an error of 3.3e-7 / (2 r)
+// in r = sqrt(L): below u0 = 1 - om = 2^-10 (r < 0.044, error > 3.7e-6) the logarithm is the series
+// 2 u (1 + u/2 + u^2/3) instead (truncation < 2^-31 relative).  One lane in 1024 needs it, so callers test it
+// once per group of pairs (bm_fast_L + bm_fast_fix) and the series stays off the common path.
+// stddev = 1, mean = 0 (the default call) skips the multiply and the add: x * 1 and 0 + x are exact; only a
+// result of -0 (u0 = 0, sin < 0) comes out as -0 where the three-operation form gives +0.
+constexpr float BM_SERIES_BELOW = 0.0009765625f;   // 2^-10
+VKP_HD float bm_fast_series(float u0) {
+  float p = ffma(u0, 0.6666667f, 1.0f);
+  p = ffma(p, u0, 2.0f);
+  return p * u0;
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ float bm_fast_L(float om) {      // -2 ln(om) >= 0 through lg2.approx
+  float l2;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(om));
+  return l2 * -1.3862943611198906f;
+}
+template <bool UNIT>
+__device__ __forceinline__ void bm_fast_finish(float L, float u1, float mean, float stddev, float& o0, float& o1) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(L));
+  const float angle = 6.28318530718f * u1;
+  if (UNIT) {
+    o0 = r * __sinf(angle);
+    o1 = r * __cosf(angle);
+  } else {
+    r *= stddev;
+    o0 = mean + r * __sinf(angle);
+    o1 = mean + r * __cosf(angle);
+  }
+}
+#endif
 VKP_HD void box_muller_fast(float om, float u1, float mean, float stddev, float& o0, float& o1) {
 #if defined(__CUDA_ARCH__)
-  float l2, r;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(om));
-  float L = l2 * -1.3862943611198906f;                 // -2 ln(om) >= 0
   const float u0 = 1.0f - om;                          // exact
-  if (u0 < 0.03125f) {
-    float p = ffma(u0, 0.4f, 0.5f);
-    p = ffma(p, u0, 0.6666667f);
-    p = ffma(p, u0, 1.0f);
-    p = ffma(p, u0, 2.0f);
-    L = p * u0;
-  }
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(L));
-  r *= stddev;
-  const float angle = 6.28318530718f * u1;
-  o0 = mean + r * __sinf(angle);
-  o1 = mean + r * __cosf(angle);
+  float L = bm_fast_L(om);
+  if (u0 < BM_SERIES_BELOW) L = bm_fast_series(u0);
+  if (mean == 0.0f && stddev == 1.0f) bm_fast_finish<true>(L, u1, mean, stddev, o0, o1);
+  else bm_fast_finish<false>(L, u1, mean, stddev, o0, o1);
 #else
   box_muller_core(om, u1, mean, stddev, o0, o1);
 #endif

@@ -234,7 +234,7 @@ xoshiro_stream_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ st
 // Fused uniform -> Box-Muller (random.py:60-124 + prng_box_muller.comp:19-32): a thread owns the
 // lane pair (l0, l0+1), whose draws are the adjacent outputs (2i, 2i+1); the uniforms never leave
 // registers.  n_draw = n rounded up to even (the reference draws n+1 uniforms for odd n).
-template <bool FAST>
+template <bool FAST, bool UNIT>
 __global__ void __launch_bounds__(128)
 xoshiro_normal_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ state_out, float* __restrict__ out,
                       const uint4* __restrict__ jump, uint32_t size, uint64_t n_draw, uint64_t n_out,
@@ -275,6 +275,31 @@ xoshiro_normal_kernel(const uint4* __restrict__ state_in, uint4* __restrict__ st
   // for an odd request the very last pair stores one value only; it is some thread's final emit
   const bool half_last = (n_out & 1) && rem == 0 && iters > 0 && e1 == full && l0 == size - 2;
   if (half_last) iters--;
+  if (FAST) {
+    // four pairs per trip: the logarithm's series (one lane in 1024, see vkpm::box_muller_fast) is tested once
+    // per trip through the minimum of the four u0, so the common path carries no series instructions
+    for (; iters >= 4; iters -= 4) {
+      float om[4], u1[4], L[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        om[k] = 2.0f - __uint_as_float((next_dev(s0) >> 9) | 0x3f800000u);
+        u1[k] = u2f01(next_dev(s1));
+        L[k] = vkpm::bm_fast_L(om[k]);
+      }
+      if (fmaxf(fmaxf(om[0], om[1]), fmaxf(om[2], om[3])) > 1.0f - vkpm::BM_SERIES_BELOW) {
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (1.0f - om[k] < vkpm::BM_SERIES_BELOW) L[k] = vkpm::bm_fast_series(1.0f - om[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        float o0, o1;
+        vkpm::bm_fast_finish<UNIT>(L[k], u1[k], mean, stddev, o0, o1);
+        __stcs(reinterpret_cast<float2*>(o), make_float2(o0, o1));
+        o += size;
+      }
+    }
+  }
   while (iters > 0) {
     const uint32_t batch = iters > 0x40000000ull ? 0x40000000u : (uint32_t)iters;
     for (uint32_t i = 0; i < batch; i++) {
@@ -442,11 +467,14 @@ static int rng_generate(vkp_rng* rng, void* out, uint64_t n_out, float mean, flo
       // VKP_NORMAL_PRECISE=1: log / sqrt / sin / cos as <= 2 ulp float32 routines instead of the special-function
       // unit (see vkpm::box_muller_fast); read per call so a test can flip it
       if (vkp_normal_precise())
-        xoshiro_normal_kernel<false><<<grid, 128, 0, ctx->stream>>>(sin_, sout, (float*)out, rng->jump, size, n_draw,
-                                                                    n_out, log2L, nseg, mean, stddev);
+        xoshiro_normal_kernel<false, false><<<grid, 128, 0, ctx->stream>>>(sin_, sout, (float*)out, rng->jump, size,
+                                                                           n_draw, n_out, log2L, nseg, mean, stddev);
+      else if (mean == 0.0f && stddev == 1.0f)
+        xoshiro_normal_kernel<true, true><<<grid, 128, 0, ctx->stream>>>(sin_, sout, (float*)out, rng->jump, size,
+                                                                         n_draw, n_out, log2L, nseg, mean, stddev);
       else
-        xoshiro_normal_kernel<true><<<grid, 128, 0, ctx->stream>>>(sin_, sout, (float*)out, rng->jump, size, n_draw,
-                                                                   n_out, log2L, nseg, mean, stddev);
+        xoshiro_normal_kernel<true, false><<<grid, 128, 0, ctx->stream>>>(sin_, sout, (float*)out, rng->jump, size,
+                                                                          n_draw, n_out, log2L, nseg, mean, stddev);
     }
     else if (lpt == 4) { LAUNCH(4); }
     else if (lpt == 2) { LAUNCH(2); }
