@@ -167,3 +167,30 @@ def test_he_normal_initializer(gpu):
     ref = vk.random.Xoshiro128pp(gpu, seed=3).normal(shape=(4, 8), stddev=np.sqrt(2 / 8))
     np.testing.assert_array_equal(np.asarray(w), np.asarray(ref))
     np.testing.assert_allclose(np.asarray(nn.Constant(0.25)(gpu, (3, 2))), np.full((3, 2), 0.25))
+
+
+@pytest.mark.parametrize("size", [64, 6, 1 << 12])
+def test_advance_folds_into_the_next_draw(gpu, size):
+    """vkp_rng_advance by whole chunks is lazy: consecutive skips merge and the next draw folds them into its own
+    jump-ahead.  Every combination must equal drawing-and-discarding on the oracle (bit-exact), including draws
+    shorter than one chunk (lanes that draw nothing still skip), the normal kernel, a partial-chunk advance after a
+    pending one, and reading the state while a skip is pending."""
+    seed = 31
+    o = orc.Xoshiro128pp(size, seed)
+    r = vk.random.Xoshiro128pp(gpu, size, seed=seed)
+    r.rng.advance(3 * size); o.randint(3 * size)
+    r.rng.advance(5 * size); o.randint(5 * size)
+    np.testing.assert_array_equal(np.asarray(r.randint(shape=(size * 300 + 7,))), o.randint(size * 300 + 7))
+    r.rng.advance(2 * size); o.randint(2 * size)
+    short = max(1, size // 2 - 1)
+    np.testing.assert_array_equal(np.asarray(r.random(shape=(short,))), o.random(short))      # most lanes draw nothing
+    r.rng.advance(7 * size); o.randint(7 * size)
+    np.testing.assert_array_equal(r.rng.state(), o.state)                                            # flushes the skip
+    r.rng.advance(4 * size); o.randint(4 * size)
+    r.rng.advance(size + 3); o.randint(size + 3)                                                 # partial chunk: eager
+    np.testing.assert_array_equal(np.asarray(r.randint(shape=(5 * size,))), o.randint(5 * size))
+    if size % 2 == 0:
+        r.rng.advance(9 * size); o.randint(9 * size)
+        np.testing.assert_allclose(np.asarray(r.normal(shape=(size * 40,))), o.normal(size * 40), rtol=0, atol=NORMAL_FAST_ATOL)
+        np.testing.assert_array_equal(np.asarray(r.randint(shape=(size,))), o.randint(size))
+    np.testing.assert_array_equal(r.rng.state(), o.state)
