@@ -51,7 +51,7 @@ BYTES_PER_ELEM = sum(b for _, b in OPS)
 # op -> kernel-name fragment in the committed ncu capture of this step (profiles/*ncu_elementwise*.csv)
 NCU_KERNEL = {"a+b": "ew_kernel<2, FAdd>", "a*b": "ew_kernel<2, FMul>", "c+=b": "ew_kernel<2, FAdd>",
               "a*2.5": "ew_kernel<1, FScalar<FMul", "a+row": "bcast_vec_kernel<BAdd", "a*col": "bcast_vec_kernel<BMul",
-              "sin(b)": "USin", "exp(b)": "TExp", "a**b": "TPow>", "a**2.7": "TPowScalar", "clamp_ss": "CClampSS",
+              "sin(b)": "USin", "exp(b)": "TExp", "a**b": "<2, TPow", "a**2.7": "ew_pows_kernel", "clamp_ss": "CClampSS",
               "clamp_vv": "CClampVV"}
 
 

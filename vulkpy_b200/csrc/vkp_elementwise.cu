@@ -252,7 +252,10 @@ __device__ __forceinline__ float4 tab_eval4(const F& f, const LaneTables& tab, f
 }
 
 // FULL: CTA `blockIdx.x` owns one whole tile -- no bounds test anywhere, all loads issued before the first
-// use.  (One kernel with a CTA-uniform "whole tile?" branch compiled to predicated loads and a serialised
+// use.  (Tried in round 2: a software-pipelined persistent form -- resident CTAs walking over half-tiles with the
+// next half-tile's loads in flight during the evaluation -- because ncu shows the pow kernel's warps mostly on
+// the long scoreboard: +1.5 % for a**b at 32 CTAs per SM, -2 ... -25 % for the single-input kernels that already
+// run at the HBM rate, profiles/r02_tab_pipe.txt.  Not kept.)  (One kernel with a CTA-uniform "whole tile?" branch compiled to predicated loads and a serialised
 // evaluation: 0.58 ms against 0.48 ms for a**2.7 on 2^28 elements, scripts/micro/pow_variants.cu.)
 // !FULL: ONE CTA for what is left after the whole tiles: the partial tile, predicated, plus the n % 4 tail.
 template <int NIN, class F, bool FULL>
