@@ -873,7 +873,7 @@ def main():
            "d2h_bytes_per_step": int(out_h.nbytes), "ms_per_step": round(e2e_ms, 2),
            "path": "Array.from_host(pinned) x2 + Array(data=) x2 -> 12 ops -> Array.to_host(pinned, wait=False); "
                    "steps software-pipelined over the two copy engines"}
-    if world > 1:
+    if True:
         # the host bound beside it: the bare pinned transfers of one step (2 GiB in, 1 GiB out, both copy
         # engines at once) on all ranks together, no kernels
         def copies_only(steps):

@@ -229,7 +229,7 @@ __device__ __noinline__ float4 redo_slow(const F f, float4 a, float4 b) {
 }
 
 // minimum resident CTAs per SM (register cap): the two-input pow kernel is fastest at 48 registers
-// (profiles/r02_pow_variants.txt: 82 -> 48 registers, 5623 -> 5860 GB/s), the others are left to the compiler
+// (profiles/r02_pow_variants.txt: 84 -> 48 registers, 5610 -> 5830 GB/s), the others are left to the compiler
 template <class F> struct TabMinBlocks { static constexpr int v = 1; };
 template <> struct TabMinBlocks<TPow> { static constexpr int v = 5; };
 

@@ -556,7 +556,7 @@ static int rng_generate(vkp_rng* rng, void* out, uint64_t n_out, float mean, flo
     const uint64_t draws_per_lane = (n_draw + size - 1) / size;
     // segment length: power of two, >= 256 draws, giving about sms * 1024 threads (VKP_PRNG_THREADS_PER_SM)
     static const uint64_t tps = getenv("VKP_PRNG_THREADS_PER_SM") ? (uint64_t)atoll(getenv("VKP_PRNG_THREADS_PER_SM")) : 1024;
-    // streaming stores: +3-4 % at both lane counts (profiles/r02_prng_variants.txt); VKP_PRNG_STCS=0 for A/B
+    // streaming stores: +3-4 % at both lane counts (profiles/r02_prng_variants_v3.txt); VKP_PRNG_STCS=0 for A/B
     static const bool cs = !(getenv("VKP_PRNG_STCS") && getenv("VKP_PRNG_STCS")[0] == '0');
     uint64_t want_seg = ((uint64_t)ctx->sms * tps + groups - 1) / groups;
     if (want_seg < 1) want_seg = 1;
