@@ -194,3 +194,22 @@ def test_advance_folds_into_the_next_draw(gpu, size):
         np.testing.assert_allclose(np.asarray(r.normal(shape=(size * 40,))), o.normal(size * 40), rtol=0, atol=NORMAL_FAST_ATOL)
         np.testing.assert_array_equal(np.asarray(r.randint(shape=(size,))), o.randint(size))
     np.testing.assert_array_equal(r.rng.state(), o.state)
+
+
+@pytest.mark.parametrize("size,segs,extra", [(64, 71, 5), (6, 100, 3), (64, 129, 0), (10, 65, 7), (4096, 9, 100)])
+def test_segment_start_states_prepass(gpu, size, segs, extra):
+    """Requests that cut a lane's stream into >= 8 segments take the start-state pre-pass (xoshiro_starts_kernel:
+    coarse blocks of 64 segments + fine doubling inside them).  Ragged cases: a partial last coarse block, lane
+    counts below one CTA's 8 lanes, 65 / 129 segments (one past a power of two), a pending skip folded into entry 0,
+    uint32 / float / normal kernels -- all bit-exact (normal: tolerance) against the oracle, state included."""
+    seed = 5
+    n = size * (256 * (segs - 1) + 17) + extra
+    o = orc.Xoshiro128pp(size, seed)
+    r = vk.random.Xoshiro128pp(gpu, size, seed=seed)
+    np.testing.assert_array_equal(np.asarray(r.randint(shape=(n,))), o.randint(n))
+    r.rng.advance(3 * size); o.randint(3 * size)                      # pending skip -> entry 0 of the pre-pass
+    np.testing.assert_array_equal(np.asarray(r.random(shape=(n,))), o.random(n))
+    if size % 2 == 0:
+        m = n - (n % 2)
+        np.testing.assert_allclose(np.asarray(r.normal(shape=(m,))), o.normal(m), rtol=0, atol=NORMAL_FAST_ATOL)
+    np.testing.assert_array_equal(r.rng.state(), o.state)
