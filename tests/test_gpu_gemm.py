@@ -188,3 +188,19 @@ def test_fused_relu_epilogues_equal_separate_kernels(gpu, rs):
         sep = vk.Array(gpu, shape=(M, N))
         sep.job = gpu.gpu.nn_activation_backward(0, Y.buffer, nob.buffer, sep.buffer)
         np.testing.assert_array_equal(np.asarray(C).view(np.uint32), np.asarray(sep).view(np.uint32))
+
+
+@pytest.mark.parametrize("M,N,K,tb", [(2048, 8192, 512, True), (2048, 8192 + 64, 256, True), (1024, 8192, 256, True)])
+def test_tc_bn224_tile(gpu, M, N, K, tb):
+    """Shapes whose 128x256 tiling wastes most of a wave take 128x224 tiles (vkp_gemm_tc.cu prefer_bn224): 37 column
+    tiles of which the last is ragged (TMA zero fill + masked epilogue), TMEM allocation rounded up to 512 columns,
+    UMMA N = 224.  K-major B (the pre-split NT form Dense.forward and the row-sharded matmul use), bias + ReLU epilogue."""
+    rs = np.random.default_rng(M + N)
+    a = rs.uniform(-1, 1, (M, K)).astype(F)
+    b = rs.uniform(-1, 1, (N, K) if tb else (K, N)).astype(F)
+    want, mag = exact(a, b, False, tb)
+    got = gemm(gpu, a, b, tb=tb, flags=TC)
+    assert (np.abs(got - want) / mag).max() < TOL
+    bias = rs.uniform(-1, 1, N).astype(F)
+    got = gemm(gpu, a, b, tb=tb, bias=bias, flags=TC)
+    assert (np.abs(got - (want + bias)) / (mag + np.abs(bias))).max() < TOL

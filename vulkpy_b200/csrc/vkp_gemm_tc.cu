@@ -227,7 +227,7 @@ struct Cfg {
   static constexpr int B_TILE_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // hi + lo of A and B
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;                 // BN=256: 2 (BK=32) / 4 (BK=16)
-  static constexpr int TMEM_COLS = 2 * BN;                                  // two accumulators
+  static constexpr int TMEM_COLS = 2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512));   // two accumulators; allocations are powers of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -727,6 +727,19 @@ int launch_tc(vkp_ctx* ctx, const float* A, const float* Bt, const float* Alo, c
   return VKP_OK;
 }
 
+// 128x224 instead of 128x256 tiles when that saves whole waves: 1024 x 8192 outputs (a rank's rows of the
+// fixed-size 8192^3 product on 8 GPUs) are 256 tiles = 1.73 waves of 148 CTAs -> 2, but 8 x 37 = 296 tiles of
+// 224 columns = exactly 2 waves that are 12.5 % shorter (the last column tile is ragged: TMA zero-fills, the
+// epilogue masks).  VKP_TC_BN224=0 keeps 256.
+static bool prefer_bn224(const vkp_ctx* ctx, uint32_t M, uint32_t N) {
+  static const bool off = getenv("VKP_TC_BN224") && getenv("VKP_TC_BN224")[0] == '0';
+  if (off || N < 1024) return false;
+  const uint64_t mt = (M + BM - 1) / BM, sms = (uint64_t)ctx->sms;
+  const uint64_t t256 = mt * ((N + 255) / 256), t224 = mt * ((N + 223) / 224);
+  const uint64_t c256 = (t256 + sms - 1) / sms * 256, c224 = (t224 + sms - 1) / sms * 224;
+  return c224 * 100 <= c256 * 90;    // at least 10 % fewer column-steps: a 224-wide tile runs ~5 % below a 256-wide one per column (profiles/r02_bn224.txt)
+}
+
 }  // namespace
 
 int vkp_gemm_tc_supported(int transA, int transB, uint32_t M, uint32_t N, uint32_t K, const float* A,
@@ -818,6 +831,7 @@ int vkp_gemm_tc(vkp_ctx* ctx, int transA, int transB, uint32_t M, uint32_t N, ui
     int rc;
     const int am = a_mn ? mn_mode : 0, bm = b_mn ? mn_mode : 0;
     if (N <= 32) rc = launch_tc<32, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm, post);
+    else if (wide && bk16 && !bm && prefer_bn224(ctx, M, N)) rc = launch_tc<224, 16>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm, post);
     else if (wide && bk16) rc = launch_tc<256, 16>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm, post);
     else if (wide) rc = launch_tc<256, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm, post);
     else rc = launch_tc<128, 32>(ctx, Ak, Bk, Alo, Blo, C, bias, M, N, K, accumulate, no_chunks, nullptr, am, bm, post);
@@ -845,6 +859,7 @@ int vkp_gemm_tc_chunked(vkp_ctx* ctx, uint32_t M, uint32_t N, uint32_t K, const 
                         const float* Bt, const float* Btlo, float* C, vkp_tc_chunks ch, const vkp_tc_pull* pull) {
   VKP_CHECK(ch.n_chunks >= 1 && K % ch.n_chunks == 0 && (K / ch.n_chunks) % 32 == 0,
             "vkp_gemm_tc_chunked: K = %u does not split into %u ranges of whole k-blocks", K, ch.n_chunks);
+  if (prefer_bn224(ctx, M, N)) return launch_tc<224, 16>(ctx, A, Bt, Alo, Btlo, C, nullptr, M, N, K, 0, ch, pull);
   if (N % 256 == 0 || N >= 1024) return launch_tc<256, 16>(ctx, A, Bt, Alo, Btlo, C, nullptr, M, N, K, 0, ch, pull);
   return launch_tc<128, 32>(ctx, A, Bt, Alo, Btlo, C, nullptr, M, N, K, 0, ch, pull);
 }
