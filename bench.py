@@ -650,12 +650,13 @@ def sharded_block(B):
     r = row("matmul 8192^3 row-sharded (fixed size), peers' B pulled inside one tcgen05 GEMM", lambda: A @ Bm,
             lambda: A1 @ B1, 2 * M ** 3 / 1e9, "TFLOP/s aggregate", weak=False, min_ms=40.0)
     nv1 = nvlink_bytes(B.local_rank)
-    tiles = (M // world // 128) * (M // 256) if (M // world) % 128 == 0 else None
-    if tiles:
-        waves = tiles / 148.0
-        r["limiter"] = (f"wave quantisation: {M // world} local rows x {M} columns = {tiles} tiles of 128x256 on 148 SMs = "
-                        f"{waves:.2f} waves -> {math.ceil(waves)} (ideal {r.get('ms_one_gpu_whole_problem', 0) / world:.3f} ms "
-                        f"x {math.ceil(waves) / waves:.2f}) + transpose/split pre-pass of the local shard + barrier")
+    pull_bytes = 4 * M * M * (world - 1) / world
+    r["limiter"] = (f"NVLink pull rate: every rank pulls {pull_bytes / 1e6:.0f} MB of B through the kernel's four spare warps per CTA "
+                    f"while it multiplies; {pull_bytes / r['ms'] / 1e6:.0f} GB/s sustained over the call.  The same staging + GEMM with "
+                    "nothing crossing NVLink (VKP_COMM_NO_PULL=1, timing only) takes 0.51 ms on 8 GPUs against 0.73-0.77 ms with the "
+                    "pulls (profiles/r02_mm_fused_probe_n8.txt); 8 -> 16 loads in flight per pulling thread bought 4 %, the 128x224 "
+                    "tile (2 waves of 224 instead of 2 of 256 columns for 1024 x 8192 outputs) 5 % without the pulls and nothing "
+                    f"with them.  Ideal = one GPU's {r.get('ms_one_gpu_whole_problem', 0):.3f} ms / {world}")
     if nv0 and nv1:
         r["nvlink_rx_bytes_per_call_counter"] = None     # the counters move with every rank's calls; reported raw below
         r["nvlink_counter_delta_bytes"] = {"tx": nv1[0] - nv0[0], "rx": nv1[1] - nv0[1]}

@@ -71,7 +71,9 @@ VKP_API int vkp_download(vkp_ctx* ctx, void* dst_host, const void* src, size_t b
  * `dst`, operations bound to `dst` wait for the upload; the download sees everything enqueued
  * before it, later operations bound to `src` wait for it.  `*job` completes with the transfer
  * (the source of an upload may be rewritten / the destination of a download read after that).
- * vkp_alloc_for_upload prefers a cached block no enqueued work can still touch.  The reference
+ * vkp_alloc_for_upload prefers a cached block no enqueued work can still touch and, when every cached
+ * block is still in the compute stream's future, takes a fresh one (while the pool is below half of the
+ * device memory) so that the upload never waits for compute.  The reference
  * has no counterpart: Buffer::set (_vkarray.cc:98-108) is a blocking memcpy into mapped memory. */
 VKP_API int vkp_alloc_for_upload(vkp_ctx* ctx, size_t bytes, void** ptr);
 VKP_API int vkp_upload_async(vkp_ctx* ctx, void* dst, const void* src_pinned, size_t bytes, vkp_job** job);
@@ -226,7 +228,9 @@ VKP_API int vkp_rng_float(vkp_rng* rng, float* out, uint32_t n, vkp_job** job);
 VKP_API int vkp_rng_normal(vkp_rng* rng, float* out, uint32_t n, float mean, float stddev, vkp_job** job);
 VKP_API int vkp_rng_state(vkp_rng* rng, uint32_t* host_out /* 4*size words */);
 /* discard n draws exactly as vkp_rng_uint32(n) would consume them (GF(2) jump-ahead): lets every rank
- * of a sharded generator start at its own chunk of the single-GPU stream */
+ * of a sharded generator start at its own chunk of the single-GPU stream.  Whole multiples of the lane
+ * count are recorded and applied lazily: consecutive skips merge and the next draw folds them into its
+ * own jump-ahead (vkp_rng_state applies a pending skip first) */
 VKP_API int vkp_rng_advance(vkp_rng* rng, uint64_t n);
 
 /* ---- timing on the context stream (bench only) ------------------------------------ */

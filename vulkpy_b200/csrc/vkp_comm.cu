@@ -796,6 +796,13 @@ extern "C" int vkp_comm_matmul_allgather(vkp_ctx* ctx, uint32_t M, uint32_t N, u
     pl.src[r] = reinterpret_cast<const float*>(static_cast<const char*>(st->peer[r]) + copy_off);
   pl.hi = bt_hi; pl.lo = bt_lo; pl.counters = st->flags + VKP_MAX_RANKS;
   pl.rows = N; pl.ld = K; pl.kc = kc;
+  // VKP_COMM_NO_PULL=1 (timing diagnostic only, WRONG results): the same GEMM over the staging matrix as it is,
+  // no K ranges, no pulls -- what the kernel costs when nothing has to cross NVLink
+  static const bool no_pull = getenv("VKP_COMM_NO_PULL") != nullptr;
+  if (no_pull) {
+    VKP_TRY(vkp_gemm_tc_chunked(ctx, M, N, K, A, a_lo, bt_hi, bt_lo, C, vkp_tc_chunks{nullptr, 0, 0, 0, 1}, nullptr));
+    return vkp_finish_op(ctx, job);
+  }
   VKP_TRY(vkp_gemm_tc_chunked(ctx, M, N, K, A, a_lo, bt_hi, bt_lo, C, ch, &pl));
   return vkp_finish_op(ctx, job);
 }

@@ -137,7 +137,7 @@ __device__ __forceinline__ uint32_t tf32_lo_bits(uint32_t xb) {
 // the mapped peer pointers, 8 in flight per thread, store hi and lo locally, then count the CTA
 // in; the last one publishes the range to every producer warp (release / acquire on the flag).
 __device__ __forceinline__ void pull_ranges(const vkp_tc_pull& pl, const vkp_tc_chunks& ch, int tid) {
-  constexpr int U = 8, PT = 128;
+  constexpr int U = 16, PT = 128;   // 16 loads in flight per thread: with 8 the pulls sustained ~320 GB/s and the fixed-size product on 8 GPUs was pull-bound (0.77 ms against 0.51 ms for the same GEMM with nothing crossing NVLink, profiles/r02_mm_fused_probe_n8.txt)
   const uint32_t c4 = pl.kc / 4;
   const size_t n4 = (size_t)pl.rows * c4;
   const size_t stride = (size_t)gridDim.x * PT;
